@@ -1,0 +1,142 @@
+/*
+ * asvgf.h -- C ABI of the B200-native A-SVGF denoiser (libasvgf.so).
+ *
+ * Drop-in boundary: the pass sequence that RTGL1 records in
+ *     RTGL1::Denoiser::Denoise( VkCommandBuffer, uint32_t frameIndex, shared_ptr<const GlobalUniform> )
+ *                                                           (Source/Denoiser.h:45-47, Source/Denoiser.cpp:64-255)
+ * plus the image-space half of
+ *     RTGL1::PathTracer::CalculateGradientsSamples( const TraceParams& )            (Source/PathTracer.cpp:196-219)
+ *
+ * Mapping of the reference's interface onto this one
+ *     VkCommandBuffer cmd            -> a CUDA stream; calls only ENQUEUE work, like vkCmd* recording
+ *     descriptor set 0 (Framebuffers)-> the image table below, same indices (asvgf_layout.h), same cur/prev
+ *                                        swap by frameIndex (Source/Framebuffers.cpp:35-50)
+ *     descriptor set 1 (UBO)         -> const AsvgfGlobalUniform*, byte-compatible with ShGlobalUniform
+ *     VK_CHECKERROR / RgException    -> AsvgfResult return codes, never throws (Source/RTGL1.cpp:150-168)
+ *
+ * Images are linear, pitched device memory (row pitch a multiple of 256 B) in the reference's storage formats.
+ * A handle is not thread-safe; distinct handles are independent (one handle per view stream).
+ * There is NO CPU fallback: every entry point that computes fails with ASVGF_CUDA_ERROR when no device is usable.
+ */
+#ifndef ASVGF_H_
+#define ASVGF_H_
+
+#include "asvgf_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined( _WIN32 )
+    #define ASVGF_API __declspec( dllexport )
+#else
+    #define ASVGF_API __attribute__( ( visibility( "default" ) ) )
+#endif
+
+typedef struct AsvgfDenoiser_T* AsvgfDenoiser;
+typedef void*                   AsvgfStream; /* a cudaStream_t; NULL = the legacy default stream */
+
+/* RgResult-style (Include/RTGL1/RTGL1.h:79-94) */
+typedef enum AsvgfResult
+{
+    ASVGF_SUCCESS         = 0,
+    ASVGF_WRONG_ARGUMENT  = 1,
+    ASVGF_CUDA_ERROR      = 2,
+    ASVGF_OUT_OF_MEMORY   = 3,
+    ASVGF_UNSUPPORTED     = 4,
+    ASVGF_NOT_BOUND       = 5 /* a pass needs an image that is neither owned nor bound */
+} AsvgfResult;
+
+typedef enum AsvgfCreateFlagBits
+{
+    ASVGF_CREATE_EXPORT_DEBUG_MASK = 1u << 0, /* temporal pass also writes ASVGF_IMAGE_DEBUG_MASK               */
+    ASVGF_CREATE_EXTERNAL_IMAGES   = 1u << 1, /* allocate nothing: every image comes from asvgfBindExternalImage */
+    ASVGF_CREATE_NO_FUSION         = 1u << 2  /* one kernel per reference dispatch (used by per-pass parity tests)*/
+} AsvgfCreateFlagBits;
+
+/* = Denoiser ctor + Framebuffers::PrepareForSize (Source/Denoiser.cpp:24-55, Source/Framebuffers.cpp:216-230) */
+typedef struct AsvgfCreateInfo
+{
+    uint32_t renderWidth;      /* full frame, must be even (Source/VulkanDevice.cpp:186-187)                     */
+    uint32_t renderHeight;
+    uint32_t atrousIterations; /* 4 = the reference; 1..8 accepted (5 = BASELINE config 3, parity unpinned)      */
+    uint32_t flags;            /* AsvgfCreateFlagBits                                                            */
+    int32_t  device;           /* CUDA ordinal, -1 = the calling thread's current device                        */
+    /* Horizontal band owned by this handle, for one-process-per-GPU frame splitting.  bandRowEnd == 0 means the
+       whole frame.  Rows are full-resolution rows and must be multiples of 3 (strata do not straddle bands).
+       The handle stores rows [bandRowBegin-bandHaloRows, bandRowEnd+bandHaloRows) clipped to the frame; a pass
+       COMPUTES only the owned rows and READS halo rows, which the host fills (NCCL/P2P) before the pass. */
+    uint32_t bandRowBegin;
+    uint32_t bandRowEnd;
+    uint32_t bandHaloRows;     /* multiple of 3; >= 8*2^(atrousIterations-4) for the a-trous reach               */
+} AsvgfCreateInfo;
+
+/* Passes in the reference's dispatch order (Source/Denoiser.cpp:87-254, Source/PathTracer.cpp:212-218). */
+typedef enum AsvgfPass
+{
+    ASVGF_PASS_GRADIENT_SAMPLES  = 0,  /* RtGradients.rgen (image-space part)     */
+    ASVGF_PASS_GRADIENT_ATROUS_0 = 1,  /* CmASVGFGradientAtrous.comp, iteration 0 */
+    ASVGF_PASS_GRADIENT_ATROUS_1 = 2,
+    ASVGF_PASS_GRADIENT_ATROUS_2 = 3,
+    ASVGF_PASS_GRADIENT_ATROUS_3 = 4,
+    ASVGF_PASS_TEMPORAL          = 5,  /* CmSVGFTemporalAccumulation.comp         */
+    ASVGF_PASS_ANTIFIREFLY       = 6,  /* CmAntiFirefly.comp                      */
+    ASVGF_PASS_VARIANCE          = 7,  /* CmSVGFEstimateVariance.comp             */
+    ASVGF_PASS_ATROUS_0          = 8,  /* CmSVGFAtrous_Iter0.comp; ASVGF_PASS_ATROUS_0+i = CmSVGFAtrous.comp, i  */
+    ASVGF_PASS_COUNT             = 8 + ASVGF_MAX_ATROUS_ITERATIONS
+} AsvgfPass;
+
+ASVGF_API AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser );
+ASVGF_API AsvgfResult asvgfDestroy( AsvgfDenoiser denoiser );
+
+/* Size/format of an image of the table for a given frame size: (W,H) or ((W+1)/3,(H+1)/3) (Framebuffers.cpp:639-700).
+   Returns ASVGF_WRONG_ARGUMENT for indices the denoiser path does not use. */
+ASVGF_API AsvgfResult asvgfGetImageInfo( uint32_t imageIndex, uint32_t renderWidth, uint32_t renderHeight,
+                                         uint32_t* pFormat, uint32_t* pWidth, uint32_t* pHeight,
+                                         uint32_t* pBytesPerPixel );
+
+/* = Framebuffers::GetImage(fbImageIndex, frameIndex): applies the cur/prev swap.  *ppDevice addresses the first
+   STORED row, whose frame row number is *pFirstRow (0 unless banded); *pRows rows are stored. */
+ASVGF_API AsvgfResult asvgfGetImage( AsvgfDenoiser denoiser, uint32_t imageIndex, uint32_t frameIndex,
+                                     void** ppDevice, size_t* pPitchBytes, uint32_t* pWidth, uint32_t* pFirstRow,
+                                     uint32_t* pRows );
+
+/* Caller-owned storage for one PHYSICAL image (no swap applied: bind X and X_PREV separately).  pDevice addresses
+   the first stored row (same row range as asvgfGetImage reports).  Vulkan-CUDA interop is the caller's business. */
+ASVGF_API AsvgfResult asvgfBindExternalImage( AsvgfDenoiser denoiser, uint32_t imageIndex, void* pDevice,
+                                              size_t pitchBytes );
+
+/* Host <-> device copies of the stored rows of one image (swap applied), enqueued on `stream`.  The host buffer
+   holds the stored rows back to back with hostPitchBytes per row (0 = tightly packed). */
+ASVGF_API AsvgfResult asvgfUploadImage( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t imageIndex,
+                                        uint32_t frameIndex, const void* pHost, size_t hostPitchBytes );
+ASVGF_API AsvgfResult asvgfDownloadImage( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t imageIndex,
+                                          uint32_t frameIndex, void* pHost, size_t hostPitchBytes );
+/* Zero every owned image (= fresh images after a resolution change, Framebuffers.cpp:216-230). */
+ASVGF_API AsvgfResult asvgfResetHistory( AsvgfDenoiser denoiser, AsvgfStream stream );
+
+/* = PathTracer::CalculateGradientsSamples, image-space part (RtGradients.rgen:44-105,139-181); the ray-traced
+   re-shade is read from ASVGF_IMAGE_FWD_LUM.  Enqueues only. */
+ASVGF_API AsvgfResult asvgfGradientSamples( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                            const AsvgfGlobalUniform* pUniform );
+/* = Denoiser::Denoise.  Enqueues the whole chain (gradient a-trous x4, temporal, anti-firefly, variance,
+   a-trous x N with the composition in the last iteration) and returns immediately. */
+ASVGF_API AsvgfResult asvgfDenoise( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                    const AsvgfGlobalUniform* pUniform );
+/* One reference dispatch at a time (per-pass parity tests; banded multi-GPU runs interleave halo exchanges). */
+ASVGF_API AsvgfResult asvgfDenoisePass( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                        const AsvgfGlobalUniform* pUniform, uint32_t pass );
+
+/* Number of CUDA kernels this handle has launched since creation. */
+ASVGF_API uint64_t    asvgfGetLaunchCount( AsvgfDenoiser denoiser );
+/* Name of the kernel that implements a pass and its algorithmic HBM bytes per full-resolution pixel. */
+ASVGF_API const char* asvgfPassName( uint32_t pass );
+ASVGF_API double      asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations );
+ASVGF_API const char* asvgfResultString( AsvgfResult result );
+ASVGF_API const char* asvgfLastErrorMessage( void ); /* thread-local detail of the last failure */
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ASVGF_H_ */

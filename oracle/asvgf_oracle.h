@@ -1,0 +1,57 @@
+/*
+ * asvgf_oracle.h -- C API of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  The oracle is a scalar fp32 restatement of RTGL1's denoiser shaders
+ * (see asvgf_oracle.cpp for the file:line map).  It may be loaded only by tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs -- never by the product path (libasvgf.so), which has
+ * no CPU fallback.
+ *
+ * PARITY UNPINNED BY THE REFERENCE: RTGL1 ships no golden vectors, tests or prebuilt SPIR-V for this path and
+ * the shaders cannot be executed in the build container (no glslc / Vulkan loader / lavapipe), so the oracle is
+ * pinned only by (i) being a line-by-line restatement and (ii) the analytic known-answer tests in tests/.
+ */
+#ifndef ASVGF_ORACLE_H_
+#define ASVGF_ORACLE_H_
+
+#include "../include/asvgf_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct AsvgfOracle_T* AsvgfOracle;
+
+AsvgfOracle asvgfOracleCreate( uint32_t renderWidth, uint32_t renderHeight, uint32_t atrousIterations );
+void        asvgfOracleDestroy( AsvgfOracle o );
+void        asvgfOracleSetThreads( int threads ); /* <=0: all cores */
+int         asvgfOracleGetThreads( void );
+
+/* host pointer of an image, cur/prev swap applied (Framebuffers.cpp:35-50); rows are tightly packed */
+int asvgfOracleGetImage( AsvgfOracle o, uint32_t imageIndex, uint32_t frameIndex, void** ppHost, uint32_t* pWidth,
+                         uint32_t* pHeight, uint32_t* pBytesPerPixel );
+void asvgfOracleResetHistory( AsvgfOracle o );
+
+/* pass numbering = AsvgfPass of include/asvgf.h */
+void asvgfOracleRunPass( AsvgfOracle o, uint32_t pass, uint32_t frameIndex, const AsvgfGlobalUniform* u );
+void asvgfOracleGradientSamples( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
+void asvgfOracleDenoise( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
+
+/* helper primitives exposed for unit tests */
+uint32_t asvgfOracleEncodeE5B9G9R9( float r, float g, float b );
+void     asvgfOracleDecodeE5B9G9R9( uint32_t packed, float* rgb );
+uint32_t asvgfOracleEncodeNormal( float x, float y, float z );
+void     asvgfOracleDecodeNormal( uint32_t packed, float* xyz );
+uint16_t asvgfOracleFloatToHalf( float f );
+float    asvgfOracleHalfToFloat( uint16_t h );
+uint32_t asvgfOraclePackUfloat111110( float r, float g, float b );
+void     asvgfOracleUnpackUfloat111110( uint32_t packed, float* rgb );
+uint8_t  asvgfOracleFloatToUnorm8( float f );
+void     asvgfOracleCheckerboardPix( int x, int y, int fullWidth, int* outXY );          /* regular -> checkerboard */
+void     asvgfOracleRegularPix( int x, int y, int fullWidth, int* outXY );               /* checkerboard -> regular */
+void     asvgfOraclePrevScreenPos( float mx, float my, int x, int y, float renderWidth, float renderHeight,
+                                   float* outXY );
+
+#ifdef __cplusplus
+}
+#endif
+#endif
