@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- A-SVGF denoise throughput (Mpixel/s, ms/frame) on N B200s, with the HBM roofline of the dominant
+kernel and the CPU oracle timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 4k|4k-n5|1080p|720p]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one frame of the hot path: asvgfGradientSamples + the Denoiser::Denoise pass chain (gradient a-trous x4,
+temporal, anti-firefly, variance, a-trous xN with composition) over one synthetic G-buffer.
+  value : whole-job Mpixel/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e   : the same metric through the C ABI with HOST buffers: every step uploads that frame's producer images from
+          pinned host memory and reads PreFinal + HistogramInput back, copies inside the timed region
+  N > 1 : one process per GPU, each denoising its own independent view stream (weak scaling, no data-path collective)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, a-trous iterations, description)
+    "4k": (3840, 2160, 4, "3840x2160 synthetic G-buffer, full A-SVGF chain (gradient samples + gradient a-trous x4 + "
+                          "temporal + anti-firefly + variance + 4 a-trous iterations + composition), 1 view stream per GPU"),
+    "4k-n5": (3840, 2160, 5, "3840x2160 synthetic G-buffer, full chain with 5 a-trous iterations (BASELINE config 3)"),
+    "1080p": (1920, 1080, 4, "1920x1080 synthetic G-buffer, full chain, 4 a-trous iterations"),
+    "720p": (1280, 720, 4, "1280x720 synthetic G-buffer, full chain, 4 a-trous iterations"),
+}
+METRIC = "asvgf_denoise_throughput"
+UNIT = "Mpixel/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:  # noqa: BLE001
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+        for bit, name in names.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.sample()
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def run_reference(args, rank, world):
+    """The reference arm for this tier: the reference's CPU-side stand-in (the oracle, kind 'port' -- the GLSL
+    reference cannot be compiled or run here) on all host threads, each step a bounded band of the
+    same workload."""
+    if rank != 0:
+        return
+    import oracle
+    import synth
+    W, H, N, desc = WORKLOADS[args.workload]
+    oracle.set_threads(0)
+    cores = oracle.get_threads()
+    # calibrate on a small frame, then size the per-step band so that (steps+warmup) steps take about 100 s
+    cal_w, cal_h = 640, 360
+    o = oracle.Oracle(cal_w, cal_h, N)
+    g = synth.generate(cal_w, cal_h, 1)
+    for k, v in g.items():
+        o.image(k, 1)[...] = v
+    u = synth.uniform(cal_w, cal_h, 1)
+    o.gradient_samples(1, u); o.denoise(1, u)
+    t0 = time.perf_counter()
+    o.gradient_samples(1, u); o.denoise(1, u)
+    rate = cal_w * cal_h / (time.perf_counter() - t0)           # pixels per second
+    o.close()
+    budget_s = 100.0
+    rows = int(rate * budget_s / (args.steps + args.warmup) / W)
+    rows = max(36, min(H, rows - rows % 3))
+    o = oracle.Oracle(W, rows, N)
+    frames = []
+    for f in (0, 1):                                            # the top `rows` rows of two consecutive 4K-wide frames
+        frames.append((synth.generate(W, rows, f), synth.uniform(W, rows, f)))
+
+    def step(i):
+        fi = i & 1
+        g, u = frames[fi]
+        for k, v in g.items():
+            o.image(k, fi)[...] = v
+        o.gradient_samples(fi, u)
+        o.denoise(fi, u)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = W * rows * args.steps / dt / 1e6
+    sample = "%dx%d band (top rows of the %dx%d frame) per step, %d steps" % (W, rows, W, H, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "atrous_iterations": N, "reference_kind": "CPU oracle port of the GLSL shaders; "
+                   "the SPIR-V/lavapipe reference is unavailable in this image (no glslc, no Vulkan ICD)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(W, H, N, frames):
+    """Oracle (kind 'port') on all host cores over a bounded sample of the same workload: one warm-up frame and one
+    timed frame of the top band of the frame, sized from a quick calibration to about 10-20 s of CPU work."""
+    import oracle
+    oracle.set_threads(0)
+    cores = oracle.get_threads()
+    o = oracle.Oracle(640, 360, N)
+    import synth
+    g = synth.generate(640, 360, 1)
+    for k, v in g.items():
+        o.image(k, 1)[...] = v
+    u = synth.uniform(640, 360, 1)
+    o.gradient_samples(1, u); o.denoise(1, u)
+    t0 = time.perf_counter()
+    o.gradient_samples(1, u); o.denoise(1, u)
+    rate = 640 * 360 / (time.perf_counter() - t0)
+    o.close()
+    rows = int(rate * 7.0 / W)
+    rows = max(36, min(H, rows - rows % 3))
+    o = oracle.Oracle(W, rows, N)
+    t_tot = 0.0
+    for f in (0, 1):
+        g = synth.generate(W, rows, f)
+        u = synth.uniform(W, rows, f)
+        for k, v in g.items():
+            o.image(k, f)[...] = v
+        t0 = time.perf_counter()
+        o.gradient_samples(f, u)
+        o.denoise(f, u)
+        t_tot = time.perf_counter() - t0                 # keep the second (history present) frame
+    o.close()
+    return {"value": W * rows / t_tot / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 warm-up + 1 timed frame of a %dx%d band (top rows of the %dx%d frame)" % (W, rows, W, H)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    import synth
+    from raytracedgl1_b200 import denoiser as dn
+    from raytracedgl1_b200 import layout
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the A-SVGF path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    W, H, N, desc = WORKLOADS[args.workload]
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    d = dn.Denoiser(W, H, N, device=local_rank)
+
+    # two consecutive synthetic frames in pinned host memory (independent stream per rank: its own seed)
+    seed = synth.DEFAULT_SEED + rank
+    host = []
+    for f in (0, 1):
+        bufs = {}
+        for name in layout.PRODUCER_IMAGES:
+            dtype, shape = layout.image_numpy_shape(name, W, H)
+            t = torch.empty(int(np.prod(shape)) * dtype.itemsize, dtype=torch.uint8, pin_memory=True)
+            bufs[name] = t.numpy().view(dtype).reshape(shape)
+            bufs["_keep_" + name] = t
+        synth.generate(W, H, f, seed, out={k: v for k, v in bufs.items() if not k.startswith("_keep_")})
+        host.append((bufs, synth.uniform(W, H, f)))
+    h2d_bytes = sum(host[0][0][n].nbytes for n in layout.PRODUCER_IMAGES)
+    out_host = {}
+    for name in ("PreFinal", "HistogramInput"):
+        dtype, shape = layout.image_numpy_shape(name, W, H)
+        t = torch.empty(int(np.prod(shape)) * dtype.itemsize, dtype=torch.uint8, pin_memory=True)
+        out_host[name] = (t, t.numpy().view(dtype).reshape(shape))
+    d2h_bytes = sum(v[1].nbytes for v in out_host.values())
+
+    def upload(fi):
+        bufs, _ = host[fi]
+        for name in layout.PRODUCER_IMAGES:
+            d.upload(name, fi, bufs[name], stream=sh)
+
+    passes = list(range(0, layout.PASS_ATROUS_0 + N))
+
+    def step_resident(i, events=None):
+        fi = i & 1
+        u = host[fi][1]
+        for k, p in enumerate(passes):
+            if p == 0:
+                d.gradient_samples(fi, u, stream=sh)
+            else:
+                d.denoise_pass(p, fi, u, stream=sh)
+            if events is not None:
+                events[k + 1].record(stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: inputs of both frame slots already in HBM ----
+    upload(0); upload(1)
+    torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step_resident(i)
+    n_ev = len(passes) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = d.launch_count
+    sampler.start() if sampler.ok else None
+    for i in range(args.steps):
+        evs[i][0].record(stream)
+        step_resident(args.warmup + i, evs[i])
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = d.launch_count - launches0
+    barrier()
+    total_ms = evs[0][0].elapsed_time(evs[-1][-1])
+    pass_ms = [sum(evs[i][k].elapsed_time(evs[i][k + 1]) for i in range(args.steps)) / args.steps for k in range(len(passes))]
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        fi = i & 1
+        upload(fi); d.gradient_samples(fi, host[fi][1], stream=sh); d.denoise(fi, host[fi][1], stream=sh)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(e2e_steps):
+        fi = i & 1
+        upload(fi)
+        d.gradient_samples(fi, host[fi][1], stream=sh)
+        d.denoise(fi, host[fi][1], stream=sh)
+        for name, (t, arr) in out_host.items():
+            d.download(name, fi, stream=sh, out=arr.ctypes.data)
+        stream.synchronize()                                   # the caller consumes the frame's result
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+
+    # ---- max over ranks ----
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln)
+        launches = int(ln[0])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        value = world * W * H * args.steps / (total_ms * 1e-3) / 1e6
+        bpp = [dn.pass_bytes_per_pixel(p, N) for p in passes]
+        chain_bpp = sum(bpp)
+        per_pass = []
+        for k, p in enumerate(passes):
+            name = dn.lib().asvgfPassName(p).decode()
+            gbs = bpp[k] * W * H / (pass_ms[k] * 1e-3) / 1e9 if pass_ms[k] > 0 else 0.0
+            per_pass.append({"pass": p, "kernel": name, "ms": round(pass_ms[k], 5), "bytes_per_px": bpp[k],
+                             "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+        # dominant kernel = the kernel function with the largest share of the step
+        share = {}
+        for e in per_pass:
+            s = share.setdefault(e["kernel"], {"ms": 0.0, "bytes": 0.0, "launches": 0})
+            s["ms"] += e["ms"]; s["bytes"] += e["bytes_per_px"] * W * H; s["launches"] += 1
+        dom = max(share.items(), key=lambda kv: kv[1]["ms"])
+        dom_gbs = dom[1]["bytes"] / (dom[1]["ms"] * 1e-3) / 1e9
+        frame_ms = total_ms / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": W, "height": H, "atrous_iterations": N,
+                       "streams_per_gpu": 1, "parallelism": "independent view streams, 1 per GPU, no collective",
+                       "l2": "no flush: per-stream images total %.2f GB, each pass streams > 126 MB L2" % (201 * W * H / 1e9),
+                       "algorithmic_bytes_per_px": chain_bpp},
+            "clocks": clocks,
+            "e2e": {"value": world * W * H * e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom[0], "launches_per_step": dom[1]["launches"],
+                         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "chain": {"achieved": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9,
+                                   "frac": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9 / peak,
+                                   "frac_of_8000_nominal": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9 / 8000.0}},
+            "passes": per_pass,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(W, H, N, host)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    d.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,10 @@ ASVGF_API AsvgfResult asvgfDenoise( AsvgfDenoiser denoiser, AsvgfStream stream, 
 ASVGF_API AsvgfResult asvgfDenoisePass( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                         const AsvgfGlobalUniform* pUniform, uint32_t pass );
 
+/* Blocks the host until everything enqueued on `stream` has finished (= waiting for the frame fence,
+   Source/VulkanDevice.cpp:791-796).  Surfaces asynchronous kernel faults as ASVGF_CUDA_ERROR. */
+ASVGF_API AsvgfResult asvgfSynchronize( AsvgfDenoiser denoiser, AsvgfStream stream );
+
 /* Number of CUDA kernels this handle has launched since creation. */
 ASVGF_API uint64_t    asvgfGetLaunchCount( AsvgfDenoiser denoiser );
 /* Name of the kernel that implements a pass and its algorithmic HBM bytes per full-resolution pixel. */

@@ -1,0 +1,604 @@
+// asvgf.cu -- host side of libasvgf.so: the Framebuffers mirror (image table with the cur/prev swap), the
+// Denoiser mirror (stream launcher of the pass kernels) and the C ABI of include/asvgf.h.
+//
+// Reference: Source/Denoiser.cpp:64-255 (dispatch order, ping-pong routing), Source/Framebuffers.cpp:35-50
+// (FrameIndexToFBIndex), :639-700 (image extents), Source/PathTracer.cpp:196-219 (gradient samples dispatch).
+#include "../../include/asvgf.h"
+
+#include "asvgf_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace asvgf;
+
+namespace
+{
+
+thread_local std::string g_lastError;
+
+AsvgfResult fail( AsvgfResult r, const std::string& msg )
+{
+    g_lastError = msg;
+    return r;
+}
+AsvgfResult cudaFail( cudaError_t e, const char* what )
+{
+    return fail( e == cudaErrorMemoryAllocation ? ASVGF_OUT_OF_MEMORY : ASVGF_CUDA_ERROR, std::string( what ) + ": " + cudaGetErrorString( e ) );
+}
+#define CUDA_TRY( expr )                                         \
+    do                                                           \
+    {                                                            \
+        cudaError_t e_ = ( expr );                               \
+        if( e_ != cudaSuccess ) return cudaFail( e_, #expr );    \
+    } while( 0 )
+
+struct ImageDesc { uint32_t format, bpp; bool thirdRes; };
+
+bool describe( uint32_t i, ImageDesc* d )
+{
+    switch( i )
+    {
+        case ASVGF_IMAGE_IS_SKY: *d = { ASVGF_FORMAT_R8_UINT, 1, false }; return true;
+        case ASVGF_IMAGE_DEBUG_MASK: *d = { ASVGF_FORMAT_R8_UINT, 1, false }; return true;
+        case ASVGF_IMAGE_GRADIENT_PREV_PIX: *d = { ASVGF_FORMAT_R8_UINT, 1, true }; return true;
+        case ASVGF_IMAGE_METALLIC_ROUGHNESS: case ASVGF_IMAGE_METALLIC_ROUGHNESS_PREV: *d = { ASVGF_FORMAT_R8G8_UNORM, 2, false }; return true;
+        case ASVGF_IMAGE_DEPTH_WORLD: case ASVGF_IMAGE_DEPTH_WORLD_PREV: case ASVGF_IMAGE_DEPTH_GRAD:
+        case ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE: case ASVGF_IMAGE_HISTOGRAM_INPUT: *d = { ASVGF_FORMAT_R16_SFLOAT, 2, false }; return true;
+        case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV: case ASVGF_IMAGE_GRADIENT_INPUTS:
+        case ASVGF_IMAGE_GRADIENT_INPUTS_PREV: case ASVGF_IMAGE_FWD_LUM: *d = { ASVGF_FORMAT_R16G16_SFLOAT, 4, false }; return true;
+        case ASVGF_IMAGE_MOTION: case ASVGF_IMAGE_VIEW_DIRECTION: case ASVGF_IMAGE_THROUGHPUT: case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH:
+        case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV: case ASVGF_IMAGE_DIFF_COLOR_HISTORY: case ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE:
+        case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: *d = { ASVGF_FORMAT_R16G16B16A16_SFLOAT, 8, false }; return true;
+        case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: *d = { ASVGF_FORMAT_R32G32B32A32_SFLOAT, 16, false }; return true;
+        case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
+        case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR:
+        case ASVGF_IMAGE_UNFILTERED_INDIR: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR: case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV:
+        case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR: case ASVGF_IMAGE_SPEC_PONG_COLOR:
+        case ASVGF_IMAGE_INDIR_ACCUM: case ASVGF_IMAGE_INDIR_ACCUM_PREV: case ASVGF_IMAGE_INDIR_PING: case ASVGF_IMAGE_INDIR_PONG:
+            *d = { ASVGF_FORMAT_R32_UINT, 4, false }; return true;
+        case ASVGF_IMAGE_DIS_PING_GRADIENT: case ASVGF_IMAGE_DIS_PONG_GRADIENT: case ASVGF_IMAGE_DIS_GRADIENT_HISTORY:
+            *d = { ASVGF_FORMAT_R8G8B8A8_UNORM, 4, true }; return true;
+        default: return false;
+    }
+}
+
+// Framebuffers.cpp:35-50: 1 = "cur" of a swappable pair (physical = index + frameIndex), 2 = its _PREV twin
+int swapKind( uint32_t i )
+{
+    switch( i )
+    {
+        case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_METALLIC_ROUGHNESS: case ASVGF_IMAGE_DEPTH_WORLD: case ASVGF_IMAGE_SURFACE_POSITION:
+        case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH: case ASVGF_IMAGE_DIFF_ACCUM_COLOR: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS:
+        case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_INDIR_ACCUM: case ASVGF_IMAGE_GRADIENT_INPUTS: return 1;
+        case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_METALLIC_ROUGHNESS_PREV: case ASVGF_IMAGE_DEPTH_WORLD_PREV: case ASVGF_IMAGE_SURFACE_POSITION_PREV:
+        case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV: case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV:
+        case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_INDIR_ACCUM_PREV: case ASVGF_IMAGE_GRADIENT_INPUTS_PREV: return 2;
+        default: return 0;
+    }
+}
+
+// ---- normal-codec trig table, one per device, shared by all handles ----
+struct LutEntry { float2* phi = nullptr; float2* theta = nullptr; int refs = 0; };
+std::mutex g_lutMutex;
+LutEntry   g_lut[ 64 ];
+
+AsvgfResult acquireLut( int device, NormalLut* out )
+{
+    std::lock_guard< std::mutex > lock( g_lutMutex );
+    if( device < 0 || device >= 64 ) return fail( ASVGF_WRONG_ARGUMENT, "device ordinal out of range" );
+    LutEntry& e = g_lut[ device ];
+    if( e.refs == 0 )
+    {
+        // Utils.h:124-140: phi = j*pi/65535, theta = k*2*pi/65536 evaluated in fp32 as GLSL does, then sin/cos
+        // correctly rounded (double libm -> float), the same pin the oracle uses.
+        const float             PI_F = 3.14159265358979323846f;
+        std::vector< float2 > phi( 65536 ), theta( 65536 );
+        for( uint32_t j = 0; j < 65536; j++ )
+        {
+            const float p = ( float )j * PI_F / 65535.0f;
+            const float t = ( float )( j * 2u ) * PI_F / 65536.0f;
+            phi[ j ]      = make_float2( ( float )sin( ( double )p ), ( float )cos( ( double )p ) );
+            theta[ j ]    = make_float2( ( float )sin( ( double )t ), ( float )cos( ( double )t ) );
+        }
+        CUDA_TRY( cudaMalloc( &e.phi, 65536 * sizeof( float2 ) ) );
+        CUDA_TRY( cudaMalloc( &e.theta, 65536 * sizeof( float2 ) ) );
+        CUDA_TRY( cudaMemcpy( e.phi, phi.data(), 65536 * sizeof( float2 ), cudaMemcpyHostToDevice ) );
+        CUDA_TRY( cudaMemcpy( e.theta, theta.data(), 65536 * sizeof( float2 ), cudaMemcpyHostToDevice ) );
+    }
+    e.refs++;
+    out->phi   = e.phi;
+    out->theta = e.theta;
+    return ASVGF_SUCCESS;
+}
+void releaseLut( int device )
+{
+    std::lock_guard< std::mutex > lock( g_lutMutex );
+    LutEntry& e = g_lut[ device ];
+    if( e.refs > 0 && --e.refs == 0 )
+    {
+        cudaFree( e.phi ); cudaFree( e.theta );
+        e.phi = e.theta = nullptr;
+    }
+}
+
+struct DeviceGuard
+{
+    int  prev = -1;
+    bool ok   = false;
+    explicit DeviceGuard( int device )
+    {
+        if( cudaGetDevice( &prev ) != cudaSuccess ) return;
+        ok = prev == device || cudaSetDevice( device ) == cudaSuccess;
+    }
+    ~DeviceGuard() { if( ok && prev >= 0 ) { int cur = -1; cudaGetDevice( &cur ); if( cur != prev ) cudaSetDevice( prev ); } }
+};
+
+} // namespace
+
+struct AsvgfDenoiser_T
+{
+    AsvgfCreateInfo info{};
+    int             device = 0;
+    uint32_t        W = 0, H = 0, iterations = 4;
+    // stored rows of full-resolution and 1/3-resolution images; owned rows are what passes compute
+    int32_t   row0 = 0, rows = 0, ownBegin = 0, ownEnd = 0;
+    int32_t   grow0 = 0, grows = 0, gownBegin = 0, gownEnd = 0;
+    Img       img[ ASVGF_IMAGE_COUNT ]{};
+    bool      owned[ ASVGF_IMAGE_COUNT ]{};
+    NormalLut lut{};
+    bool      haveLut     = false;
+    uint64_t  launchCount = 0;
+
+    const Img& get( uint32_t index, uint32_t frameIndex ) const
+    {
+        const int k = swapKind( index );
+        return img[ k == 1 ? index + frameIndex : k == 2 ? index - frameIndex : index ];
+    }
+};
+
+namespace
+{
+
+Uniform makeUniform( const AsvgfDenoiser_T& d, const AsvgfGlobalUniform& g )
+{
+    Uniform u;
+    std::memcpy( u.view, g.view, 64 ); std::memcpy( u.viewPrev, g.viewPrev, 64 );
+    std::memcpy( u.projection, g.projection, 64 ); std::memcpy( u.projectionPrev, g.projectionPrev, 64 );
+    for( int i = 0; i < 3; i++ ) { u.cameraPosition[ i ] = g.cameraPosition[ i ]; u.cameraPositionPrev[ i ] = g.cameraPositionPrev[ i ]; }
+    u.renderWidth = g.renderWidth; u.renderHeight = g.renderHeight; u.timeDelta = g.timeDelta;
+    u.lightmapScreenCoverage = g.lightmapScreenCoverage;
+    u.gradientMult[ 0 ] = g.gradientMultDiffuse; u.gradientMult[ 1 ] = g.gradientMultIndirect; u.gradientMult[ 2 ] = g.gradientMultSpecular;
+    u.debugShowFlags = g.debugShowFlags; u.antiFireflyEnabled = g.antiFireflyEnabled;
+    u.W = ( int32_t )g.renderWidth; u.H = ( int32_t )g.renderHeight;
+    u.yBegin = d.ownBegin; u.yEnd = d.ownEnd;
+    return u;
+}
+
+dim3 gridFor( int w, int rows ) { return dim3( ( unsigned )( ( w + kBlockW - 1 ) / kBlockW ), ( unsigned )( ( rows + kBlockH - 1 ) / kBlockH ), 1 ); }
+const dim3 kBlock( kBlockW, kBlockH, 1 );
+
+AsvgfResult need( const AsvgfDenoiser_T& d, uint32_t frameIndex, std::initializer_list< uint32_t > indices )
+{
+    for( uint32_t i : indices )
+        if( d.get( i, frameIndex ).p == nullptr ) return fail( ASVGF_NOT_BOUND, "image " + std::to_string( i ) + " is neither owned nor bound" );
+    return ASVGF_SUCCESS;
+}
+#define NEED( ... )                                                        \
+    do                                                                     \
+    {                                                                      \
+        AsvgfResult r_ = need( d, fi, { __VA_ARGS__ } );                   \
+        if( r_ != ASVGF_SUCCESS ) return r_;                               \
+    } while( 0 )
+
+AsvgfResult launchCheck( AsvgfDenoiser_T& d, const char* name )
+{
+    d.launchCount++;
+    cudaError_t e = cudaGetLastError();
+    if( e != cudaSuccess ) return cudaFail( e, name );
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
+{
+    NEED( ASVGF_IMAGE_GRADIENT_PREV_PIX, ASVGF_IMAGE_DIS_PING_GRADIENT, ASVGF_IMAGE_DIS_GRADIENT_HISTORY, ASVGF_IMAGE_MOTION,
+          ASVGF_IMAGE_GRADIENT_INPUTS_PREV, ASVGF_IMAGE_IS_SKY, ASVGF_IMAGE_INDIR_ACCUM_PREV, ASVGF_IMAGE_FWD_LUM );
+    GradientSamplesArgs a;
+    a.gradientPrevPix = d.get( ASVGF_IMAGE_GRADIENT_PREV_PIX, fi ); a.disPing = d.get( ASVGF_IMAGE_DIS_PING_GRADIENT, fi );
+    a.disHistory = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi ); a.motion = d.get( ASVGF_IMAGE_MOTION, fi );
+    a.gradientInputsPrev = d.get( ASVGF_IMAGE_GRADIENT_INPUTS_PREV, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
+    a.indirAccumPrev = d.get( ASVGF_IMAGE_INDIR_ACCUM_PREV, fi ); a.fwdLum = d.get( ASVGF_IMAGE_FWD_LUM, fi );
+    a.gyBegin = d.gownBegin; a.gyEnd = d.gownEnd;
+    k_gradient_samples<<< gridFor( a.disPing.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_gradient_samples" );
+}
+
+AsvgfResult runGradientAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t iteration )
+{
+    NEED( ASVGF_IMAGE_DIS_PING_GRADIENT, ASVGF_IMAGE_DIS_PONG_GRADIENT, ASVGF_IMAGE_DIS_GRADIENT_HISTORY );
+    const bool         even = ( iteration % 2 ) == 0; // CmASVGFGradientAtrous.comp:89-104
+    GradientAtrousArgs a;
+    a.src = d.get( even ? ASVGF_IMAGE_DIS_PING_GRADIENT : ASVGF_IMAGE_DIS_PONG_GRADIENT, fi );
+    a.dst = d.get( even ? ASVGF_IMAGE_DIS_PONG_GRADIENT : ASVGF_IMAGE_DIS_PING_GRADIENT, fi );
+    a.history = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi );
+    a.iteration = ( int32_t )iteration; a.gyBegin = d.gownBegin; a.gyEnd = d.gownEnd;
+    k_gradient_atrous<<< gridFor( a.dst.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_gradient_atrous" );
+}
+
+AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
+{
+    NEED( ASVGF_IMAGE_UNFILTERED_DIRECT, ASVGF_IMAGE_UNFILTERED_INDIR, ASVGF_IMAGE_UNFILTERED_SPECULAR, ASVGF_IMAGE_VIEW_DIRECTION, ASVGF_IMAGE_MOTION,
+          ASVGF_IMAGE_DEPTH_WORLD, ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_METALLIC_ROUGHNESS, ASVGF_IMAGE_SURFACE_POSITION, ASVGF_IMAGE_DIS_PING_GRADIENT,
+          ASVGF_IMAGE_DEPTH_WORLD_PREV, ASVGF_IMAGE_NORMAL_PREV, ASVGF_IMAGE_DIFF_COLOR_HISTORY, ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV,
+          ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV, ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV, ASVGF_IMAGE_INDIR_ACCUM_PREV, ASVGF_IMAGE_SURFACE_POSITION_PREV,
+          ASVGF_IMAGE_DIFF_TEMPORARY, ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, ASVGF_IMAGE_SPEC_ACCUM_COLOR, ASVGF_IMAGE_INDIR_ACCUM );
+    TemporalArgs a;
+    a.unfDirect = d.get( ASVGF_IMAGE_UNFILTERED_DIRECT, fi ); a.unfIndir = d.get( ASVGF_IMAGE_UNFILTERED_INDIR, fi );
+    a.unfSpec = d.get( ASVGF_IMAGE_UNFILTERED_SPECULAR, fi ); a.viewDir = d.get( ASVGF_IMAGE_VIEW_DIRECTION, fi );
+    a.motion = d.get( ASVGF_IMAGE_MOTION, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi );
+    a.metRough = d.get( ASVGF_IMAGE_METALLIC_ROUGHNESS, fi ); a.surfPos = d.get( ASVGF_IMAGE_SURFACE_POSITION, fi );
+    a.disPing = d.get( ASVGF_IMAGE_DIS_PING_GRADIENT, fi );
+    a.depthPrev = d.get( ASVGF_IMAGE_DEPTH_WORLD_PREV, fi ); a.normalPrev = d.get( ASVGF_IMAGE_NORMAL_PREV, fi );
+    a.diffHistory = d.get( ASVGF_IMAGE_DIFF_COLOR_HISTORY, fi ); a.momentsPrev = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV, fi );
+    a.histLenPrev = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV, fi ); a.specPrev = d.get( ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV, fi );
+    a.indirPrev = d.get( ASVGF_IMAGE_INDIR_ACCUM_PREV, fi ); a.surfPosPrev = d.get( ASVGF_IMAGE_SURFACE_POSITION_PREV, fi );
+    a.outDiffTemporary = d.get( ASVGF_IMAGE_DIFF_TEMPORARY, fi ); a.outMoments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
+    a.outHistLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.outSpecAccum = d.get( ASVGF_IMAGE_SPEC_ACCUM_COLOR, fi );
+    a.outIndirAccum = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi ); a.outMask = d.get( ASVGF_IMAGE_DEBUG_MASK, fi );
+    a.lut = d.lut;
+    a.writeMask = ( ( d.info.flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) && a.outMask.p ) ? 1 : 0;
+    k_temporal<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_temporal" );
+}
+
+AsvgfResult runAntiFirefly( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
+{
+    NEED( ASVGF_IMAGE_DIFF_TEMPORARY, ASVGF_IMAGE_SPEC_ACCUM_COLOR, ASVGF_IMAGE_INDIR_ACCUM, ASVGF_IMAGE_DIFF_ACCUM_COLOR, ASVGF_IMAGE_SPEC_PING_COLOR,
+          ASVGF_IMAGE_INDIR_PING );
+    AntiFireflyArgs a;
+    a.src[ 0 ] = d.get( ASVGF_IMAGE_DIFF_TEMPORARY, fi ); a.src[ 1 ] = d.get( ASVGF_IMAGE_SPEC_ACCUM_COLOR, fi ); a.src[ 2 ] = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi );
+    a.dst[ 0 ] = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SPEC_PING_COLOR, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_INDIR_PING, fi );
+    k_antifirefly<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_antifirefly" );
+}
+
+AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
+{
+    NEED( ASVGF_IMAGE_DIFF_ACCUM_COLOR, ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_DEPTH_WORLD, ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, ASVGF_IMAGE_DIFF_ACCUM_MOMENTS,
+          ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE );
+    VarianceArgs a;
+    a.color = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
+    a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
+    a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
+    k_variance<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_variance" );
+}
+
+AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t iteration )
+{
+    if( iteration >= d.iterations ) return fail( ASVGF_WRONG_ARGUMENT, "a-trous iteration beyond atrousIterations" );
+    const bool last = iteration + 1 == d.iterations;
+    // routing: CmSVGFAtrous_Iter0.comp:312-334, CmSVGFAtrous.comp:237-276; beyond 4 iterations it keeps ping-ponging
+    uint32_t sDiff, sSpec, sIndir, dDiff, dSpec, dIndir;
+    if( iteration == 0 )
+    {
+        sDiff = ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE; sSpec = ASVGF_IMAGE_SPEC_PING_COLOR; sIndir = ASVGF_IMAGE_INDIR_PING;
+        dDiff = ASVGF_IMAGE_DIFF_COLOR_HISTORY; dSpec = ASVGF_IMAGE_SPEC_PONG_COLOR; dIndir = ASVGF_IMAGE_INDIR_PONG;
+    }
+    else if( iteration % 2 == 1 )
+    {
+        sDiff = iteration == 1 ? ASVGF_IMAGE_DIFF_COLOR_HISTORY : ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE;
+        sSpec = ASVGF_IMAGE_SPEC_PONG_COLOR; sIndir = ASVGF_IMAGE_INDIR_PONG;
+        dDiff = ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE; dSpec = ASVGF_IMAGE_SPEC_PING_COLOR; dIndir = ASVGF_IMAGE_INDIR_PING;
+    }
+    else
+    {
+        sDiff = ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE; sSpec = ASVGF_IMAGE_SPEC_PING_COLOR; sIndir = ASVGF_IMAGE_INDIR_PING;
+        dDiff = ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE; dSpec = ASVGF_IMAGE_SPEC_PONG_COLOR; dIndir = ASVGF_IMAGE_INDIR_PONG;
+    }
+    NEED( sDiff, sSpec, sIndir, ASVGF_IMAGE_DEPTH_WORLD, ASVGF_IMAGE_DEPTH_GRAD, ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_METALLIC_ROUGHNESS,
+          ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE );
+    if( last ) NEED( ASVGF_IMAGE_ALBEDO, ASVGF_IMAGE_THROUGHPUT, ASVGF_IMAGE_IS_SKY, ASVGF_IMAGE_PRE_FINAL, ASVGF_IMAGE_HISTOGRAM_INPUT );
+    else NEED( dDiff, dSpec, dIndir );
+
+    AtrousArgs a;
+    a.srcDiff = d.get( sDiff, fi ); a.srcSpec = d.get( sSpec, fi ); a.srcIndir = d.get( sIndir, fi );
+    a.dstDiff = d.get( dDiff, fi ); a.dstSpec = d.get( dSpec, fi ); a.dstIndir = d.get( dIndir, fi );
+    a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi ); a.depthGrad = d.get( ASVGF_IMAGE_DEPTH_GRAD, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi );
+    a.metRough = d.get( ASVGF_IMAGE_METALLIC_ROUGHNESS, fi ); a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi );
+    a.filteredVariance = d.get( ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE, fi );
+    a.albedo = d.get( ASVGF_IMAGE_ALBEDO, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
+    a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.histogramInput = d.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
+    a.lut = d.lut; a.iteration = ( int32_t )iteration;
+
+    const dim3 grid = gridFor( ( int )d.W, d.ownEnd - d.ownBegin );
+    if( iteration == 0 ) k_atrous< true, false ><<< grid, kBlock, 0, s >>>( a, u );
+    else if( last ) k_atrous< false, true ><<< grid, kBlock, 0, s >>>( a, u );
+    else k_atrous< false, false ><<< grid, kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_atrous" );
+}
+
+AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
+{
+    if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return runGradientSamples( d, s, fi, u );
+    if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return runGradientAtrous( d, s, fi, u, pass - ASVGF_PASS_GRADIENT_ATROUS_0 );
+    if( pass == ASVGF_PASS_TEMPORAL ) return runTemporal( d, s, fi, u );
+    if( pass == ASVGF_PASS_ANTIFIREFLY ) return runAntiFirefly( d, s, fi, u );
+    if( pass == ASVGF_PASS_VARIANCE ) return runVariance( d, s, fi, u );
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_ATROUS_0 + d.iterations ) return runAtrous( d, s, fi, u, pass - ASVGF_PASS_ATROUS_0 );
+    return fail( ASVGF_WRONG_ARGUMENT, "unknown pass " + std::to_string( pass ) );
+}
+
+AsvgfResult checkCall( AsvgfDenoiser d, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    if( !d ) return fail( ASVGF_WRONG_ARGUMENT, "null denoiser" );
+    if( frameIndex > 1 ) return fail( ASVGF_WRONG_ARGUMENT, "frameIndex must be 0 or 1 (MAX_FRAMES_IN_FLIGHT)" );
+    if( !pUniform ) return fail( ASVGF_WRONG_ARGUMENT, "null uniform" );
+    if( ( uint32_t )pUniform->renderWidth != d->W || ( uint32_t )pUniform->renderHeight != d->H )
+        return fail( ASVGF_WRONG_ARGUMENT, "uniform renderWidth/renderHeight differ from the created size" );
+    return ASVGF_SUCCESS;
+}
+
+} // namespace
+
+extern "C" {
+
+AsvgfResult asvgfGetImageInfo( uint32_t imageIndex, uint32_t W, uint32_t H, uint32_t* pFormat, uint32_t* pWidth, uint32_t* pHeight, uint32_t* pBpp )
+{
+    ImageDesc desc;
+    if( imageIndex >= ASVGF_IMAGE_COUNT || !describe( imageIndex, &desc ) ) return fail( ASVGF_WRONG_ARGUMENT, "image index not used by the denoiser path" );
+    if( pFormat ) *pFormat = desc.format;
+    if( pWidth ) *pWidth = desc.thirdRes ? ( ( W + 1 ) / 3 > 1 ? ( W + 1 ) / 3 : 1 ) : W; // Framebuffers.cpp:691-699
+    if( pHeight ) *pHeight = desc.thirdRes ? ( ( H + 1 ) / 3 > 1 ? ( H + 1 ) / 3 : 1 ) : H;
+    if( pBpp ) *pBpp = desc.bpp;
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser )
+{
+    if( !pInfo || !pDenoiser ) return fail( ASVGF_WRONG_ARGUMENT, "null argument" );
+    *pDenoiser = nullptr;
+    if( pInfo->renderWidth == 0 || pInfo->renderHeight == 0 || ( pInfo->renderWidth & 1u ) ) return fail( ASVGF_WRONG_ARGUMENT, "renderWidth must be even and non-zero" );
+    if( pInfo->renderWidth > 32768 || pInfo->renderHeight > 32768 ) return fail( ASVGF_WRONG_ARGUMENT, "render size too large" );
+    if( pInfo->atrousIterations < 2 || pInfo->atrousIterations > ASVGF_MAX_ATROUS_ITERATIONS ) return fail( ASVGF_WRONG_ARGUMENT, "atrousIterations must be 2..8" );
+
+    int deviceCount = 0;
+    if( cudaGetDeviceCount( &deviceCount ) != cudaSuccess || deviceCount == 0 )
+    {
+        cudaGetLastError();
+        return fail( ASVGF_CUDA_ERROR, "no CUDA device: libasvgf has no CPU fallback" );
+    }
+    int device = pInfo->device;
+    if( device < 0 ) CUDA_TRY( cudaGetDevice( &device ) );
+    if( device >= deviceCount ) return fail( ASVGF_WRONG_ARGUMENT, "device ordinal out of range" );
+
+    AsvgfDenoiser_T* d = new( std::nothrow ) AsvgfDenoiser_T();
+    if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
+    d->info = *pInfo; d->device = device;
+    d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
+    const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
+
+    if( pInfo->bandRowEnd == 0 )
+    {
+        d->ownBegin = 0; d->ownEnd = H; d->row0 = 0; d->rows = H;
+        d->gownBegin = 0; d->gownEnd = gH; d->grow0 = 0; d->grows = gH;
+    }
+    else
+    {
+        if( pInfo->bandRowBegin >= pInfo->bandRowEnd || pInfo->bandRowEnd > d->H || pInfo->bandRowBegin % 3 || ( pInfo->bandRowEnd % 3 && pInfo->bandRowEnd != d->H ) ||
+            pInfo->bandHaloRows % 3 )
+        {
+            delete d;
+            return fail( ASVGF_WRONG_ARGUMENT, "band rows must be ordered, inside the frame and multiples of 3" );
+        }
+        const int32_t halo = ( int32_t )pInfo->bandHaloRows;
+        d->ownBegin = ( int32_t )pInfo->bandRowBegin; d->ownEnd = ( int32_t )pInfo->bandRowEnd;
+        d->row0 = d->ownBegin - halo > 0 ? d->ownBegin - halo : 0;
+        const int32_t rend = d->ownEnd + halo < H ? d->ownEnd + halo : H;
+        d->rows = rend - d->row0;
+        d->gownBegin = d->ownBegin / 3;
+        d->gownEnd   = d->ownEnd == H ? gH : d->ownEnd / 3;
+        d->grow0     = d->gownBegin - halo / 3 > 0 ? d->gownBegin - halo / 3 : 0;
+        const int32_t grend = d->gownEnd + halo / 3 < gH ? d->gownEnd + halo / 3 : gH;
+        d->grows = grend - d->grow0;
+    }
+
+    DeviceGuard guard( device );
+    if( !guard.ok ) { delete d; return fail( ASVGF_CUDA_ERROR, "cudaSetDevice failed" ); }
+
+    AsvgfResult r = acquireLut( device, &d->lut );
+    if( r != ASVGF_SUCCESS ) { delete d; return r; }
+    d->haveLut = true;
+
+    for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
+    {
+        ImageDesc desc;
+        if( !describe( i, &desc ) ) continue;
+        Img& im = d->img[ i ];
+        uint32_t w, h;
+        asvgfGetImageInfo( i, d->W, d->H, nullptr, &w, &h, nullptr );
+        im.w = ( int32_t )w; im.h = ( int32_t )h;
+        im.row0 = desc.thirdRes ? d->grow0 : d->row0;
+        im.rows = desc.thirdRes ? d->grows : d->rows;
+        im.pitch = ( w * desc.bpp + 255u ) & ~255u;
+        im.p = nullptr;
+        if( pInfo->flags & ASVGF_CREATE_EXTERNAL_IMAGES ) continue;
+        if( i == ASVGF_IMAGE_DEBUG_MASK && !( pInfo->flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) ) continue;
+        const size_t bytes = ( size_t )im.pitch * ( size_t )im.rows;
+        cudaError_t  e     = cudaMalloc( ( void** )&im.p, bytes );
+        if( e == cudaSuccess ) e = cudaMemset( im.p, 0, bytes );
+        if( e != cudaSuccess )
+        {
+            AsvgfResult rr = cudaFail( e, "cudaMalloc(image)" );
+            std::string msg = g_lastError;
+            asvgfDestroy( d );
+            return fail( rr, msg );
+        }
+        d->owned[ i ] = true;
+    }
+    *pDenoiser = d;
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult asvgfDestroy( AsvgfDenoiser d )
+{
+    if( !d ) return ASVGF_SUCCESS;
+    DeviceGuard guard( d->device );
+    for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
+        if( d->owned[ i ] && d->img[ i ].p ) cudaFree( d->img[ i ].p );
+    if( d->haveLut ) releaseLut( d->device );
+    delete d;
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult asvgfGetImage( AsvgfDenoiser d, uint32_t imageIndex, uint32_t frameIndex, void** ppDevice, size_t* pPitch, uint32_t* pWidth, uint32_t* pFirstRow,
+                           uint32_t* pRows )
+{
+    ImageDesc desc;
+    if( !d || frameIndex > 1 || imageIndex >= ASVGF_IMAGE_COUNT || !describe( imageIndex, &desc ) ) return fail( ASVGF_WRONG_ARGUMENT, "bad image index / frameIndex" );
+    const Img& im = d->get( imageIndex, frameIndex );
+    if( ppDevice ) *ppDevice = im.p;
+    if( pPitch ) *pPitch = im.pitch;
+    if( pWidth ) *pWidth = ( uint32_t )im.w;
+    if( pFirstRow ) *pFirstRow = ( uint32_t )im.row0;
+    if( pRows ) *pRows = ( uint32_t )im.rows;
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult asvgfBindExternalImage( AsvgfDenoiser d, uint32_t imageIndex, void* pDevice, size_t pitchBytes )
+{
+    ImageDesc desc;
+    if( !d || imageIndex >= ASVGF_IMAGE_COUNT || !describe( imageIndex, &desc ) ) return fail( ASVGF_WRONG_ARGUMENT, "bad image index" );
+    Img& im = d->img[ imageIndex ];
+    if( !pDevice || pitchBytes < ( size_t )im.w * desc.bpp || pitchBytes % desc.bpp || pitchBytes > 0xffffffffull )
+        return fail( ASVGF_WRONG_ARGUMENT, "bad pointer or pitch" );
+    if( ( ( uintptr_t )pDevice % ( desc.bpp < 16 ? desc.bpp : 16 ) ) || ( pitchBytes % ( desc.bpp < 16 ? desc.bpp : 16 ) ) )
+        return fail( ASVGF_WRONG_ARGUMENT, "pointer/pitch must be texel-aligned" );
+    if( d->owned[ imageIndex ] && im.p )
+    {
+        DeviceGuard guard( d->device );
+        cudaFree( im.p );
+        d->owned[ imageIndex ] = false;
+    }
+    im.p = ( uint8_t* )pDevice; im.pitch = ( uint32_t )pitchBytes;
+    return ASVGF_SUCCESS;
+}
+
+static AsvgfResult copyImage( AsvgfDenoiser d, AsvgfStream stream, uint32_t imageIndex, uint32_t frameIndex, void* pHost, size_t hostPitch, bool upload )
+{
+    ImageDesc desc;
+    if( !d || frameIndex > 1 || !pHost || imageIndex >= ASVGF_IMAGE_COUNT || !describe( imageIndex, &desc ) ) return fail( ASVGF_WRONG_ARGUMENT, "bad argument" );
+    const Img& im = d->get( imageIndex, frameIndex );
+    if( !im.p ) return fail( ASVGF_NOT_BOUND, "image has no storage" );
+    const size_t rowBytes = ( size_t )im.w * desc.bpp;
+    if( hostPitch == 0 ) hostPitch = rowBytes;
+    if( hostPitch < rowBytes ) return fail( ASVGF_WRONG_ARGUMENT, "host pitch smaller than a row" );
+    DeviceGuard guard( d->device );
+    if( upload ) CUDA_TRY( cudaMemcpy2DAsync( im.p, im.pitch, pHost, hostPitch, rowBytes, ( size_t )im.rows, cudaMemcpyHostToDevice, ( cudaStream_t )stream ) );
+    else CUDA_TRY( cudaMemcpy2DAsync( pHost, hostPitch, im.p, im.pitch, rowBytes, ( size_t )im.rows, cudaMemcpyDeviceToHost, ( cudaStream_t )stream ) );
+    return ASVGF_SUCCESS;
+}
+AsvgfResult asvgfUploadImage( AsvgfDenoiser d, AsvgfStream stream, uint32_t imageIndex, uint32_t frameIndex, const void* pHost, size_t hostPitch )
+{
+    return copyImage( d, stream, imageIndex, frameIndex, const_cast< void* >( pHost ), hostPitch, true );
+}
+AsvgfResult asvgfDownloadImage( AsvgfDenoiser d, AsvgfStream stream, uint32_t imageIndex, uint32_t frameIndex, void* pHost, size_t hostPitch )
+{
+    return copyImage( d, stream, imageIndex, frameIndex, pHost, hostPitch, false );
+}
+
+AsvgfResult asvgfResetHistory( AsvgfDenoiser d, AsvgfStream stream )
+{
+    if( !d ) return fail( ASVGF_WRONG_ARGUMENT, "null denoiser" );
+    DeviceGuard guard( d->device );
+    for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
+        if( d->owned[ i ] && d->img[ i ].p ) CUDA_TRY( cudaMemsetAsync( d->img[ i ].p, 0, ( size_t )d->img[ i ].pitch * d->img[ i ].rows, ( cudaStream_t )stream ) );
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult asvgfGradientSamples( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    DeviceGuard guard( d->device );
+    return runPass( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), ASVGF_PASS_GRADIENT_SAMPLES );
+}
+
+AsvgfResult asvgfDenoise( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    DeviceGuard   guard( d->device );
+    const Uniform u = makeUniform( *d, *pUniform );
+    for( uint32_t pass = ASVGF_PASS_GRADIENT_ATROUS_0; pass < ASVGF_PASS_ATROUS_0 + d->iterations; pass++ ) // Denoiser.cpp:87-254
+    {
+        r = runPass( *d, ( cudaStream_t )stream, frameIndex, u, pass );
+        if( r != ASVGF_SUCCESS ) return r;
+    }
+    return ASVGF_SUCCESS;
+}
+
+AsvgfResult asvgfDenoisePass( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform, uint32_t pass )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    DeviceGuard guard( d->device );
+    return runPass( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), pass );
+}
+
+AsvgfResult asvgfSynchronize( AsvgfDenoiser d, AsvgfStream stream )
+{
+    if( !d ) return fail( ASVGF_WRONG_ARGUMENT, "null denoiser" );
+    DeviceGuard guard( d->device );
+    CUDA_TRY( cudaStreamSynchronize( ( cudaStream_t )stream ) );
+    return ASVGF_SUCCESS;
+}
+
+uint64_t asvgfGetLaunchCount( AsvgfDenoiser d ) { return d ? d->launchCount : 0; }
+
+const char* asvgfPassName( uint32_t pass )
+{
+    if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return "k_gradient_samples";
+    if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return "k_gradient_atrous";
+    if( pass == ASVGF_PASS_TEMPORAL ) return "k_temporal";
+    if( pass == ASVGF_PASS_ANTIFIREFLY ) return "k_antifirefly";
+    if( pass == ASVGF_PASS_VARIANCE ) return "k_variance";
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous";
+    return "?";
+}
+
+// Algorithmic HBM bytes per full-resolution pixel: unique reads + writes in the reference's storage formats
+// (BASELINE.md section 3).
+double asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations )
+{
+    if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return 12.8;
+    if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return 1.0;
+    if( pass == ASVGF_PASS_TEMPORAL ) return 126.4;
+    if( pass == ASVGF_PASS_ANTIFIREFLY ) return 24.0;
+    if( pass == ASVGF_PASS_VARIANCE ) return 30.0;
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_ATROUS_0 + atrousIterations ) return pass + 1 == ASVGF_PASS_ATROUS_0 + atrousIterations ? 55.0 : 52.0;
+    return 0.0;
+}
+
+const char* asvgfResultString( AsvgfResult r )
+{
+    switch( r )
+    {
+        case ASVGF_SUCCESS: return "ASVGF_SUCCESS";
+        case ASVGF_WRONG_ARGUMENT: return "ASVGF_WRONG_ARGUMENT";
+        case ASVGF_CUDA_ERROR: return "ASVGF_CUDA_ERROR";
+        case ASVGF_OUT_OF_MEMORY: return "ASVGF_OUT_OF_MEMORY";
+        case ASVGF_UNSUPPORTED: return "ASVGF_UNSUPPORTED";
+        case ASVGF_NOT_BOUND: return "ASVGF_NOT_BOUND";
+        default: return "ASVGF_?";
+    }
+}
+const char* asvgfLastErrorMessage( void ) { return g_lastError.c_str(); }
+
+} // extern "C"

@@ -1,0 +1,176 @@
+"""Host-side mirror of RTGL1's Denoiser + Framebuffers over the C ABI of libasvgf.so (include/asvgf.h).
+
+Reference interface mirrored here (same call order, argument meaning and error behaviour):
+  RTGL1::Denoiser::Denoise(cmd, frameIndex, uniform)            Source/Denoiser.h:45-47
+  RTGL1::PathTracer::CalculateGradientsSamples(params)          Source/PathTracer.cpp:196-219
+  RTGL1::Framebuffers::GetImage(fbImageIndex, frameIndex)       Source/Framebuffers.cpp:35-50 (cur/prev swap)
+`cmd` becomes a CUDA stream handle (an int, e.g. torch.cuda.current_stream().cuda_stream); calls only enqueue.
+There is no CPU fallback: constructing a Denoiser without libasvgf.so or without a CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import layout
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libasvgf.so")
+_lib = None
+
+SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND = range(6)
+CREATE_EXPORT_DEBUG_MASK = 1 << 0
+CREATE_EXTERNAL_IMAGES = 1 << 1
+CREATE_NO_FUSION = 1 << 2
+
+EXPORTED_SYMBOLS = [
+    "asvgfCreate", "asvgfDestroy", "asvgfGetImageInfo", "asvgfGetImage", "asvgfBindExternalImage", "asvgfUploadImage",
+    "asvgfDownloadImage", "asvgfResetHistory", "asvgfGradientSamples", "asvgfDenoise", "asvgfDenoisePass",
+    "asvgfSynchronize", "asvgfGetLaunchCount", "asvgfPassName", "asvgfPassBytesPerPixel", "asvgfResultString",
+    "asvgfLastErrorMessage",
+]
+
+
+class CreateInfo(ctypes.Structure):
+    _fields_ = [("renderWidth", ctypes.c_uint32), ("renderHeight", ctypes.c_uint32),
+                ("atrousIterations", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("device", ctypes.c_int32),
+                ("bandRowBegin", ctypes.c_uint32), ("bandRowEnd", ctypes.c_uint32), ("bandHaloRows", ctypes.c_uint32)]
+
+
+class AsvgfError(RuntimeError):
+    def __init__(self, code, where):
+        L = lib()
+        self.code = code
+        super().__init__("%s: %s (%s)" % (where, L.asvgfResultString(code).decode(),
+                                          L.asvgfLastErrorMessage().decode()))
+
+
+def lib():
+    """Loads libasvgf.so; raises (never falls back) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError("libasvgf.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                              "the A-SVGF path has no CPU fallback")
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, u32, sz = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_size_t
+        pu32 = ctypes.POINTER(u32)
+        puni = ctypes.POINTER(layout.GlobalUniform)
+        L.asvgfCreate.argtypes = [ctypes.POINTER(CreateInfo), ctypes.POINTER(vp)]
+        L.asvgfDestroy.argtypes = [vp]
+        L.asvgfGetImageInfo.argtypes = [u32, u32, u32, pu32, pu32, pu32, pu32]
+        L.asvgfGetImage.argtypes = [vp, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(sz), pu32, pu32, pu32]
+        L.asvgfBindExternalImage.argtypes = [vp, u32, vp, sz]
+        L.asvgfUploadImage.argtypes = [vp, vp, u32, u32, vp, sz]
+        L.asvgfDownloadImage.argtypes = [vp, vp, u32, u32, vp, sz]
+        L.asvgfResetHistory.argtypes = [vp, vp]
+        L.asvgfGradientSamples.argtypes = [vp, vp, u32, puni]
+        L.asvgfDenoise.argtypes = [vp, vp, u32, puni]
+        L.asvgfDenoisePass.argtypes = [vp, vp, u32, puni, u32]
+        L.asvgfSynchronize.argtypes = [vp, vp]
+        L.asvgfGetLaunchCount.argtypes = [vp]
+        L.asvgfGetLaunchCount.restype = ctypes.c_uint64
+        L.asvgfPassName.argtypes = [u32]
+        L.asvgfPassName.restype = ctypes.c_char_p
+        L.asvgfPassBytesPerPixel.argtypes = [u32, u32]
+        L.asvgfPassBytesPerPixel.restype = ctypes.c_double
+        L.asvgfResultString.argtypes = [ctypes.c_int]
+        L.asvgfResultString.restype = ctypes.c_char_p
+        L.asvgfLastErrorMessage.restype = ctypes.c_char_p
+        for name in EXPORTED_SYMBOLS:
+            f = getattr(L, name)
+            if f.restype is ctypes.c_int and name not in ("asvgfGetLaunchCount",):
+                f.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _check(code, where):
+    if code != SUCCESS:
+        raise AsvgfError(code, where)
+
+
+def pass_bytes_per_pixel(p, iterations=4):
+    return lib().asvgfPassBytesPerPixel(p, iterations)
+
+
+def chain_bytes_per_pixel(iterations=4, with_gradient_samples=True):
+    """Algorithmic HBM bytes per pixel of one frame (408 for the reference chain)."""
+    first = 0 if with_gradient_samples else 1
+    return sum(pass_bytes_per_pixel(p, iterations) for p in range(first, layout.PASS_ATROUS_0 + iterations))
+
+
+class Denoiser:
+    """One view stream (= one RTGL1 instance's Denoiser + its Framebuffers)."""
+
+    def __init__(self, width, height, atrous_iterations=4, flags=0, device=-1, band=None, halo_rows=0):
+        self._h = ctypes.c_void_p()
+        self.width, self.height, self.iterations = width, height, atrous_iterations
+        info = CreateInfo(width, height, atrous_iterations, flags, device,
+                          band[0] if band else 0, band[1] if band else 0, halo_rows)
+        _check(lib().asvgfCreate(ctypes.byref(info), ctypes.byref(self._h)), "asvgfCreate")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().asvgfDestroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @staticmethod
+    def _index(name):
+        return layout.INDEX[name] if isinstance(name, str) else int(name)
+
+    def image(self, name, frame_index):
+        """(device pointer, pitch bytes, width, first stored row, stored rows), cur/prev swap applied."""
+        p, pitch = ctypes.c_void_p(), ctypes.c_size_t()
+        w, r0, rows = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        _check(lib().asvgfGetImage(self._h, self._index(name), frame_index, ctypes.byref(p), ctypes.byref(pitch),
+                                   ctypes.byref(w), ctypes.byref(r0), ctypes.byref(rows)), "asvgfGetImage")
+        return p.value, pitch.value, w.value, r0.value, rows.value
+
+    def bind_external(self, name, device_ptr, pitch_bytes):
+        _check(lib().asvgfBindExternalImage(self._h, self._index(name), device_ptr, pitch_bytes),
+               "asvgfBindExternalImage")
+
+    def upload(self, name, frame_index, host, stream=0):
+        """host: C-contiguous numpy array (or a host pointer int) holding the stored rows, tightly packed."""
+        ptr = host if isinstance(host, int) else host.ctypes.data
+        _check(lib().asvgfUploadImage(self._h, stream, self._index(name), frame_index, ptr, 0), "asvgfUploadImage")
+
+    def download(self, name, frame_index, stream=0, out=None):
+        idx = self._index(name)
+        _, _, w, r0, rows = self.image(idx, frame_index)
+        dtype, shape = layout.image_numpy_shape(idx, self.width, self.height)
+        shape = (rows,) + tuple(shape[1:])
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        ptr = out if isinstance(out, int) else out.ctypes.data
+        _check(lib().asvgfDownloadImage(self._h, stream, idx, frame_index, ptr, 0), "asvgfDownloadImage")
+        if not isinstance(out, int):
+            self.synchronize(stream)
+        return out
+
+    def reset_history(self, stream=0):
+        _check(lib().asvgfResetHistory(self._h, stream), "asvgfResetHistory")
+
+    def gradient_samples(self, frame_index, uniform, stream=0):
+        _check(lib().asvgfGradientSamples(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfGradientSamples")
+
+    def denoise(self, frame_index, uniform, stream=0):
+        _check(lib().asvgfDenoise(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfDenoise")
+
+    def denoise_pass(self, p, frame_index, uniform, stream=0):
+        _check(lib().asvgfDenoisePass(self._h, stream, frame_index, ctypes.byref(uniform), p), "asvgfDenoisePass")
+
+    def synchronize(self, stream=0):
+        _check(lib().asvgfSynchronize(self._h, stream), "asvgfSynchronize")
+
+    @property
+    def launch_count(self):
+        return lib().asvgfGetLaunchCount(self._h)
