@@ -51,7 +51,8 @@ typedef enum AsvgfCreateFlagBits
 {
     ASVGF_CREATE_EXPORT_DEBUG_MASK = 1u << 0, /* temporal pass also writes ASVGF_IMAGE_DEBUG_MASK               */
     ASVGF_CREATE_EXTERNAL_IMAGES   = 1u << 1, /* allocate nothing: every image comes from asvgfBindExternalImage */
-    ASVGF_CREATE_NO_FUSION         = 1u << 2  /* one kernel per reference dispatch (used by per-pass parity tests)*/
+    ASVGF_CREATE_LITERAL_KERNELS   = 1u << 2  /* run the literal one-thread-per-pixel kernels (precise powf/expf, no
+                                                 tiling): slow, closest to the shader text; for A/B numerics checks  */
 } AsvgfCreateFlagBits;
 
 /* = Denoiser ctor + Framebuffers::PrepareForSize (Source/Denoiser.cpp:24-55, Source/Framebuffers.cpp:216-230) */

@@ -6,6 +6,7 @@
 #include "../../include/asvgf.h"
 
 #include "asvgf_kernels.cuh"
+#include "asvgf_atrous_tiled.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -317,11 +318,32 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.histogramInput = d.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
 
-    const dim3 grid = gridFor( ( int )d.W, d.ownEnd - d.ownBegin );
-    if( iteration == 0 ) k_atrous< true, false ><<< grid, kBlock, 0, s >>>( a, u );
-    else if( last ) k_atrous< false, true ><<< grid, kBlock, 0, s >>>( a, u );
-    else k_atrous< false, false ><<< grid, kBlock, 0, s >>>( a, u );
-    return launchCheck( d, "k_atrous" );
+    const int    step = 1 << iteration;
+    const size_t smem = atrousTiledSmemBytes( step );
+    if( ( d.info.flags & ASVGF_CREATE_LITERAL_KERNELS ) || smem > 200 * 1024 )
+    {
+        const dim3 grid = gridFor( ( int )d.W, d.ownEnd - d.ownBegin );
+        if( iteration == 0 ) k_atrous< true, false ><<< grid, kBlock, 0, s >>>( a, u );
+        else if( last ) k_atrous< false, true ><<< grid, kBlock, 0, s >>>( a, u );
+        else k_atrous< false, false ><<< grid, kBlock, 0, s >>>( a, u );
+        return launchCheck( d, "k_atrous" );
+    }
+    // dilated tiles: 64 columns x 16 rows spaced `step` apart; grid.y enumerates (band of 16*step rows, residue)
+    const int  rows  = d.ownEnd - d.ownBegin;
+    const int  bands = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
+    const dim3 grid( ( unsigned )( ( d.W + kAtTileW - 1 ) / kAtTileW ), ( unsigned )( bands * step ), 1 );
+    auto launch = [ & ]( auto kernel ) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+        if( e != cudaSuccess ) return e;
+        kernel<<< grid, kAtThreads, smem, s >>>( a, u );
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if( iteration == 0 ) e = launch( k_atrous_tiled< true, false > );
+    else if( last ) e = launch( k_atrous_tiled< false, true > );
+    else e = launch( k_atrous_tiled< false, false > );
+    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_tiled)" );
+    return launchCheck( d, "k_atrous_tiled" );
 }
 
 AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
@@ -569,7 +591,7 @@ const char* asvgfPassName( uint32_t pass )
     if( pass == ASVGF_PASS_TEMPORAL ) return "k_temporal";
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return "k_antifirefly";
     if( pass == ASVGF_PASS_VARIANCE ) return "k_variance";
-    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous";
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_tiled";
     return "?";
 }
 

@@ -20,7 +20,7 @@ _lib = None
 SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND = range(6)
 CREATE_EXPORT_DEBUG_MASK = 1 << 0
 CREATE_EXTERNAL_IMAGES = 1 << 1
-CREATE_NO_FUSION = 1 << 2
+CREATE_LITERAL_KERNELS = 1 << 2
 
 EXPORTED_SYMBOLS = [
     "asvgfCreate", "asvgfDestroy", "asvgfGetImageInfo", "asvgfGetImage", "asvgfBindExternalImage", "asvgfUploadImage",
