@@ -210,18 +210,35 @@ def run_ours(args, rank, world, local_rank):
     sh = stream.cuda_stream
     d = dn.Denoiser(W, H, N, device=local_rank)
 
-    # two consecutive synthetic frames in pinned host memory (independent stream per rank: its own seed)
+    # A cycled sequence of consecutive synthetic frames (camera motion, moving objects, disocclusions, fireflies;
+    # independent stream per rank: its own seed).  Host copies live in pinned memory (the e2e leg uploads them),
+    # device copies stay resident in HBM and are bound as the producer images of the frame slot before each step
+    # (asvgfBindExternalImage = the G-buffer producer handing over its images; no copy).
     seed = synth.DEFAULT_SEED + rank
-    host = []
-    for f in (0, 1):
-        bufs = {}
+    n_frames = max(2, args.frames - args.frames % 2)
+    swappable = {n for n in layout.PRODUCER_IMAGES if n + "_Prev" in layout.IMAGES}
+    host, resident = [], []
+    for f in range(n_frames):
+        bufs, dev = {}, {}
         for name in layout.PRODUCER_IMAGES:
             dtype, shape = layout.image_numpy_shape(name, W, H)
             t = torch.empty(int(np.prod(shape)) * dtype.itemsize, dtype=torch.uint8, pin_memory=True)
             bufs[name] = t.numpy().view(dtype).reshape(shape)
             bufs["_keep_" + name] = t
         synth.generate(W, H, f, seed, out={k: v for k, v in bufs.items() if not k.startswith("_keep_")})
+        for name in layout.PRODUCER_IMAGES:
+            _, pitch, _, _, rows = d.image(name, 0)
+            row_bytes = bufs[name].nbytes // rows
+            dt = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
+            dt[:, :row_bytes].copy_(bufs["_keep_" + name].view(rows, row_bytes), non_blocking=True)
+            dev[name] = (dt, pitch)
         host.append((bufs, synth.uniform(W, H, f)))
+        resident.append(dev)
+    torch.cuda.synchronize()
+    # two slot-sized staging sets for the e2e leg (host -> device copies land here)
+    staging = []
+    for fi in (0, 1):
+        staging.append({name: (torch.zeros_like(resident[0][name][0]), resident[0][name][1]) for name in layout.PRODUCER_IMAGES})
     h2d_bytes = sum(host[0][0][n].nbytes for n in layout.PRODUCER_IMAGES)
     out_host = {}
     for name in ("PreFinal", "HistogramInput"):
@@ -230,64 +247,90 @@ def run_ours(args, rank, world, local_rank):
         out_host[name] = (t, t.numpy().view(dtype).reshape(shape))
     d2h_bytes = sum(v[1].nbytes for v in out_host.values())
 
-    def upload(fi):
-        bufs, _ = host[fi]
+    def bind(fi, images):
+        """Producer images of frame slot fi := `images` (physical image X for slot 0, X_Prev for slot 1: the
+        reference's cur/prev swap, Framebuffers.cpp:35-50)."""
+        for name in layout.PRODUCER_IMAGES:
+            t, pitch = images[name]
+            d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
+
+    def upload(fi, f):
+        bufs, _ = host[f]
         for name in layout.PRODUCER_IMAGES:
             d.upload(name, fi, bufs[name], stream=sh)
 
+    # the launches of one frame in dispatch order: gradient samples, gradient a-trous x4, temporal, anti-firefly,
+    # variance, N a-trous iterations
     passes = list(range(0, layout.PASS_ATROUS_0 + N))
 
-    def step_resident(i, events=None):
-        fi = i & 1
-        u = host[fi][1]
+    def step_production(i):
+        f, fi = i % n_frames, i & 1
+        u = host[f][1]
+        bind(fi, resident[f])
+        d.gradient_samples(fi, u, stream=sh)      # = PathTracer::CalculateGradientsSamples (image-space part)
+        d.denoise(fi, u, stream=sh)               # = Denoiser::Denoise
+
+    def step_per_pass(i, events):
+        f, fi = i % n_frames, i & 1
+        u = host[f][1]
+        bind(fi, resident[f])
         for k, p in enumerate(passes):
             if p == 0:
                 d.gradient_samples(fi, u, stream=sh)
             else:
                 d.denoise_pass(p, fi, u, stream=sh)
-            if events is not None:
-                events[k + 1].record(stream)
+            events[k + 1].record(stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: inputs of both frame slots already in HBM ----
-    upload(0); upload(1)
-    torch.cuda.synchronize()
+    # ---- device-resident throughput: every frame's inputs already in HBM ----
     for i in range(args.warmup):
-        step_resident(i)
-    n_ev = len(passes) + 1
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+        step_production(i)
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     barrier()
     launches0 = d.launch_count
     sampler.start() if sampler.ok else None
+    e_begin.record(stream)
     for i in range(args.steps):
-        evs[i][0].record(stream)
-        step_resident(args.warmup + i, evs[i])
+        step_production(args.warmup + i)
+    e_end.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
     launches = d.launch_count - launches0
     barrier()
-    total_ms = evs[0][0].elapsed_time(evs[-1][-1])
-    pass_ms = [sum(evs[i][k].elapsed_time(evs[i][k + 1]) for i in range(args.steps)) / args.steps for k in range(len(passes))]
+    total_ms = e_begin.elapsed_time(e_end)
+
+    # ---- per-pass breakdown (same launches, an event after each): explains the number above, not part of it ----
+    pp_steps = max(3, min(args.steps, 50))
+    n_ev = len(passes) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(pp_steps)]
+    for i in range(pp_steps):
+        evs[i][0].record(stream)
+        step_per_pass(args.warmup + args.steps + i, evs[i])
+    torch.cuda.synchronize()
+    pass_ms = [sum(evs[i][k].elapsed_time(evs[i][k + 1]) for i in range(pp_steps)) / pp_steps for k in range(len(passes))]
 
     # ---- end to end through the C ABI with host buffers ----
     e2e_steps = max(3, min(args.steps, 20))
-    for i in range(2):
-        fi = i & 1
-        upload(fi); d.gradient_samples(fi, host[fi][1], stream=sh); d.denoise(fi, host[fi][1], stream=sh)
+    i0 = args.warmup + args.steps + pp_steps
+    i0 += i0 & 1
+    bind(0, staging[0]); bind(1, staging[1])
+    for i in range(i0, i0 + 2):
+        f, fi = i % n_frames, i & 1
+        upload(fi, f); d.gradient_samples(fi, host[f][1], stream=sh); d.denoise(fi, host[f][1], stream=sh)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(e2e_steps):
-        fi = i & 1
-        upload(fi)
-        d.gradient_samples(fi, host[fi][1], stream=sh)
-        d.denoise(fi, host[fi][1], stream=sh)
+    for i in range(i0 + 2, i0 + 2 + e2e_steps):
+        f, fi = i % n_frames, i & 1
+        upload(fi, f)
+        d.gradient_samples(fi, host[f][1], stream=sh)
+        d.denoise(fi, host[f][1], stream=sh)
         for name, (t, arr) in out_host.items():
             d.download(name, fi, stream=sh, out=arr.ctypes.data)
         stream.synchronize()                                   # the caller consumes the frame's result
@@ -329,6 +372,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "atrous_iterations": N,
                        "streams_per_gpu": 1, "parallelism": "independent view streams, 1 per GPU, no collective",
+                       "sequence": "%d consecutive synthetic frames (camera motion, moving objects, disocclusions), cycled" % n_frames,
                        "l2": "no flush: per-stream images total %.2f GB, each pass streams > 126 MB L2" % (201 * W * H / 1e9),
                        "algorithmic_bytes_per_px": chain_bpp},
             "clocks": clocks,
@@ -345,7 +389,7 @@ def run_ours(args, rank, world, local_rank):
             "passes": per_pass,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(W, H, N, host)
+            line["cpu_baseline"] = cpu_baseline(W, H, N, None)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -362,6 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=8, help="distinct synthetic frames in the cycled sequence (even)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

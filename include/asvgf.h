@@ -84,7 +84,9 @@ typedef enum AsvgfPass
     ASVGF_PASS_ANTIFIREFLY       = 6,  /* CmAntiFirefly.comp                      */
     ASVGF_PASS_VARIANCE          = 7,  /* CmSVGFEstimateVariance.comp             */
     ASVGF_PASS_ATROUS_0          = 8,  /* CmSVGFAtrous_Iter0.comp; ASVGF_PASS_ATROUS_0+i = CmSVGFAtrous.comp, i  */
-    ASVGF_PASS_COUNT             = 8 + ASVGF_MAX_ATROUS_ITERATIONS
+    ASVGF_PASS_COUNT             = 8 + ASVGF_MAX_ATROUS_ITERATIONS,
+    /* the four gradient a-trous dispatches in one call, as asvgfDenoise issues them (Denoiser.cpp:87-120) */
+    ASVGF_PASS_GRADIENT_ATROUS_ALL = 100
 } AsvgfPass;
 
 ASVGF_API AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser );

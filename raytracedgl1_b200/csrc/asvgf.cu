@@ -6,10 +6,13 @@
 #include "../../include/asvgf.h"
 
 #include "asvgf_kernels.cuh"
+#include "asvgf_fast.cuh"
 #include "asvgf_atrous_tiled.cuh"
+#include "asvgf_atrous_pair.cuh"
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -128,6 +131,13 @@ void releaseLut( int device )
     }
 }
 
+void setImgStorage( Img& im, uint8_t* p, uint32_t pitch, uint32_t bpp )
+{
+    im.p = p; im.pitch = pitch;
+    im.pitchT = pitch / bpp;
+    im.p0 = p ? p - ( ptrdiff_t )im.row0 * ( ptrdiff_t )pitch : nullptr;
+}
+
 struct DeviceGuard
 {
     int  prev = -1;
@@ -155,6 +165,7 @@ struct AsvgfDenoiser_T
     NormalLut lut{};
     bool      haveLut     = false;
     uint64_t  launchCount = 0;
+    bool      atrousPair  = true; // packed-f32x2 a-trous kernel (ASVGF_ATROUS=tiled selects the scalar tiled one, for A/B runs)
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
     {
@@ -178,6 +189,12 @@ Uniform makeUniform( const AsvgfDenoiser_T& d, const AsvgfGlobalUniform& g )
     u.debugShowFlags = g.debugShowFlags; u.antiFireflyEnabled = g.antiFireflyEnabled;
     u.W = ( int32_t )g.renderWidth; u.H = ( int32_t )g.renderHeight;
     u.yBegin = d.ownBegin; u.yEnd = d.ownEnd;
+    u.halfW = g.renderWidth / 2.0f; u.invHalfW = 1.0f / u.halfW; u.invH = 1.0f / g.renderHeight;
+    {
+        const float rcp = g.timeDelta <= 0.0f ? 0.0f : 1.0f / g.timeDelta;
+        u.specMinFrames = std::fmin( std::fmax( 0.2f * rcp, 0.0f ), 128.0f );
+    }
+    for( int i = 0; i < 3; i++ ) u.cameraDelta[ i ] = g.cameraPositionPrev[ i ] - g.cameraPosition[ i ];
     return u;
 }
 
@@ -205,6 +222,8 @@ AsvgfResult launchCheck( AsvgfDenoiser_T& d, const char* name )
     return ASVGF_SUCCESS;
 }
 
+bool literal( const AsvgfDenoiser_T& d ) { return ( d.info.flags & ASVGF_CREATE_LITERAL_KERNELS ) != 0; }
+
 AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
 {
     NEED( ASVGF_IMAGE_GRADIENT_PREV_PIX, ASVGF_IMAGE_DIS_PING_GRADIENT, ASVGF_IMAGE_DIS_GRADIENT_HISTORY, ASVGF_IMAGE_MOTION,
@@ -215,7 +234,8 @@ AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi,
     a.gradientInputsPrev = d.get( ASVGF_IMAGE_GRADIENT_INPUTS_PREV, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
     a.indirAccumPrev = d.get( ASVGF_IMAGE_INDIR_ACCUM_PREV, fi ); a.fwdLum = d.get( ASVGF_IMAGE_FWD_LUM, fi );
     a.gyBegin = d.gownBegin; a.gyEnd = d.gownEnd;
-    k_gradient_samples<<< gridFor( a.disPing.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_gradient_samples<<< gridFor( a.disPing.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    else k_gradient_samples_fast<<< gridFor( a.disPing.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_gradient_samples" );
 }
 
@@ -228,7 +248,8 @@ AsvgfResult runGradientAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, 
     a.dst = d.get( even ? ASVGF_IMAGE_DIS_PONG_GRADIENT : ASVGF_IMAGE_DIS_PING_GRADIENT, fi );
     a.history = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi );
     a.iteration = ( int32_t )iteration; a.gyBegin = d.gownBegin; a.gyEnd = d.gownEnd;
-    k_gradient_atrous<<< gridFor( a.dst.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_gradient_atrous<<< gridFor( a.dst.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    else k_gradient_atrous_fast<<< gridFor( a.dst.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_gradient_atrous" );
 }
 
@@ -254,7 +275,8 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.outIndirAccum = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi ); a.outMask = d.get( ASVGF_IMAGE_DEBUG_MASK, fi );
     a.lut = d.lut;
     a.writeMask = ( ( d.info.flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) && a.outMask.p ) ? 1 : 0;
-    k_temporal<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_temporal<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    else k_temporal_fast<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_temporal" );
 }
 
@@ -265,7 +287,12 @@ AsvgfResult runAntiFirefly( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, con
     AntiFireflyArgs a;
     a.src[ 0 ] = d.get( ASVGF_IMAGE_DIFF_TEMPORARY, fi ); a.src[ 1 ] = d.get( ASVGF_IMAGE_SPEC_ACCUM_COLOR, fi ); a.src[ 2 ] = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi );
     a.dst[ 0 ] = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SPEC_PING_COLOR, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_INDIR_PING, fi );
-    k_antifirefly<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_antifirefly<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    else
+    {
+        const dim3 grid( ( unsigned )( ( d.W + kAfTile - 1 ) / kAfTile ), ( unsigned )( ( d.ownEnd - d.ownBegin + kAfTile - 1 ) / kAfTile ), 3 );
+        k_antifirefly_fast<<< grid, kAfThreads, 0, s >>>( a, u );
+    }
     return launchCheck( d, "k_antifirefly" );
 }
 
@@ -277,7 +304,8 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.color = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
     a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
     a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
-    k_variance<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_variance<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    else k_variance_fast<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_variance" );
 }
 
@@ -319,8 +347,9 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
 
     const int    step = 1 << iteration;
-    const size_t smem = atrousTiledSmemBytes( step );
-    if( ( d.info.flags & ASVGF_CREATE_LITERAL_KERNELS ) || smem > 200 * 1024 )
+    const bool   pair = d.atrousPair;
+    const size_t smem = pair ? atrousPairSmemBytes( step ) : atrousTiledSmemBytes( step );
+    if( literal( d ) || step > 32 )
     {
         const dim3 grid = gridFor( ( int )d.W, d.ownEnd - d.ownBegin );
         if( iteration == 0 ) k_atrous< true, false ><<< grid, kBlock, 0, s >>>( a, u );
@@ -333,21 +362,43 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     const int  bands = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
     const dim3 grid( ( unsigned )( ( d.W + kAtTileW - 1 ) / kAtTileW ), ( unsigned )( bands * step ), 1 );
     auto launch = [ & ]( auto kernel ) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 );
+        cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
         if( e != cudaSuccess ) return e;
         kernel<<< grid, kAtThreads, smem, s >>>( a, u );
         return cudaSuccess;
     };
-    cudaError_t e;
-    if( iteration == 0 ) e = launch( k_atrous_tiled< true, false > );
-    else if( last ) e = launch( k_atrous_tiled< false, true > );
-    else e = launch( k_atrous_tiled< false, false > );
-    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_tiled)" );
-    return launchCheck( d, "k_atrous_tiled" );
+    cudaError_t e = cudaErrorInvalidValue;
+#define ASVGF_ATROUS_CASE( S )                                                                                              \
+    case S:                                                                                                                 \
+        if( pair ) e = last ? launch( k_atrous_pair< S, false, true > ) : launch( k_atrous_pair< S, false, false > );       \
+        else e = last ? launch( k_atrous_tiled< S, false, true > ) : launch( k_atrous_tiled< S, false, false > );           \
+        break;
+    switch( step )
+    {
+        case 1: e = pair ? launch( k_atrous_pair< 1, true, false > ) : launch( k_atrous_tiled< 1, true, false > ); break; // iteration 0 is never the last
+        ASVGF_ATROUS_CASE( 2 )
+        ASVGF_ATROUS_CASE( 4 )
+        ASVGF_ATROUS_CASE( 8 )
+        ASVGF_ATROUS_CASE( 16 )
+        ASVGF_ATROUS_CASE( 32 )
+        default: break;
+    }
+#undef ASVGF_ATROUS_CASE
+    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous)" );
+    return launchCheck( d, pair ? "k_atrous_pair" : "k_atrous_tiled" );
 }
 
 AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
 {
+    if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL )
+    {
+        for( uint32_t i = 0; i < ASVGF_GRADIENT_ATROUS_ITERATIONS; i++ )
+        {
+            AsvgfResult r = runGradientAtrous( d, s, fi, u, i );
+            if( r != ASVGF_SUCCESS ) return r;
+        }
+        return ASVGF_SUCCESS;
+    }
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return runGradientSamples( d, s, fi, u );
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return runGradientAtrous( d, s, fi, u, pass - ASVGF_PASS_GRADIENT_ATROUS_0 );
     if( pass == ASVGF_PASS_TEMPORAL ) return runTemporal( d, s, fi, u );
@@ -403,6 +454,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     AsvgfDenoiser_T* d = new( std::nothrow ) AsvgfDenoiser_T();
     if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
     d->info = *pInfo; d->device = device;
+    if( const char* e = std::getenv( "ASVGF_ATROUS" ) ) d->atrousPair = std::strcmp( e, "tiled" ) != 0;
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
@@ -448,13 +500,18 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
         im.w = ( int32_t )w; im.h = ( int32_t )h;
         im.row0 = desc.thirdRes ? d->grow0 : d->row0;
         im.rows = desc.thirdRes ? d->grows : d->rows;
-        im.pitch = ( w * desc.bpp + 255u ) & ~255u;
-        im.p = nullptr;
+        setImgStorage( im, nullptr, ( w * desc.bpp + 255u ) & ~255u, desc.bpp );
         if( pInfo->flags & ASVGF_CREATE_EXTERNAL_IMAGES ) continue;
         if( i == ASVGF_IMAGE_DEBUG_MASK && !( pInfo->flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) ) continue;
         const size_t bytes = ( size_t )im.pitch * ( size_t )im.rows;
-        cudaError_t  e     = cudaMalloc( ( void** )&im.p, bytes );
-        if( e == cudaSuccess ) e = cudaMemset( im.p, 0, bytes );
+        uint8_t*     mem   = nullptr;
+        cudaError_t  e     = cudaMalloc( ( void** )&mem, bytes );
+        if( e == cudaSuccess )
+        {
+            setImgStorage( im, mem, im.pitch, desc.bpp );
+            d->owned[ i ] = true;
+            e = cudaMemset( mem, 0, bytes );
+        }
         if( e != cudaSuccess )
         {
             AsvgfResult rr = cudaFail( e, "cudaMalloc(image)" );
@@ -462,7 +519,6 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             asvgfDestroy( d );
             return fail( rr, msg );
         }
-        d->owned[ i ] = true;
     }
     *pDenoiser = d;
     return ASVGF_SUCCESS;
@@ -508,7 +564,7 @@ AsvgfResult asvgfBindExternalImage( AsvgfDenoiser d, uint32_t imageIndex, void* 
         cudaFree( im.p );
         d->owned[ imageIndex ] = false;
     }
-    im.p = ( uint8_t* )pDevice; im.pitch = ( uint32_t )pitchBytes;
+    setImgStorage( im, ( uint8_t* )pDevice, ( uint32_t )pitchBytes, desc.bpp );
     return ASVGF_SUCCESS;
 }
 
@@ -558,7 +614,9 @@ AsvgfResult asvgfDenoise( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameInd
     if( r != ASVGF_SUCCESS ) return r;
     DeviceGuard   guard( d->device );
     const Uniform u = makeUniform( *d, *pUniform );
-    for( uint32_t pass = ASVGF_PASS_GRADIENT_ATROUS_0; pass < ASVGF_PASS_ATROUS_0 + d->iterations; pass++ ) // Denoiser.cpp:87-254
+    r = runPass( *d, ( cudaStream_t )stream, frameIndex, u, ASVGF_PASS_GRADIENT_ATROUS_ALL ); // Denoiser.cpp:87-120
+    if( r != ASVGF_SUCCESS ) return r;
+    for( uint32_t pass = ASVGF_PASS_TEMPORAL; pass < ASVGF_PASS_ATROUS_0 + d->iterations; pass++ ) // Denoiser.cpp:87-254
     {
         r = runPass( *d, ( cudaStream_t )stream, frameIndex, u, pass );
         if( r != ASVGF_SUCCESS ) return r;
@@ -588,10 +646,11 @@ const char* asvgfPassName( uint32_t pass )
 {
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return "k_gradient_samples";
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return "k_gradient_atrous";
+    if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL ) return "k_gradient_atrous";
     if( pass == ASVGF_PASS_TEMPORAL ) return "k_temporal";
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return "k_antifirefly";
     if( pass == ASVGF_PASS_VARIANCE ) return "k_variance";
-    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_tiled";
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_pair";
     return "?";
 }
 
@@ -601,6 +660,7 @@ double asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations )
 {
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return 12.8;
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return 1.0;
+    if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL ) return 4.0; // the reference's four dispatches (36 B per gradient pixel)
     if( pass == ASVGF_PASS_TEMPORAL ) return 126.4;
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return 24.0;
     if( pass == ASVGF_PASS_VARIANCE ) return 30.0;

@@ -1,130 +1,159 @@
 // asvgf_atrous_tiled.cuh -- the production a-trous kernel (all iterations), sm_100a.
 //
 // Same arithmetic as CmSVGFAtrous_Iter0.comp:158-335 / CmSVGFAtrous.comp:65-349 (see k_atrous in asvgf_kernels.cuh for
-// the literal form), restructured for the B200 SM, where the literal form is instruction-issue bound (ncu: 2200
-// instructions per pixel, DRAM at 6 % -- profiles/r01_v1_*):
+// the literal form), restructured for the B200 SM, where the pass is instruction-issue bound (ncu: the literal form
+// runs 2200 instructions per pixel with DRAM at 6 %; profiles/r01_v1_*, r01_v2_*):
 //
 //  * DILATED TILE.  For stride s a pixel only ever touches rows y, y+-s.  A CTA therefore owns 64 contiguous columns of
 //    16 rows spaced s apart (rows y0+r, y0+r+s, ...; the s residues r go to s different CTAs).  Its halo is one dilated
 //    row above/below and s columns left/right, so the read amplification is (18/16)*((64+2s)/64) = 1.16..1.41 for
 //    every stride instead of the (1+2s/T)^2 of a square tile, and every global access is still a full-line row segment.
-//  * DECODE ONCE.  Each tile pixel is unpacked once on the way into shared memory: normal through the exact sin/cos
-//    table, E5B9G9R9 -> fp16 triples (every E5 value is exactly representable in fp16), luminance in the oracle's
-//    operation order.  The 8 taps then cost shared-memory loads and converts only.
-//  * WEIGHTS THROUGH ONE LOG.  w_n = (n.n')^128 and the specular lobe (n.n')^P share L = lg2(n.n'):
-//      wBase = k * ex2(128 L - wz^2 log2e),  wDiff = k * ex2(128 L - (wz^2 + wl) log2e),  wSpec = wBase * r * ex2(P L)
-//    i.e. 1 lg2 + 3 ex2 on the MUFU pipe instead of two powf and two expf (~150 FMA-pipe instructions) per tap.
+//  * DECODE ONCE.  Each tile pixel is unpacked once on the way into shared memory -- normal through the exact sin/cos
+//    table, E5B9G9R9 and fp16 to fp32, luminance -- into four float4 planes, so a tap costs four conflict-free
+//    LDS.128 and no conversions.  The stride is a template parameter: every tap address is an immediate offset.
+//  * WEIGHTS THROUGH ONE LOG.  w_n = (n.n')^128 and the specular lobe (n.n')^P share L = lg2(n.n'), and the wavelet
+//    kernel weight / inside-the-render-area test is folded into the exponent (lk = log2 k, or -inf outside):
+//      wBase = ex2(128 L + lk - wz^2 log2e),  wDiff = ex2(128 L + lk - (wz^2 + wl) log2e),  wSpec = r * ex2(. + P L)
+//    i.e. 1 lg2 + 3 ex2 on the MUFU pipe and ~40 FMA-pipe instructions per tap instead of two powf and two expf.
 //    Relative weight error <= ~3e-4 (|P|<=1152 times the 2^-22 absolute error of lg2.approx), inside the 1e-3 output
 //    tolerance because the weights are normalised; integer/boolean outputs do not depend on this kernel.
 #pragma once
 
-#include "asvgf_kernels.cuh"
+#include "asvgf_fast.cuh"
 
 namespace asvgf
 {
 
-constexpr int kAtTileW   = 64;  // columns per CTA
-constexpr int kAtTileH   = 16;  // dilated rows per CTA
-constexpr int kAtThreads = 256; // 4 pixels per thread
-constexpr int kAtBytesPerTilePixel = 16 + 4 + 8 + 8 + 8;
+#ifndef ASVGF_AT_TILE_H
+    #define ASVGF_AT_TILE_H 16
+#endif
+#ifndef ASVGF_AT_THREADS
+    #define ASVGF_AT_THREADS 256
+#endif
+#ifndef ASVGF_AT_MIN_CTAS
+    #define ASVGF_AT_MIN_CTAS 2
+#endif
+constexpr int kAtTileW   = 64;               // columns per CTA
+constexpr int kAtTileH   = ASVGF_AT_TILE_H;  // dilated rows per CTA
+constexpr int kAtThreads = ASVGF_AT_THREADS; // 4 pixels per thread
+constexpr int kAtBytesPerTilePixel = 64;
 
-ASVGF_DEVICE float ex2Approx( float x ) { float r; asm( "ex2.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
+ASVGF_DEVICE float ex2Approx( float x ) { return fex2( x ); }
 // exp2 that keeps denormal results (MUFU.EX2 flushes them): a vanishing weight must stay non-zero exactly as long as
 // the shader's exp() does, because an infinite fp16 variance times a zero weight is NaN but times a denormal weight is inf
 ASVGF_DEVICE float ex2ApproxDenorm( float x )
 {
     const bool  tiny = x < -126.0f;
-    const float r    = ex2Approx( tiny ? x * 0.5f : x );
+    const float r    = fex2( tiny ? x * 0.5f : x );
     return tiny ? r * r : r;
 }
-ASVGF_DEVICE float lg2Approx( float x ) { float r; asm( "lg2.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
-ASVGF_DEVICE float rcpApprox( float x ) { float r; asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
 
-// E5B9G9R9 -> three exact fp16 values packed as (r | g<<16, b)
-ASVGF_DEVICE uint2 e5ToHalf3( uint32_t p )
+// B10G11R11_UFLOAT <-> fp32 through the fp16 bit layout (a uf11 is the top 11 bits of a positive half, a uf10 the top 10)
+ASVGF_DEVICE float3 unpackUfloat111110Fast( uint32_t p )
 {
-    const float3 c = decodeE5( p );
-    const __half2 rg = __floats2half2_rn( c.x, c.y );
-    const __half2 b0 = __floats2half2_rn( c.z, 0.0f );
-    return make_uint2( *reinterpret_cast< const uint32_t* >( &rg ), *reinterpret_cast< const uint32_t* >( &b0 ) );
+    return make_float3( h2f( ( uint16_t )( ( p & 0x7ffu ) << 4 ) ), h2f( ( uint16_t )( ( ( p >> 11 ) & 0x7ffu ) << 4 ) ), h2f( ( uint16_t )( ( p >> 22 ) << 5 ) ) );
 }
-ASVGF_DEVICE float3 half3ToFloat( uint2 v )
+template< uint32_t MBITS > ASVGF_DEVICE uint32_t floatToUfloatFast( float f ) // RTNE; NaN, negatives -> 0; overflow -> max finite
 {
-    const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &v.x ) );
-    const float  b  = __low2float( *reinterpret_cast< const __half2* >( &v.y ) );
-    return make_float3( rg.x, rg.y, b );
+    constexpr uint32_t maxCode = ( 30u << MBITS ) | ( ( 1u << MBITS ) - 1u );
+    constexpr uint32_t drop    = 23u - MBITS;
+    if( !( f > 0.0f ) ) return 0u;
+    if( f < 6.103515625e-05f ) return __float2uint_rn( f * ( float )( 1u << ( 14u + MBITS ) ) ); // below 2^-14: m * 2^(-14-MBITS)
+    const uint32_t x = __float_as_uint( f );
+    const uint32_t r = ( x - 0x38000000u + ( ( 1u << ( drop - 1u ) ) - 1u ) + ( ( x >> drop ) & 1u ) ) >> drop;
+    return min( r, maxCode );
 }
+ASVGF_DEVICE uint32_t packUfloat111110Fast( float3 c ) { return floatToUfloatFast< 6 >( c.x ) | ( floatToUfloatFast< 6 >( c.y ) << 11 ) | ( floatToUfloatFast< 5 >( c.z ) << 22 ); }
 
-template< bool ITER0, bool LAST >
-__global__ void __launch_bounds__( kAtThreads ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
+template< int STEP, bool ITER0, bool LAST >
+__global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
     extern __shared__ __align__( 16 ) uint8_t smemRaw[];
-    const int step = ITER0 ? 1 : ( 1 << a.iteration );
-    const int tw   = kAtTileW + 2 * step; // tile width incl. halo columns
+    constexpr int TW    = kAtTileW + 2 * STEP; // tile width incl. halo columns
     constexpr int TROWS = kAtTileH + 2;
-    const int npx  = tw * TROWS;
-    float4*   sND    = reinterpret_cast< float4* >( smemRaw );               // normal.xyz, (depth half bits << 16 | roughness unorm8)
-    uint2*    sDiff  = reinterpret_cast< uint2* >( sND + npx );              // diffuse rgb + variance, 4 x fp16 as stored
-    uint2*    sSpec  = sDiff + npx;                                          // specular as 3 x fp16
-    uint2*    sIndir = sSpec + npx;                                          // indirect as 3 x fp16
-    float*    sLum   = reinterpret_cast< float* >( sIndir + npx );           // luminance of the diffuse rgb
+    constexpr int NPX   = TW * TROWS;
+    float4* sA = reinterpret_cast< float4* >( smemRaw ); // normal.xyz, depth
+    float4* sB = sA + NPX;                               // diffuse rgb, variance
+    float4* sC = sB + NPX;                               // specular rgb, luminance of the diffuse rgb
+    float4* sD = sC + NPX;                               // indirect rgb, roughness
 
-    // dilated rows: blockIdx.y enumerates (band, residue); row(j) = yBase + j*step, j = -1 .. kAtTileH
-    const int band  = blockIdx.y / step, res = blockIdx.y - band * step;
-    const int yBase = u.yBegin + band * ( kAtTileH * step ) + res;
+    // dilated rows: blockIdx.y enumerates (band, residue); row(j) = yBase + j*STEP, j = -1 .. kAtTileH
+    const int band  = blockIdx.y / STEP, res = blockIdx.y - band * STEP;
+    const int yBase = u.yBegin + band * ( kAtTileH * STEP ) + res;
     const int xBase = blockIdx.x * kAtTileW;
+    const Rows rows = rowsOf( a.depth );
 
-    // ---- stage the tile: unpack every pixel once ----
-    for( int e = threadIdx.x; e < npx; e += kAtThreads )
+    // ---- centre-only inputs of this thread's four pixels: issued first so their latency hides behind the staging ----
+    constexpr int PIX = ( kAtTileW * kAtTileH ) / kAtThreads;
+    uint16_t cGradDepth[ PIX ], cHistLenSpec[ PIX ], cSigma[ PIX ];
+    uint32_t cAlbedo[ PIX ], cSkyMetal[ PIX ];
+    uint2    cThroughput[ PIX ];
+#pragma unroll
+    for( int k = 0; k < PIX; k++ )
     {
-        const int r = e / tw, c = e - r * tw;
-        const int gx = xBase - step + c, gy = yBase + ( r - 1 ) * step;
-        const uint32_t encN  = fetchU32( a.normal, gx, gy );
-        const float3   n     = decodeNormal( a.lut, encN );
-        uint32_t       dbits = 0, rbits = 0;
-        uint2          dv    = make_uint2( 0u, 0u );
-        if( inImage( a.depth, gx, gy ) )
+        const int  p  = threadIdx.x + k * kAtThreads;
+        const int  j  = p / kAtTileW, c = p - j * kAtTileW;
+        const int  px = xBase + c, py = yBase + j * STEP;
+        const bool ok = px < u.W && py < u.yEnd;
+        cGradDepth[ k ]   = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
+        cHistLenSpec[ k ] = ( uint16_t )( ldIf< uint2 >( a.histLen, px, py, ok, make_uint2( 0u, 0u ) ).y & 0xffffu ); // .z of the rgba16f texel
+        if( !ITER0 ) cSigma[ k ] = ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
+        if( LAST )
         {
-            dbits = __ldg( texel< uint16_t >( a.depth, gx, gy ) );
-            rbits = __ldg( texel< uint16_t >( a.metRough, gx, gy ) ) >> 8;
-            dv    = __ldg( texel< uint2 >( a.srcDiff, gx, gy ) );
+            const int sepx = u.W / 2, isOdd = px >= sepx ? 1 : 0;
+            const int regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
+            cAlbedo[ k ]     = ldIf< uint32_t >( a.albedo, regX, py, ok, 0u );
+            cThroughput[ k ] = ldIf< uint2 >( a.throughput, px, py, ok, make_uint2( 0u, 0u ) );
+            cSkyMetal[ k ]   = ( uint32_t )ldIf< uint8_t >( a.isSky, px, py, ok, ( uint8_t )0 ) | ( ( ( uint32_t )ldIf< uint16_t >( a.metRough, px, py, ok, ( uint16_t )0 ) & 0xffu ) << 8 );
         }
-        sND[ e ]    = make_float4( n.x, n.y, n.z, __uint_as_float( ( dbits << 16 ) | rbits ) );
-        sDiff[ e ]  = dv;
-        sSpec[ e ]  = e5ToHalf3( fetchU32( a.srcSpec, gx, gy ) );
-        sIndir[ e ] = e5ToHalf3( fetchU32( a.srcIndir, gx, gy ) );
-        const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dv.x ) );
-        const float  b  = __low2float( *reinterpret_cast< const __half2* >( &dv.y ) );
-        sLum[ e ] = luminance( make_float3( rg.x, rg.y, b ) );
+    }
+
+    // ---- stage the tile: unpack every pixel once (fully unrolled so that all loads are in flight together) ----
+#pragma unroll
+    for( int it = 0; it < ( NPX + kAtThreads - 1 ) / kAtThreads; it++ )
+    {
+        const int e = threadIdx.x + it * kAtThreads;
+        if( e >= NPX ) break;
+        const int  r = e / TW, c = e - r * TW;
+        const int  gx = xBase - STEP + c, gy = yBase + ( r - 1 ) * STEP;
+        const bool ok = rows.in( gx, gy );
+        const uint32_t encN  = ldIf< uint32_t >( a.normal, gx, gy, ok, 0u );
+        const uint32_t dbits = ldIf< uint16_t >( a.depth, gx, gy, ok, ( uint16_t )0 );
+        const uint32_t mr    = ldIf< uint16_t >( a.metRough, gx, gy, ok, ( uint16_t )0 );
+        const uint2    dv    = ldIf< uint2 >( a.srcDiff, gx, gy, ok, make_uint2( 0u, 0u ) );
+        const uint32_t es    = ldIf< uint32_t >( a.srcSpec, gx, gy, ok, 0u );
+        const uint32_t ei    = ldIf< uint32_t >( a.srcIndir, gx, gy, ok, 0u );
+        const float3   n     = decodeNormal( a.lut, encN );
+        const float2   rg    = __half22float2( *reinterpret_cast< const __half2* >( &dv.x ) );
+        const float2   bv    = __half22float2( *reinterpret_cast< const __half2* >( &dv.y ) );
+        const float3   sp    = decodeE5( es ), in = decodeE5( ei );
+        sA[ e ] = make_float4( n.x, n.y, n.z, h2f( ( uint16_t )dbits ) );
+        sB[ e ] = make_float4( rg.x, rg.y, bv.x, bv.y );
+        sC[ e ] = make_float4( sp.x, sp.y, sp.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
+        sD[ e ] = make_float4( in.x, in.y, in.z, unorm8ToFloatFast( mr >> 8 ) );
     }
     __syncthreads();
 
-    const int   sep     = u.W / 2;
+    const int       sep   = u.W / 2;
     constexpr float LOG2E = 1.4426950408889634f;
+    const float     NINF  = __uint_as_float( 0xff800000u );
 
-    for( int k = 0; k < ( kAtTileW * kAtTileH ) / kAtThreads; k++ )
+#pragma unroll
+    for( int k = 0; k < PIX; k++ )
     {
         const int p  = threadIdx.x + k * kAtThreads;
         const int j  = p / kAtTileW, c = p - j * kAtTileW;
-        const int px = xBase + c, py = yBase + j * step;
+        const int px = xBase + c, py = yBase + j * STEP;
         if( px >= u.W || py >= u.yEnd ) continue;
 
-        // checkerboarded render area of this pixel (ShaderCommonGLSLFunc.h:345-358): taps never cross x = W/2
-        const int ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+        const int    ce = ( j + 1 ) * TW + ( c + STEP );
+        const float4 cA = sA[ ce ], cB = sB[ ce ], cC = sC[ ce ], cD = sD[ ce ];
+        float3 outDiff = make_float3( cB.x, cB.y, cB.z ), outSpec = make_float3( cC.x, cC.y, cC.z ), outIndir = make_float3( cD.x, cD.y, cD.z );
+        float  outVariance = cB.w;
 
-        const int    ce  = ( j + 1 ) * tw + ( c + step );
-        const float4 cnd = sND[ ce ];
-        const uint2  cdv = sDiff[ ce ];
-        const float2 crg = __half22float2( *reinterpret_cast< const __half2* >( &cdv.x ) );
-        const float2 cbv = __half22float2( *reinterpret_cast< const __half2* >( &cdv.y ) );
-        float3 outDiff     = make_float3( crg.x, crg.y, cbv.x );
-        float  outVariance = cbv.y;
-        float3 outSpec     = half3ToFloat( sSpec[ ce ] );
-        float3 outIndir    = half3ToFloat( sIndir[ ce ] );
-
-        const uint32_t cw      = __float_as_uint( cnd.w );
-        const float    depth   = h2f( ( uint16_t )( cw >> 16 ) );
-        const bool     invalid = depth < 0.0f || depth > 10000.0f;
+        const float depth     = cA.w;
+        const float roughness = cD.w;
+        const bool  invalid   = depth < 0.0f || depth > 10000.0f;
 
         if( invalid )
         {
@@ -136,137 +165,127 @@ __global__ void __launch_bounds__( kAtThreads ) k_atrous_tiled( const __grid_con
         }
         else
         {
-            const float3 normal    = make_float3( cnd.x, cnd.y, cnd.z );
-            const float  gradDepth = fetchR16F( a.depthGrad, px, py );
-            const float  l         = sLum[ ce ];
+            const float gradDepth = h2f( cGradDepth[ k ] );
+            const float l         = cC.w;
 
             float sigmaL;
-            if( ITER0 ) // Iter0.comp:158-187, exact operation order
+            if( ITER0 ) // Iter0.comp:158-187: 3x3 Gaussian {1/4,1/8,1/16} of the variance (products by powers of two are exact)
             {
                 float r = 0.0f;
 #pragma unroll
                 for( int yy = -1; yy <= 1; yy++ )
 #pragma unroll
                     for( int xx = -1; xx <= 1; xx++ )
-                    {
-                        const uint2 q = sDiff[ ce + yy * tw + xx ];
-                        const float v = __high2float( *reinterpret_cast< const __half2* >( &q.y ) );
-                        const float w = ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f );
-                        r             = addr( r, mulr( v, w ) );
-                    }
-                r = __fsqrt_rn( fmaxf( r, 0.0f ) );
-                storeR16F( a.filteredVariance, px, py, r );
+                        r = fmaf( sB[ ce + yy * TW + xx ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+                r      = __fsqrt_rn( fmaxf( r, 0.0f ) );
+                *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( r );
                 sigmaL = r;
             }
             else
             {
-                sigmaL = fetchR16F( a.filteredVariance, px, py );
+                sigmaL = h2f( cSigma[ k ] );
             }
-            const float kLum = mulr( divr( 1.0f, addr( mulr( 4.0f, sigmaL ), 0.00001f ) ), LOG2E );
+            const float kLum = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
 
-            const float roughness        = unorm8ToFloat( cw & 0xffu );
-            const float wRoughMultiplier = clampf( subr( mulr( roughness, 30.0f ), ( float )a.iteration ), 0.0f, 1.0f );
-            const float historyLengthSpec = fetchRGBA16F( a.histLen, px, py ).z;
-            const float normalWeightScale = clampf( divr( historyLengthSpec, 8.0f ), 0.0f, 1.0f );
-            const float alpha             = mulr( roughness, roughness );
-            float       P                 = fmaxf( 0.01f, subr( divr( 2.0f, addr( mulr( alpha, alpha ), 1e-4f ) ), 2.0f ) );
-            P                             = mulr( clampf( P, 8.0f, 1024.0f ), normalWeightScale );
-            const bool  useP              = P > 0.0f;
-            const float invK1 = rcpApprox( fmaxf( gradDepth, 0.01f ) ), invK2 = rcpApprox( fmaxf( mulr( gradDepth, 2.0f ), 0.01f ) );
+            const float wRoughMultiplier  = saturatef( fmaf( roughness, 30.0f, -( float )a.iteration ) );
+            const float historyLengthSpec = h2f( cHistLenSpec[ k ] );
+            const float alpha             = roughness * roughness;
+            float       P                 = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
+            P                             = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
+            const float invK1 = frcp( fmaxf( gradDepth, 0.01f ) ), invK2 = frcp( fmaxf( gradDepth * 2.0f, 0.01f ) );
+
+            // log2 of the wavelet weight per tap, -inf for taps outside the checkerboarded render area
+            // (ShaderCommonGLSLFunc.h:345-366): taps never cross x = W/2 or leave the frame
+            const int   ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+            const float lkx[ 3 ] = { px - STEP >= ax0 ? -1.0f : NINF, 0.0f, px + STEP < ax1 ? -1.0f : NINF };
+            const float lky[ 3 ] = { py - STEP >= 0 ? -1.0f : NINF, 0.0f, py + STEP < u.H ? -1.0f : NINF };
 
             float weightSum = 1.0f, weightSumSpec = 1.0f, weightSumIndir = 1.0f;
 
 #pragma unroll
             for( int yy = -1; yy <= 1; yy++ )
             {
-                const int  qy   = py + yy * step;
-                const bool yIn  = qy >= 0 && qy < u.H;
 #pragma unroll
                 for( int xx = -1; xx <= 1; xx++ )
                 {
                     if( xx == 0 && yy == 0 ) continue;
-                    const int   qx  = px + xx * step;
-                    const float kf  = ( yIn && qx >= ax0 && qx < ax1 ) ? ( yy == 0 ? 1.0f : 0.5f ) * ( xx == 0 ? 1.0f : 0.5f ) : 0.0f;
-                    const int   qe  = ce + yy * tw + xx * step;
-                    const float4 qnd = sND[ qe ];
-                    const uint2  qdv = sDiff[ qe ];
-                    const float  lQ  = sLum[ qe ];
-                    const float3 specQ  = half3ToFloat( sSpec[ qe ] );
-                    const float3 indirQ = half3ToFloat( sIndir[ qe ] );
+                    const int    qe = ce + yy * TW + xx * STEP;
+                    const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
 
-                    const uint32_t qw     = __float_as_uint( qnd.w );
-                    const float    depthQ = h2f( ( uint16_t )( qw >> 16 ) );
-                    const float    roughQ = ( float )( qw & 0xffu ) * ( 1.0f / 255.0f );
-                    const float2   qrg    = __half22float2( *reinterpret_cast< const __half2* >( &qdv.x ) );
-                    const float2   qbv    = __half22float2( *reinterpret_cast< const __half2* >( &qdv.y ) );
+                    const float nN = fmaxf( 0.0f, fmaf( cA.z, qA.z, fmaf( cA.y, qA.y, cA.x * qA.x ) ) );
+                    const float L  = fmaxf( flg2( nN ), -126.0f );
+                    const float wZ = fabsf( depth - qA.w ) * ( ( xx != 0 && yy != 0 ) ? invK2 : invK1 );
+                    const float e0    = fmaf( 128.0f, L, lkx[ xx + 1 ] + lky[ yy + 1 ] );
+                    const float eBase = fmaf( wZ * -LOG2E, wZ, e0 );
+                    const float eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
+                    const float wBase = fex2( eBase );
+                    const float wDiff = ex2ApproxDenorm( eDiff );
+                    const float rfac  = fmaxf( 0.0f, fmaf( fabsf( roughness - qD.w ), -10.0f, 1.0f ) ) * wRoughMultiplier;
+                    const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
 
-                    const float nN = fmaxf( 0.0f, normal.x * qnd.x + normal.y * qnd.y + normal.z * qnd.z );
-                    const float L  = lg2Approx( nN );
-                    const float wZ = fabsf( depth - depthQ ) * ( ( xx != 0 && yy != 0 ) ? invK2 : invK1 );
-                    const float eBase = 128.0f * L - ( wZ * wZ ) * LOG2E;
-                    const float eDiff = eBase - fabsf( l - lQ ) * kLum;
-                    const float wBase = ex2Approx( eBase ) * kf;
-                    const float wDiff = ex2ApproxDenorm( eDiff ) * kf;
-                    const float rfac  = fmaxf( 0.0f, 1.0f - 10.0f * fabsf( roughness - roughQ ) ) * wRoughMultiplier;
-                    const float wSpec = wBase * rfac * ex2Approx( useP ? P * L : 0.0f );
-
-                    outDiff.x += qrg.x * wDiff; outDiff.y += qrg.y * wDiff; outDiff.z += qbv.x * wDiff;
-                    outSpec.x += specQ.x * wSpec; outSpec.y += specQ.y * wSpec; outSpec.z += specQ.z * wSpec;
-                    outIndir.x += indirQ.x * wBase; outIndir.y += indirQ.y * wBase; outIndir.z += indirQ.z * wBase;
-                    outVariance = fmaf( __fmul_rn( qbv.y, wDiff ), wDiff, outVariance ); // (var*w)*w: inf*denormal stays inf, like the shader
+                    outDiff.x = fmaf( qB.x, wDiff, outDiff.x ); outDiff.y = fmaf( qB.y, wDiff, outDiff.y ); outDiff.z = fmaf( qB.z, wDiff, outDiff.z );
+                    outSpec.x = fmaf( qC.x, wSpec, outSpec.x ); outSpec.y = fmaf( qC.y, wSpec, outSpec.y ); outSpec.z = fmaf( qC.z, wSpec, outSpec.z );
+                    outIndir.x = fmaf( qD.x, wBase, outIndir.x ); outIndir.y = fmaf( qD.y, wBase, outIndir.y ); outIndir.z = fmaf( qD.z, wBase, outIndir.z );
+                    outVariance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, outVariance ); // (var*w)*w: inf*denormal stays inf, like the shader
                     weightSum += wDiff; weightSumSpec += wSpec; weightSumIndir += wBase;
                 }
             }
-            const float inv = divr( 1.0f, weightSum ), invSpec = divr( 1.0f, weightSumSpec ), invIndir = divr( 1.0f, weightSumIndir );
-            outDiff     = outDiff * inv;
-            outVariance = mulr( outVariance, mulr( inv, inv ) );
-            outSpec     = outSpec * invSpec;
-            outIndir    = outIndir * invIndir;
+            const float inv = frcp( weightSum ), invSpec = frcp( weightSumSpec ), invIndir = frcp( weightSumIndir );
+            outDiff     = make_float3( outDiff.x * inv, outDiff.y * inv, outDiff.z * inv );
+            outVariance = outVariance * ( inv * inv );
+            outSpec     = make_float3( outSpec.x * invSpec, outSpec.y * invSpec, outSpec.z * invSpec );
+            outIndir    = make_float3( outIndir.x * invIndir, outIndir.y * invIndir, outIndir.z * invIndir );
         }
 
         if( !LAST )
         {
-            storeRGBA16F( a.dstDiff, px, py, make_float4( outDiff.x, outDiff.y, outDiff.z, outVariance ) );
-            storeU32( a.dstSpec, px, py, encodeE5( outSpec ) );
-            storeU32( a.dstIndir, px, py, encodeE5( outIndir ) );
+            const __half2 o0 = __floats2half2_rn( outDiff.x, outDiff.y ), o1 = __floats2half2_rn( outDiff.z, outVariance );
+            *atW< uint2 >( a.dstDiff, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
+            *atW< uint32_t >( a.dstSpec, px, py )  = encodeE5Fast( outSpec );
+            *atW< uint32_t >( a.dstIndir, px, py ) = encodeE5Fast( outIndir );
             continue;
         }
 
-        // composition, CmSVGFAtrous.comp:278-348 (exact operation order, as in k_atrous)
-        const int2   reg        = regularPixFromCheckerboardPix( u, px, py );
-        float3       albedo     = unpackUfloat111110( fetchU32( a.albedo, reg.x, reg.y ) );
-        const float4 tp4        = fetchRGBA16F( a.throughput, px, py );
-        const float3 throughput = make_float3( tp4.x, tp4.y, tp4.z );
+        // composition, CmSVGFAtrous.comp:278-348
+        const int     isOdd = px >= sep ? 1 : 0;
+        const int     regX  = ( px - isOdd * sep ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
+        float3        albedo = unpackUfloat111110Fast( cAlbedo[ k ] );
+        const uint2   tp     = cThroughput[ k ];
+        const float2  tp01   = __half22float2( *reinterpret_cast< const __half2* >( &tp.x ) );
+        const float3  throughput = make_float3( tp01.x, tp01.y, __low2float( *reinterpret_cast< const __half2* >( &tp.y ) ) );
+        const uint32_t sky   = cSkyMetal[ k ] & 0xffu;
         if( ( u.debugShowFlags & ( 1u << 9 ) ) != 0 ) albedo = make_float3( 1.0f, 1.0f, 1.0f );
 
         float3 illuminated;
-        if( fetchU8( a.isSky, px, py ) == 0u )
+        if( sky == 0u )
         {
-            const float  roughness = unorm8ToFloat( cw & 0xffu );
-            const float  metallic  = fetchRG8( a.metRough, px, py ).x;
-            const float3 specular  = mix3r( outSpec, outIndir, smoothstepr( 0.5f, 0.5f + 0.25f, roughness ) );
-            const float3 roS       = mix3r( make_float3( 0.04f, 0.04f, 0.04f ), albedo, metallic );
-            const float3 roD       = albedo * subr( 1.0f, metallic );
-            illuminated            = ( outDiff + outIndir ) * roD + specular * roS;
-            if( ( u.debugShowFlags & ( 1u << 5 ) ) != 0 ) illuminated = outDiff * albedo;
-            else if( ( u.debugShowFlags & ( 1u << 6 ) ) != 0 ) illuminated = specular * roS;
+            const float metallic = unorm8ToFloatFast( cSkyMetal[ k ] >> 8 );
+            const float t  = saturatef( ( roughness - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
+            const float sm = t * t * ( 3.0f - 2.0f * t );
+            const float3 specular = fmix3( outSpec, outIndir, sm );
+            const float3 roS = fmix3( make_float3( 0.04f, 0.04f, 0.04f ), albedo, metallic ); // BRDF.h:49-53
+            const float  om  = 1.0f - metallic;
+            illuminated = make_float3( fmaf( ( outDiff.x + outIndir.x ) * albedo.x, om, specular.x * roS.x ), fmaf( ( outDiff.y + outIndir.y ) * albedo.y, om, specular.y * roS.y ),
+                                       fmaf( ( outDiff.z + outIndir.z ) * albedo.z, om, specular.z * roS.z ) );
+            if( ( u.debugShowFlags & ( 1u << 5 ) ) != 0 ) illuminated = make_float3( outDiff.x * albedo.x, outDiff.y * albedo.y, outDiff.z * albedo.z );
+            else if( ( u.debugShowFlags & ( 1u << 6 ) ) != 0 ) illuminated = make_float3( specular.x * roS.x, specular.y * roS.y, specular.z * roS.z );
             else if( ( u.debugShowFlags & ( 1u << 7 ) ) != 0 ) illuminated = outIndir;
-            illuminated = illuminated * throughput;
-            const float la = luminance( albedo );
+            const float la = flum( albedo ); // BRDF.h:57-64
             float       ambient = 1.0f;
-            if( !( la > 0.02f ) ) { const float q = divr( subr( la, 0.02f ), 0.02f ); ambient = subr( 1.0f, mulr( q, q ) ); }
-            illuminated = illuminated * ambient;
+            if( !( la > 0.02f ) ) { const float q = ( la - 0.02f ) * 50.0f; ambient = 1.0f - q * q; }
+            illuminated = make_float3( illuminated.x * throughput.x * ambient, illuminated.y * throughput.y * ambient, illuminated.z * throughput.z * ambient );
         }
         else
         {
-            illuminated = albedo * throughput;
+            illuminated = make_float3( albedo.x * throughput.x, albedo.y * throughput.y, albedo.z * throughput.z );
         }
-        storeR16F( a.histogramInput, reg.x, reg.y, fmaxf( 0.0f, luminance( illuminated ) ) );
-        if( ( float )reg.x < mulr( u.lightmapScreenCoverage, u.renderWidth ) ) illuminated = albedo * throughput;
-        storeU32( a.preFinal, reg.x, reg.y, packUfloat111110( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) ) );
+        *atW< uint16_t >( a.histogramInput, regX, py ) = f2h( fmaxf( 0.0f, flum( illuminated ) ) );
+        if( ( float )regX < mulr( u.lightmapScreenCoverage, u.renderWidth ) ) illuminated = make_float3( albedo.x * throughput.x, albedo.y * throughput.y, albedo.z * throughput.z ); // classicShading
+        *atW< uint32_t >( a.preFinal, regX, py ) =
+            packUfloat111110Fast( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) );
     }
 }
 
-inline size_t atrousTiledSmemBytes( int step ) { return ( size_t )( kAtTileW + 2 * step ) * ( kAtTileH + 2 ) * kAtBytesPerTilePixel; }
+constexpr size_t atrousTiledSmemBytes( int step ) { return ( size_t )( kAtTileW + 2 * step ) * ( kAtTileH + 2 ) * kAtBytesPerTilePixel; }
 
 } // namespace asvgf

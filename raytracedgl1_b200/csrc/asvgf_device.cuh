@@ -18,6 +18,8 @@
 namespace asvgf
 {
 
+#define ASVGF_DEVICE_FWD __device__ __forceinline__
+
 // Linear pitched image.  (w,h) is the full frame extent of the image; rows [row0,row0+rows) are stored
 // (a horizontal band plus halo when the frame is split across GPUs, the whole image otherwise).
 struct Img
@@ -26,7 +28,20 @@ struct Img
     uint32_t pitch; // bytes
     int32_t  w, h;
     int32_t  row0, rows;
+    // derived by the host (setImgStorage): lean addressing for the production kernels
+    uint8_t* p0;     // address frame row 0 would have (p - row0*pitch; only dereferenced at stored rows)
+    uint32_t pitchT; // pitch in texels (pitch / bytes per texel)
 };
+
+// texel (x,y) of an image whose texel type is T: one 32-bit multiply-add and one widening add
+template< typename T > ASVGF_DEVICE_FWD const T* at( const Img& im, int x, int y )
+{
+    return reinterpret_cast< const T* >( im.p0 ) + ( uint32_t )( y * ( int )im.pitchT + x );
+}
+template< typename T > ASVGF_DEVICE_FWD T* atW( const Img& im, int x, int y )
+{
+    return reinterpret_cast< T* >( im.p0 ) + ( uint32_t )( y * ( int )im.pitchT + x );
+}
 
 struct Uniform // the members of ShGlobalUniform the path reads (ShaderCommonC.h:209-304), passed by value
 {
@@ -37,6 +52,10 @@ struct Uniform // the members of ShGlobalUniform the path reads (ShaderCommonC.h
     uint32_t debugShowFlags, antiFireflyEnabled;
     int32_t  W, H;         // int(renderWidth), int(renderHeight)
     int32_t  yBegin, yEnd; // rows this launch computes (the owned band)
+    // derived on the host with the same IEEE single operations the shaders use (uniform across the launch)
+    float    halfW, invHalfW, invH; // renderWidth/2, 1/(renderWidth/2), 1/renderHeight  (ShaderCommonGLSLFunc.h:271-277)
+    float    specMinFrames;         // clamp(0.2/timeDelta, 0, 128)                       (CmSVGFTemporalAccumulation.comp:70-74)
+    float    cameraDelta[ 3 ];      // cameraPositionPrev - cameraPosition                 (:60)
 };
 
 struct NormalLut // (sin, cos) of phi_j = j*pi/65535 and theta_k = k*2*pi/65536, correctly rounded fp32

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import layout
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libasvgf.so")
+_LIB_PATH = os.environ.get("ASVGF_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libasvgf.so")  # ASVGF_LIB: A/B builds
 _lib = None
 
 SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND = range(6)

@@ -85,6 +85,7 @@ PASS_TEMPORAL = 5
 PASS_ANTIFIREFLY = 6
 PASS_VARIANCE = 7
 PASS_ATROUS_0 = 8
+PASS_GRADIENT_ATROUS_ALL = 100  # the four gradient a-trous dispatches in one call
 
 
 def image_extent(name_or_index, width, height):

@@ -1,0 +1,167 @@
+"""Band decomposition of one frame across ranks (raytracedgl1_b200/bands.py): plan arithmetic, the pass/exchange
+schedule, and the halo exchange itself over a 2-rank gloo group on CPU tensors.  The GPU leg (needs 2 GPUs) checks that
+a frame denoised as two bands is bit-identical to the single-GPU frame."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from raytracedgl1_b200 import bands, layout
+
+
+def test_band_rows_are_multiples_of_three_and_cover_the_frame():
+    for H in (2160, 4320, 1080, 720, 181):
+        for world in (1, 2, 4, 8):
+            b = bands.band_rows(H, world)
+            assert b[0] == 0 and b[-1] == H and len(b) == world + 1
+            assert all(x % 3 == 0 for x in b[:-1])
+            assert all(b[i + 1] > b[i] for i in range(world))
+    with pytest.raises(ValueError):
+        bands.band_rows(6, 8)
+
+
+def test_plan_rows():
+    p = bands.BandPlan(4320, 8, 3, halo_rows=48)
+    assert p.own == (1620, 2160) and p.stored == (1572, 2208)
+    assert p.gown == (540, 720) and p.gstored == (524, 736)
+    assert p.up == 2 and p.down == 4
+    top = bands.BandPlan(4320, 8, 0, halo_rows=48)
+    assert top.stored[0] == 0 and top.up is None
+    last = bands.BandPlan(2161 - 1, 4, 3, halo_rows=48)
+    assert last.own[1] == 2160 and last.down is None and last.gown[1] == (2160 + 1) // 3
+    with pytest.raises(ValueError):
+        bands.BandPlan(4320, 8, 0, halo_rows=50)
+
+
+def test_schedule_matches_the_dispatch_order_and_reaches():
+    s = bands.frame_schedule(4)
+    passes = [x[1] for x in s if x[0] == "pass"]
+    assert passes == list(range(0, 12))                       # Denoiser.cpp:87-254 after CalculateGradientsSamples
+    # every exchange directly precedes the pass that reads the halo, with that pass's reach
+    ex = {s[i + 1][1]: s[i] for i in range(len(s) - 1) if s[i][0] == "exchange" and s[i + 1][0] == "pass"}
+    assert ex[layout.PASS_GRADIENT_ATROUS_0 + 3][1:] == (["DISPongGradient"], 8, True)
+    assert ex[layout.PASS_ANTIFIREFLY][2] == 2 and ex[layout.PASS_VARIANCE][2] == 1
+    assert ex[layout.PASS_ATROUS_0 + 3][1:] == (["DiffPongColorAndVariance", "SpecPongColor", "IndirPong"], 8, False)
+    assert ex[layout.PASS_ATROUS_0 + 1][1][0] == "DiffColorHistory"
+    s5 = bands.frame_schedule(5)
+    assert [x for x in s5 if x[0] == "exchange"][-1][2] == 16
+    assert bands.physical_name("Normal", 1) == "Normal_Prev" and bands.physical_name("Normal_Prev", 1) == "Normal"
+    assert bands.physical_name("Motion", 1) == "Motion" and bands.physical_name("IndirAccum_Prev", 0) == "IndirAccum_Prev"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, H, pitch, halo, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        full = rng.integers(0, 256, size=(H, pitch), dtype=np.uint8)            # the frame every rank agrees on
+        gfull = rng.integers(0, 256, size=((H + 1) // 3, pitch), dtype=np.uint8)
+        plan = bands.BandPlan(H, world, rank, halo)
+        ok = True
+        for third, ref in ((False, full), (True, gfull)):
+            (o0, o1), (s0, s1) = plan.rows(third)
+            for depth in (1, 2, 8, halo // 3 if third else halo):
+                t = torch.zeros((s1 - s0, pitch), dtype=torch.uint8)
+                t[o0 - s0:o1 - s0] = torch.from_numpy(ref[o0:o1].copy())      # only the owned rows are known
+                bands.exchange_halos([t, t.clone()][:1], depth, plan, third)
+                lo, hi = max(s0, o0 - depth), min(s1, o1 + depth)
+                ok &= bool(np.array_equal(t.numpy()[lo - s0:hi - s0], ref[lo:hi]))
+                # rows beyond the exchanged depth stay untouched (zero)
+                if lo > s0:
+                    ok &= bool((t.numpy()[:lo - s0] == 0).all())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, 360, 64, 48, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def _nccl_worker(rank, world, port, W, H, frames, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        band = bands.BandedDenoiser(W, H, 4, rank=rank, world=world, device=rank, halo_rows=48)
+        whole = bands.BandedDenoiser(W, H, 4, rank=0, world=1, device=rank) if rank == 0 else None
+        ok, detail = True, []
+        for f in range(frames):
+            fi = f & 1
+            g = synth.generate(W, H, f)
+            u = synth.uniform(W, H, f)
+            for name, arr in g.items():
+                band.upload(name, fi, arr)
+                if whole:
+                    whole.upload(name, fi, arr)
+            band.frame(fi, u)
+            if whole:
+                whole.frame(fi, u)
+            torch.cuda.synchronize()
+            for name in ("PreFinal", "HistogramInput", "DiffColorHistory", "AccumHistoryLength", "SpecAccumColor", "IndirAccum",
+                         "DISPingGradient", "GradientPrevPix", "AtrousFilteredVariance"):
+                mine = torch.from_numpy(band.download_own(name, fi).copy()).cuda().view(torch.uint8).flatten()
+                parts = [torch.empty_like(mine) for _ in range(world)] if False else None
+                sizes = torch.tensor([mine.numel()], device="cuda")
+                all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+                dist.all_gather(all_sizes, sizes)
+                mx = int(max(int(s) for s in all_sizes))
+                pad = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+                pad[:mine.numel()] = mine
+                parts = [torch.zeros_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                if rank == 0:
+                    joined = np.concatenate([p[:int(s)].cpu().numpy() for p, s in zip(parts, all_sizes)])
+                    ref = whole.download_own(name, fi).view(np.uint8).flatten()
+                    same = bool(np.array_equal(joined, ref))
+                    ok &= same
+                    if not same:
+                        detail.append((f, name, int((joined != ref).sum())))
+        q.put((rank, ok, detail))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_bands_bit_identical_to_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, 640, 360, 4, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res

@@ -52,6 +52,26 @@ def test_per_pass_parity_from_identical_state(size):
         p.close()
 
 
+def test_literal_kernels_parity():
+    """ASVGF_CREATE_LITERAL_KERNELS: the one-thread-per-pixel kernels that restate the shaders expression by
+    expression stay available for A/B numerics checks; they must agree with the oracle too, and the production
+    kernels must agree with them on the integer outputs."""
+    from raytracedgl1_b200 import denoiser as dn
+    p = Pair(320, 180, flags=dn.CREATE_EXPORT_DEBUG_MASK | dn.CREATE_LITERAL_KERNELS)
+    q = Pair(320, 180)
+    try:
+        for frame in range(4):
+            fi, u = p.run_frame(frame)
+            q.run_frame(frame)
+            res = p.compare(fi)
+            assert_all_ok(res, "literal frame %d %s" % (frame, _summary(res)))
+            for name in ("DebugMask", "GradientPrevPix"):
+                assert np.array_equal(p.cuda.download(name, fi), q.cuda.download(name, fi)), name
+            p.sync_state_to_cuda(); q.sync_state_to_cuda()
+    finally:
+        p.close(); q.close()
+
+
 def test_sequence_parity_locked_and_masks_bit_exact():
     """16-frame sequence with camera motion, moving objects and the light switch (frame 24 is covered by the next
     test).  After every frame the CUDA state is re-locked to the oracle's, so each frame is compared from identical
@@ -103,8 +123,12 @@ def test_light_switch_produces_gradients():
         p.oracle.gradient_samples(fi, u)
         p.cuda.gradient_samples(fi, u)
         got = p.cuda.download("DISPingGradient", fi)
-        assert np.array_equal(got, p.oracle.image("DISPingGradient", fi))
+        ref = p.oracle.image("DISPingGradient", fi)
+        # the chosen stratum slot is an integer output: bit-exact; the unorm8 alphas may differ by one code on a few
+        # texels (colour arithmetic of the production kernel is fast-math, history is free-running here)
         assert np.array_equal(p.cuda.download("GradientPrevPix", fi), p.oracle.image("GradientPrevPix", fi))
+        diff = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= 1 and (diff == 0).mean() >= 0.99
         # alpha_D = |4x - x| / 4x * gradientMultDiffuse(0.5) = 0.375, halved by the zero history -> 48/255
         assert got[..., 0].max() >= 40 and (got[..., 0] >= 40).sum() > 20
     finally:
