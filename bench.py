@@ -216,30 +216,42 @@ def run_ours(args, rank, world, local_rank):
     # (asvgfBindExternalImage = the G-buffer producer handing over its images; no copy).
     seed = synth.DEFAULT_SEED + rank
     n_frames = max(2, args.frames - args.frames % 2)
+    n_host = min(n_frames, 4)                      # frames kept in pinned host memory for the e2e leg
     swappable = {n for n in layout.PRODUCER_IMAGES if n + "_Prev" in layout.IMAGES}
-    host, resident = [], []
+    host, resident, uniforms = [], [], []
+    scratch = None
     for f in range(n_frames):
-        bufs, dev = {}, {}
-        for name in layout.PRODUCER_IMAGES:
-            dtype, shape = layout.image_numpy_shape(name, W, H)
-            t = torch.empty(int(np.prod(shape)) * dtype.itemsize, dtype=torch.uint8, pin_memory=True)
-            bufs[name] = t.numpy().view(dtype).reshape(shape)
-            bufs["_keep_" + name] = t
+        if f < n_host or scratch is None:
+            bufs = {}
+            for name in layout.PRODUCER_IMAGES:
+                dtype, shape = layout.image_numpy_shape(name, W, H)
+                t = torch.empty(int(np.prod(shape)) * dtype.itemsize, dtype=torch.uint8, pin_memory=True)
+                bufs[name] = t.numpy().view(dtype).reshape(shape)
+                bufs["_keep_" + name] = t
+            if f >= n_host:
+                scratch = bufs
+        else:
+            torch.cuda.synchronize()               # the previous frame's copies out of the scratch buffers are done
+            bufs = scratch
         synth.generate(W, H, f, seed, out={k: v for k, v in bufs.items() if not k.startswith("_keep_")})
+        dev = {}
         for name in layout.PRODUCER_IMAGES:
             _, pitch, _, _, rows = d.image(name, 0)
             row_bytes = bufs[name].nbytes // rows
             dt = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
             dt[:, :row_bytes].copy_(bufs["_keep_" + name].view(rows, row_bytes), non_blocking=True)
             dev[name] = (dt, pitch)
-        host.append((bufs, synth.uniform(W, H, f)))
+        if f < n_host:
+            host.append(bufs)
+        uniforms.append(synth.uniform(W, H, f))
         resident.append(dev)
     torch.cuda.synchronize()
-    # two slot-sized staging sets for the e2e leg (host -> device copies land here)
+    # three slot-sized staging sets for the e2e leg (host -> device copies land here; a ring of three lets the upload
+    # of frame i+1 overlap the denoising of frame i, whose "previous" images are frame i-1's set)
     staging = []
-    for fi in (0, 1):
+    for _ in range(3):
         staging.append({name: (torch.zeros_like(resident[0][name][0]), resident[0][name][1]) for name in layout.PRODUCER_IMAGES})
-    h2d_bytes = sum(host[0][0][n].nbytes for n in layout.PRODUCER_IMAGES)
+    h2d_bytes = sum(host[0][n].nbytes for n in layout.PRODUCER_IMAGES)
     out_host = {}
     for name in ("PreFinal", "HistogramInput"):
         dtype, shape = layout.image_numpy_shape(name, W, H)
@@ -247,17 +259,20 @@ def run_ours(args, rank, world, local_rank):
         out_host[name] = (t, t.numpy().view(dtype).reshape(shape))
     d2h_bytes = sum(v[1].nbytes for v in out_host.values())
 
-    def bind(fi, images):
+    def bind(fi, images, prev_images=None):
         """Producer images of frame slot fi := `images` (physical image X for slot 0, X_Prev for slot 1: the
-        reference's cur/prev swap, Framebuffers.cpp:35-50)."""
+        reference's cur/prev swap, Framebuffers.cpp:35-50); optionally the other slot := `prev_images`."""
         for name in layout.PRODUCER_IMAGES:
             t, pitch = images[name]
             d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
+            if prev_images is not None and name in swappable:
+                t, pitch = prev_images[name]
+                d.bind_external(name if fi == 1 else name + "_Prev", t.data_ptr(), pitch)
 
-    def upload(fi, f):
-        bufs, _ = host[f]
+    def upload(fi, f, on=None):
+        bufs = host[f]
         for name in layout.PRODUCER_IMAGES:
-            d.upload(name, fi, bufs[name], stream=sh)
+            d.upload(name, fi, bufs[name], stream=sh if on is None else on)
 
     # the launches of one frame in dispatch order: gradient samples, gradient a-trous x4, temporal, anti-firefly,
     # variance, N a-trous iterations
@@ -265,14 +280,14 @@ def run_ours(args, rank, world, local_rank):
 
     def step_production(i):
         f, fi = i % n_frames, i & 1
-        u = host[f][1]
+        u = uniforms[f]
         bind(fi, resident[f])
         d.gradient_samples(fi, u, stream=sh)      # = PathTracer::CalculateGradientsSamples (image-space part)
         d.denoise(fi, u, stream=sh)               # = Denoiser::Denoise
 
     def step_per_pass(i, events):
         f, fi = i % n_frames, i & 1
-        u = host[f][1]
+        u = uniforms[f]
         bind(fi, resident[f])
         for k, p in enumerate(passes):
             if p == 0:
@@ -316,24 +331,42 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the C ABI with host buffers ----
     e2e_steps = max(3, min(args.steps, 20))
-    i0 = args.warmup + args.steps + pp_steps
-    i0 += i0 & 1
-    bind(0, staging[0]); bind(1, staging[1])
-    for i in range(i0, i0 + 2):
-        f, fi = i % n_frames, i & 1
-        upload(fi, f); d.gradient_samples(fi, host[f][1], stream=sh); d.denoise(fi, host[f][1], stream=sh)
+    # Pipelined the way a caller with host-resident G-buffers would: the upload of frame i+1 (copy stream) overlaps the
+    # denoising of frame i; every step still copies that frame's producer images in and reads its result back.
+    up = torch.cuda.Stream()
+    up_done = [torch.cuda.Event() for _ in range(e2e_steps + 4)]
+    comp_done = [torch.cuda.Event() for _ in range(e2e_steps + 4)]
+
+    def enqueue_upload(i):
+        f, fi = i % n_host, i & 1
+        if i >= 2:
+            up.wait_event(comp_done[i - 2])          # ring set i%3 was frame i-3's, read as "previous" by frame i-2
+        bind(fi, staging[i % 3])
+        upload(fi, f, on=up.cuda_stream)
+        up_done[i].record(up)
+
+    def run_step(i, read_back):
+        f, fi = i % n_host, i & 1
+        stream.wait_event(up_done[i])
+        bind(fi, staging[i % 3], staging[(i - 1) % 3])
+        d.gradient_samples(fi, uniforms[f], stream=sh)
+        d.denoise(fi, uniforms[f], stream=sh)
+        comp_done[i].record(stream)
+        enqueue_upload(i + 1)                        # next frame's copy starts while this frame is being denoised
+        if read_back:
+            for name, (t, arr) in out_host.items():
+                d.download(name, fi, stream=sh, out=arr.ctypes.data)
+            stream.synchronize()                     # the caller consumes the frame's result
+
+    torch.cuda.synchronize()
+    enqueue_upload(0)
+    run_step(0, True); run_step(1, True)             # warm-up (also fills the history)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(i0 + 2, i0 + 2 + e2e_steps):
-        f, fi = i % n_frames, i & 1
-        upload(fi, f)
-        d.gradient_samples(fi, host[f][1], stream=sh)
-        d.denoise(fi, host[f][1], stream=sh)
-        for name, (t, arr) in out_host.items():
-            d.download(name, fi, stream=sh, out=arr.ctypes.data)
-        stream.synchronize()                                   # the caller consumes the frame's result
+    for i in range(2, 2 + e2e_steps):
+        run_step(i, True)
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
@@ -406,7 +439,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frames", type=int, default=8, help="distinct synthetic frames in the cycled sequence (even)")
+    ap.add_argument("--frames", type=int, default=32, help="distinct synthetic frames in the cycled sequence (even)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

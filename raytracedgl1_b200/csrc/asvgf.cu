@@ -165,7 +165,8 @@ struct AsvgfDenoiser_T
     NormalLut lut{};
     bool      haveLut     = false;
     uint64_t  launchCount = 0;
-    bool      atrousPair  = true; // packed-f32x2 a-trous kernel (ASVGF_ATROUS=tiled selects the scalar tiled one, for A/B runs)
+    bool      atrousPair  = false; // ASVGF_ATROUS=pair selects the packed-f32x2 a-trous kernel (measured slower: the pass is smem-pipe bound)
+    int       atrousTilesPerCta = 4; // ASVGF_ATROUS_TILES: tiles one CTA walks with the next tile's loads in flight
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
     {
@@ -345,6 +346,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.albedo = d.get( ASVGF_IMAGE_ALBEDO, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
     a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.histogramInput = d.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
+    a.tilesPerCta = 1;
 
     const int    step = 1 << iteration;
     const bool   pair = d.atrousPair;
@@ -360,7 +362,9 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     // dilated tiles: 64 columns x 16 rows spaced `step` apart; grid.y enumerates (band of 16*step rows, residue)
     const int  rows  = d.ownEnd - d.ownBegin;
     const int  bands = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
-    const dim3 grid( ( unsigned )( ( d.W + kAtTileW - 1 ) / kAtTileW ), ( unsigned )( bands * step ), 1 );
+    const int  tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
+    a.tilesPerCta     = pair ? 1 : d.atrousTilesPerCta;
+    const dim3 grid( ( unsigned )( ( tilesX + a.tilesPerCta - 1 ) / a.tilesPerCta ), ( unsigned )( bands * step ), 1 );
     auto launch = [ & ]( auto kernel ) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
         if( e != cudaSuccess ) return e;
@@ -454,7 +458,8 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     AsvgfDenoiser_T* d = new( std::nothrow ) AsvgfDenoiser_T();
     if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
     d->info = *pInfo; d->device = device;
-    if( const char* e = std::getenv( "ASVGF_ATROUS" ) ) d->atrousPair = std::strcmp( e, "tiled" ) != 0;
+    if( const char* e = std::getenv( "ASVGF_ATROUS" ) ) d->atrousPair = std::strcmp( e, "pair" ) == 0;
+    if( const char* e = std::getenv( "ASVGF_ATROUS_TILES" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 64 ) d->atrousTilesPerCta = n; }
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
@@ -650,7 +655,7 @@ const char* asvgfPassName( uint32_t pass )
     if( pass == ASVGF_PASS_TEMPORAL ) return "k_temporal";
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return "k_antifirefly";
     if( pass == ASVGF_PASS_VARIANCE ) return "k_variance";
-    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_pair";
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_tiled";
     return "?";
 }
 

@@ -65,6 +65,11 @@ template< uint32_t MBITS > ASVGF_DEVICE uint32_t floatToUfloatFast( float f ) //
 }
 ASVGF_DEVICE uint32_t packUfloat111110Fast( float3 c ) { return floatToUfloatFast< 6 >( c.x ) | ( floatToUfloatFast< 6 >( c.y ) << 11 ) | ( floatToUfloatFast< 5 >( c.z ) << 22 ); }
 
+// raw (still packed) texels of one tile pixel and of one output pixel's centre-only inputs: what a thread keeps in
+// registers while the loads of the NEXT tile are in flight behind the arithmetic of the current one
+struct AtrousRaw { uint32_t n, dm, s, i; uint2 d; };                                          // 6 registers
+template< bool ITER0, bool LAST > struct AtrousCentre { uint32_t gh, sigma, albedo, skyMetal; uint2 tp; }; // gh = gradDepth | histLen.z << 16
+
 template< int STEP, bool ITER0, bool LAST >
 __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
@@ -72,67 +77,92 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
     constexpr int TW    = kAtTileW + 2 * STEP; // tile width incl. halo columns
     constexpr int TROWS = kAtTileH + 2;
     constexpr int NPX   = TW * TROWS;
+    constexpr int NIT   = ( NPX + kAtThreads - 1 ) / kAtThreads;
+    constexpr int PIX   = ( kAtTileW * kAtTileH ) / kAtThreads;
     float4* sA = reinterpret_cast< float4* >( smemRaw ); // normal.xyz, depth
     float4* sB = sA + NPX;                               // diffuse rgb, variance
     float4* sC = sB + NPX;                               // specular rgb, luminance of the diffuse rgb
     float4* sD = sC + NPX;                               // indirect rgb, roughness
 
-    // dilated rows: blockIdx.y enumerates (band, residue); row(j) = yBase + j*STEP, j = -1 .. kAtTileH
+    // dilated rows: blockIdx.y enumerates (band, residue); row(j) = yBase + j*STEP, j = -1 .. kAtTileH.
+    // A CTA walks a.tilesPerCta consecutive 64-column tiles of that row set; while it filters tile t from shared
+    // memory, the global loads of tile t+1 are already in flight into registers (software pipeline), so only the first
+    // tile's HBM latency is exposed.
     const int band  = blockIdx.y / STEP, res = blockIdx.y - band * STEP;
     const int yBase = u.yBegin + band * ( kAtTileH * STEP ) + res;
-    const int xBase = blockIdx.x * kAtTileW;
+    const int xFirst = blockIdx.x * a.tilesPerCta * kAtTileW;
     const Rows rows = rowsOf( a.depth );
 
-    // ---- centre-only inputs of this thread's four pixels: issued first so their latency hides behind the staging ----
-    constexpr int PIX = ( kAtTileW * kAtTileH ) / kAtThreads;
-    uint16_t cGradDepth[ PIX ], cHistLenSpec[ PIX ], cSigma[ PIX ];
-    uint32_t cAlbedo[ PIX ], cSkyMetal[ PIX ];
-    uint2    cThroughput[ PIX ];
-#pragma unroll
-    for( int k = 0; k < PIX; k++ )
-    {
-        const int  p  = threadIdx.x + k * kAtThreads;
-        const int  j  = p / kAtTileW, c = p - j * kAtTileW;
-        const int  px = xBase + c, py = yBase + j * STEP;
-        const bool ok = px < u.W && py < u.yEnd;
-        cGradDepth[ k ]   = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
-        cHistLenSpec[ k ] = ( uint16_t )( ldIf< uint2 >( a.histLen, px, py, ok, make_uint2( 0u, 0u ) ).y & 0xffffu ); // .z of the rgba16f texel
-        if( !ITER0 ) cSigma[ k ] = ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
-        if( LAST )
-        {
-            const int sepx = u.W / 2, isOdd = px >= sepx ? 1 : 0;
-            const int regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
-            cAlbedo[ k ]     = ldIf< uint32_t >( a.albedo, regX, py, ok, 0u );
-            cThroughput[ k ] = ldIf< uint2 >( a.throughput, px, py, ok, make_uint2( 0u, 0u ) );
-            cSkyMetal[ k ]   = ( uint32_t )ldIf< uint8_t >( a.isSky, px, py, ok, ( uint8_t )0 ) | ( ( ( uint32_t )ldIf< uint16_t >( a.metRough, px, py, ok, ( uint16_t )0 ) & 0xffu ) << 8 );
-        }
-    }
+    AtrousRaw raw[ NIT ];
+    AtrousCentre< ITER0, LAST > cen[ PIX ], cenNext[ PIX ];
 
-    // ---- stage the tile: unpack every pixel once (fully unrolled so that all loads are in flight together) ----
-#pragma unroll
-    for( int it = 0; it < ( NPX + kAtThreads - 1 ) / kAtThreads; it++ )
+    auto issue = [ & ]( int xBase, AtrousCentre< ITER0, LAST >( &cc )[ PIX ] )
     {
-        const int e = threadIdx.x + it * kAtThreads;
-        if( e >= NPX ) break;
-        const int  r = e / TW, c = e - r * TW;
-        const int  gx = xBase - STEP + c, gy = yBase + ( r - 1 ) * STEP;
-        const bool ok = rows.in( gx, gy );
-        const uint32_t encN  = ldIf< uint32_t >( a.normal, gx, gy, ok, 0u );
-        const uint32_t dbits = ldIf< uint16_t >( a.depth, gx, gy, ok, ( uint16_t )0 );
-        const uint32_t mr    = ldIf< uint16_t >( a.metRough, gx, gy, ok, ( uint16_t )0 );
-        const uint2    dv    = ldIf< uint2 >( a.srcDiff, gx, gy, ok, make_uint2( 0u, 0u ) );
-        const uint32_t es    = ldIf< uint32_t >( a.srcSpec, gx, gy, ok, 0u );
-        const uint32_t ei    = ldIf< uint32_t >( a.srcIndir, gx, gy, ok, 0u );
-        const float3   n     = decodeNormal( a.lut, encN );
-        const float2   rg    = __half22float2( *reinterpret_cast< const __half2* >( &dv.x ) );
-        const float2   bv    = __half22float2( *reinterpret_cast< const __half2* >( &dv.y ) );
-        const float3   sp    = decodeE5( es ), in = decodeE5( ei );
-        sA[ e ] = make_float4( n.x, n.y, n.z, h2f( ( uint16_t )dbits ) );
-        sB[ e ] = make_float4( rg.x, rg.y, bv.x, bv.y );
-        sC[ e ] = make_float4( sp.x, sp.y, sp.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
-        sD[ e ] = make_float4( in.x, in.y, in.z, unorm8ToFloatFast( mr >> 8 ) );
+#pragma unroll
+        for( int k = 0; k < PIX; k++ )
+        {
+            const int  p  = threadIdx.x + k * kAtThreads;
+            const int  j  = p / kAtTileW, c = p - j * kAtTileW;
+            const int  px = xBase + c, py = yBase + j * STEP;
+            const bool ok = px < u.W && py < u.yEnd;
+            cc[ k ].gh = ( uint32_t )ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 ) | ( ldIf< uint2 >( a.histLen, px, py, ok, make_uint2( 0u, 0u ) ).y << 16 );
+            if( !ITER0 ) cc[ k ].sigma = ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
+            if( LAST )
+            {
+                const int sepx = u.W / 2, isOdd = px >= sepx ? 1 : 0;
+                const int regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
+                cc[ k ].albedo   = ldIf< uint32_t >( a.albedo, regX, py, ok, 0u );
+                cc[ k ].tp       = ldIf< uint2 >( a.throughput, px, py, ok, make_uint2( 0u, 0u ) );
+                cc[ k ].skyMetal = ( uint32_t )ldIf< uint8_t >( a.isSky, px, py, ok, ( uint8_t )0 ) | ( ( ( uint32_t )ldIf< uint16_t >( a.metRough, px, py, ok, ( uint16_t )0 ) & 0xffu ) << 8 );
+            }
+        }
+#pragma unroll
+        for( int it = 0; it < NIT; it++ )
+        {
+            const int  e = threadIdx.x + it * kAtThreads;
+            const int  r = e / TW, c = e - r * TW;
+            const int  gx = xBase - STEP + c, gy = yBase + ( r - 1 ) * STEP;
+            const bool ok = e < NPX && rows.in( gx, gy );
+            raw[ it ].n  = ldIf< uint32_t >( a.normal, gx, gy, ok, 0u );
+            raw[ it ].dm = ( uint32_t )ldIf< uint16_t >( a.depth, gx, gy, ok, ( uint16_t )0 ) | ( ( uint32_t )ldIf< uint16_t >( a.metRough, gx, gy, ok, ( uint16_t )0 ) << 16 );
+            raw[ it ].d  = ldIf< uint2 >( a.srcDiff, gx, gy, ok, make_uint2( 0u, 0u ) );
+            raw[ it ].s  = ldIf< uint32_t >( a.srcSpec, gx, gy, ok, 0u );
+            raw[ it ].i  = ldIf< uint32_t >( a.srcIndir, gx, gy, ok, 0u );
+        }
+    };
+    // unpack every tile pixel once into the four float4 planes
+    auto commit = [ & ]()
+    {
+#pragma unroll
+        for( int it = 0; it < NIT; it++ )
+        {
+            const int e = threadIdx.x + it * kAtThreads;
+            if( e >= NPX ) break;
+            const float3 n  = decodeNormal( a.lut, raw[ it ].n );
+            const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &raw[ it ].d.x ) );
+            const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &raw[ it ].d.y ) );
+            const float3 sp = decodeE5( raw[ it ].s ), in = decodeE5( raw[ it ].i );
+            sA[ e ] = make_float4( n.x, n.y, n.z, h2f( ( uint16_t )( raw[ it ].dm & 0xffffu ) ) );
+            sB[ e ] = make_float4( rg.x, rg.y, bv.x, bv.y );
+            sC[ e ] = make_float4( sp.x, sp.y, sp.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
+            sD[ e ] = make_float4( in.x, in.y, in.z, unorm8ToFloatFast( raw[ it ].dm >> 24 ) );
+        }
+    };
+
+    issue( xFirst, cen );
+  for( int t = 0; t < a.tilesPerCta; t++ )
+  {
+    const int xBase = xFirst + t * kAtTileW;
+    if( xBase >= u.W ) break;
+    if( t > 0 )
+    {
+        __syncthreads(); // every warp is done reading the previous tile
+#pragma unroll
+        for( int k = 0; k < PIX; k++ ) cen[ k ] = cenNext[ k ];
     }
+    commit();
     __syncthreads();
+    if( t + 1 < a.tilesPerCta && xBase + kAtTileW < u.W ) issue( xBase + kAtTileW, cenNext ); // in flight during the arithmetic below
 
     const int       sep   = u.W / 2;
     constexpr float LOG2E = 1.4426950408889634f;
@@ -165,7 +195,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         }
         else
         {
-            const float gradDepth = h2f( cGradDepth[ k ] );
+            const float gradDepth = h2f( ( uint16_t )( cen[ k ].gh & 0xffffu ) );
             const float l         = cC.w;
 
             float sigmaL;
@@ -183,12 +213,12 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             }
             else
             {
-                sigmaL = h2f( cSigma[ k ] );
+                sigmaL = h2f( ( uint16_t )cen[ k ].sigma );
             }
             const float kLum = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
 
             const float wRoughMultiplier  = saturatef( fmaf( roughness, 30.0f, -( float )a.iteration ) );
-            const float historyLengthSpec = h2f( cHistLenSpec[ k ] );
+            const float historyLengthSpec = h2f( ( uint16_t )( cen[ k ].gh >> 16 ) );
             const float alpha             = roughness * roughness;
             float       P                 = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
             P                             = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
@@ -249,17 +279,17 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         // composition, CmSVGFAtrous.comp:278-348
         const int     isOdd = px >= sep ? 1 : 0;
         const int     regX  = ( px - isOdd * sep ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
-        float3        albedo = unpackUfloat111110Fast( cAlbedo[ k ] );
-        const uint2   tp     = cThroughput[ k ];
+        float3        albedo = unpackUfloat111110Fast( cen[ k ].albedo );
+        const uint2   tp     = cen[ k ].tp;
         const float2  tp01   = __half22float2( *reinterpret_cast< const __half2* >( &tp.x ) );
         const float3  throughput = make_float3( tp01.x, tp01.y, __low2float( *reinterpret_cast< const __half2* >( &tp.y ) ) );
-        const uint32_t sky   = cSkyMetal[ k ] & 0xffu;
+        const uint32_t sky   = cen[ k ].skyMetal & 0xffu;
         if( ( u.debugShowFlags & ( 1u << 9 ) ) != 0 ) albedo = make_float3( 1.0f, 1.0f, 1.0f );
 
         float3 illuminated;
         if( sky == 0u )
         {
-            const float metallic = unorm8ToFloatFast( cSkyMetal[ k ] >> 8 );
+            const float metallic = unorm8ToFloatFast( cen[ k ].skyMetal >> 8 );
             const float t  = saturatef( ( roughness - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
             const float sm = t * t * ( 3.0f - 2.0f * t );
             const float3 specular = fmix3( outSpec, outIndir, sm );
@@ -284,6 +314,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         *atW< uint32_t >( a.preFinal, regX, py ) =
             packUfloat111110Fast( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) );
     }
+  } // tiles of this CTA
 }
 
 constexpr size_t atrousTiledSmemBytes( int step ) { return ( size_t )( kAtTileW + 2 * step ) * ( kAtTileH + 2 ) * kAtBytesPerTilePixel; }

@@ -130,25 +130,32 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples_fast( c
         const int cx = gx * S + k % 3, cy = gy * S + k / 3;
         mv[ k ] = ldIf< uint2 >( a.motion, cx, cy, full.in( cx, cy ), make_uint2( 0u, 0u ) );
     }
+    // reprojected positions of all nine candidates, then all nine luminance gathers in flight together
+    int      ppx[ 9 ], ppy[ 9 ];
+    uint32_t lum[ 9 ];
+#pragma unroll
+    for( int k = 0; k < 9; k++ )
+    {
+        const int    cx = gx * S + k % 3, cy = gy * S + k / 3;
+        const float2 m  = __half22float2( *reinterpret_cast< const __half2* >( &mv[ k ].x ) );
+        const float  fx = mulr( addr( mulr( addr( ( float )cx, 0.5f ), u.invHalfW ), m.x ), u.halfW );
+        const float  fy = mulr( addr( mulr( addr( ( float )cy, 0.5f ), u.invH ), m.y ), u.renderHeight );
+        ppx[ k ] = f2i( floorf( fx ) ); ppy[ k ] = f2i( floorf( fy ) );
+        lum[ k ] = ldIf< uint32_t >( a.gradientInputsPrev, ppx[ k ], ppy[ k ], ( uint32_t )k != prevStrataPos && full.in( ppx[ k ], ppy[ k ] ), 0u );
+    }
     int      prevX = 0, prevY = 0, curX = 0, curY = 0;
     uint32_t curStrataPos = 0;
     float2   prevLum = make_float2( 0.0f, 0.0f );
     float    prevMax = 0.0f;
 #pragma unroll
-    for( int k = 0; k < 9; k++ )
+    for( int k = 0; k < 9; k++ ) // :75-94, candidates in slot order; last frame's slot is skipped
     {
         if( ( uint32_t )k == prevStrataPos ) continue;
-        const int    cx = gx * S + k % 3, cy = gy * S + k / 3;
-        const float2 m  = __half22float2( *reinterpret_cast< const __half2* >( &mv[ k ].x ) );
-        const float  ppx = mulr( addr( mulr( addr( ( float )cx, 0.5f ), u.invHalfW ), m.x ), u.halfW );
-        const float  ppy = mulr( addr( mulr( addr( ( float )cy, 0.5f ), u.invH ), m.y ), u.renderHeight );
-        const int    px = f2i( floorf( ppx ) ), py = f2i( floorf( ppy ) );
-        const uint32_t raw = ldIf< uint32_t >( a.gradientInputsPrev, px, py, full.in( px, py ), 0u );
-        const float2 pl = __half22float2( *reinterpret_cast< const __half2* >( &raw ) );
+        const float2 pl = __half22float2( *reinterpret_cast< const __half2* >( &lum[ k ] ) );
         const float  pm = fmaxf( pl.x, pl.y );
         if( pm > prevMax )
         {
-            prevX = px; prevY = py; curX = cx; curY = cy;
+            prevX = ppx[ k ]; prevY = ppy[ k ]; curX = gx * S + k % 3; curY = gy * S + k / 3;
             curStrataPos = ( uint32_t )k;
             prevLum = pl; prevMax = pm;
         }
@@ -290,7 +297,10 @@ ASVGF_DEVICE float specAccumSpeedFast( float minFrames, float Amax, float roughn
     return clampf( 256.0f * f, minFrames, Amax );
 }
 
-__global__ void __launch_bounds__( kBlockW* kBlockH, 3 ) k_temporal_fast( const __grid_constant__ TemporalArgs a, const __grid_constant__ Uniform u )
+#ifndef ASVGF_T_MIN_CTAS
+    #define ASVGF_T_MIN_CTAS 4 // 64 registers (100 B of spills): measured 0.485 ms vs 0.523 (3 CTAs, 80 regs) vs 0.602 (2 CTAs)
+#endif
+__global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_temporal_fast( const __grid_constant__ TemporalArgs a, const __grid_constant__ Uniform u )
 {
     const int px = blockIdx.x * kBlockW + threadIdx.x;
     const int py = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;

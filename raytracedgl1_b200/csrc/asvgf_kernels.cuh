@@ -525,6 +525,7 @@ struct AtrousArgs
     Img       albedo, throughput, isSky, preFinal, histogramInput;
     NormalLut lut;
     int32_t   iteration;
+    int32_t   tilesPerCta; // production kernels: consecutive 64-column tiles one CTA walks (software pipeline)
 };
 
 template< bool ITER0, bool LAST >
