@@ -31,9 +31,26 @@ WORKLOADS = {
     "4k-n5": (3840, 2160, 5, "3840x2160 synthetic G-buffer, full chain with 5 a-trous iterations (BASELINE config 3)"),
     "1080p": (1920, 1080, 4, "1920x1080 synthetic G-buffer, full chain, 4 a-trous iterations"),
     "720p": (1280, 720, 4, "1280x720 synthetic G-buffer, full chain, 4 a-trous iterations"),
+    # BASELINE config 4: ONE frame split into horizontal bands across the ranks (strong scaling, halo exchange per pass)
+    "8k-bands": (7680, 4320, 4, "7680x4320 synthetic G-buffer, full A-SVGF chain (4 a-trous iterations), one frame split into "
+                                "horizontal bands across the GPUs with per-pass halo exchange over NCCL/NVLink"),
+    "4k-bands": (3840, 2160, 4, "3840x2160 synthetic G-buffer, full chain, one frame split into horizontal bands across the GPUs"),
 }
 METRIC = "asvgf_denoise_throughput"
 UNIT = "Mpixel/s"
+
+
+def measured_traffic(kernel, W, H, N):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/); None when no capture exists for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic_4k.json")) as f:
+            t = json.load(f)
+        if (W, H, N) == (3840, 2160, 4):
+            return t["kernels"][kernel]["bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
 
 
 def measured_peak_gbs():
@@ -414,7 +431,9 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom[0], "launches_per_step": dom[1]["launches"],
-                         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+                         "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
+                         "traffic": measured_traffic(dom[0], W, H, N),
+                         "algorithmic_bytes_per_launch": dom[1]["bytes"] / dom[1]["launches"],
                          "peak_source": peak_src,
                          "chain": {"achieved": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9,
                                    "frac": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9 / peak,
@@ -428,6 +447,100 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     d.close()
     if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_bands(args, rank, world, local_rank):
+    """One frame per step, split into `world` horizontal bands (raytracedgl1_b200/bands.py).  value = frame pixels x
+    steps / time (strong scaling); every rank holds its band + 48-row halo of a short cycled sequence in HBM."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import synth
+    from raytracedgl1_b200 import bands, layout
+    from raytracedgl1_b200 import denoiser as dn
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H, N, desc = WORKLOADS[args.workload]
+    bd = bands.BandedDenoiser(W, H, N, rank=rank, world=world, device=local_rank, halo_rows=48)
+    s0, s1 = bd.plan.stored if world > 1 else (0, H)
+    n_frames = max(2, min(args.frames, 8) // 2 * 2)
+    swappable = {n for n in layout.PRODUCER_IMAGES if n + "_Prev" in layout.IMAGES}
+    resident, uniforms = [], []
+    for f in range(n_frames):
+        g = synth.generate_rows(W, H, f, s0, s1)
+        dev = {}
+        for name in layout.PRODUCER_IMAGES:
+            _, pitch, _, _, rows = bd.d.image(name, 0)
+            a = g[name]
+            row_bytes = a.nbytes // rows
+            dt = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
+            dt[:, :row_bytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(rows, row_bytes)))
+            dev[name] = (dt, pitch)
+        resident.append(dev)
+        uniforms.append(synth.uniform(W, H, f))
+
+    def step(i):
+        f, fi = i % n_frames, i & 1
+        for name in layout.PRODUCER_IMAGES:
+            t, pitch = resident[f][name]
+            bd.d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
+        bd.frame(fi, uniforms[f])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = bd.d.launch_count
+    sampler.start() if sampler.ok else None
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = bd.d.launch_count - launches0
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln)
+        launches = int(ln[0])
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        frame_ms = total_ms / args.steps
+        chain_bpp = dn.chain_bytes_per_pixel(N)
+        gbs = chain_bpp * W * H / (frame_ms * 1e-3) / 1e9
+        exchanges = [x for x in bd.schedule if x[0] == "exchange"]
+        line = {
+            "metric": METRIC, "value": W * H * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": W, "height": H, "atrous_iterations": N,
+                       "parallelism": "%d horizontal bands (rows multiple of 3), 48-row halo, %d neighbour exchanges per frame "
+                                      "(torch.distributed batch_isend_irecv, NCCL)" % (world, len(exchanges) if world > 1 else 0),
+                       "sequence": "%d consecutive synthetic frames, cycled" % n_frames,
+                       "l2": "no flush: the frame's images exceed the 126 MB L2", "algorithmic_bytes_per_px": chain_bpp},
+            "clocks": clocks, "e2e": None, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "whole chain", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
+                         "frac": gbs / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    bd.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
@@ -450,6 +563,9 @@ def main():
         return
     if world == 1 and args.gpus > 1:
         raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
+    if args.workload.endswith("-bands"):
+        run_bands(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 

@@ -166,7 +166,7 @@ struct AsvgfDenoiser_T
     bool      haveLut     = false;
     uint64_t  launchCount = 0;
     bool      atrousPair  = false; // ASVGF_ATROUS=pair selects the packed-f32x2 a-trous kernel (measured slower: the pass is smem-pipe bound)
-    int       atrousTilesPerCta = 4; // ASVGF_ATROUS_TILES: tiles one CTA walks with the next tile's loads in flight
+    int       atrousTilesPerCta = 1; // ASVGF_ATROUS_TILES: tiles one CTA walks with the next tile's loads in flight (measured: 1, 2, 4 equal; 8+ slower)
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
     {

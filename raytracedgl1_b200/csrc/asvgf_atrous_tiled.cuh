@@ -67,8 +67,9 @@ ASVGF_DEVICE uint32_t packUfloat111110Fast( float3 c ) { return floatToUfloatFas
 
 // raw (still packed) texels of one tile pixel and of one output pixel's centre-only inputs: what a thread keeps in
 // registers while the loads of the NEXT tile are in flight behind the arithmetic of the current one
-struct AtrousRaw { uint32_t n, dm, s, i; uint2 d; };                                          // 6 registers
-template< bool ITER0, bool LAST > struct AtrousCentre { uint32_t gh, sigma, albedo, skyMetal; uint2 tp; }; // gh = gradDepth | histLen.z << 16
+// (no arithmetic may touch a loaded value before the tile is committed: a use would stall the thread on the load)
+struct AtrousRaw { uint32_t n, s, i; uint2 d; uint16_t depth, mr; };
+template< bool ITER0, bool LAST > struct AtrousCentre { uint2 histLen, tp; uint32_t albedo; uint16_t gradDepth, sigma, metRough; uint8_t sky; };
 
 template< int STEP, bool ITER0, bool LAST >
 __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             const int  j  = p / kAtTileW, c = p - j * kAtTileW;
             const int  px = xBase + c, py = yBase + j * STEP;
             const bool ok = px < u.W && py < u.yEnd;
-            cc[ k ].gh = ( uint32_t )ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 ) | ( ldIf< uint2 >( a.histLen, px, py, ok, make_uint2( 0u, 0u ) ).y << 16 );
+            cc[ k ].gradDepth = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
+            cc[ k ].histLen   = ldIf< uint2 >( a.histLen, px, py, ok, make_uint2( 0u, 0u ) );
             if( !ITER0 ) cc[ k ].sigma = ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
             if( LAST )
             {
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
                 const int regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
                 cc[ k ].albedo   = ldIf< uint32_t >( a.albedo, regX, py, ok, 0u );
                 cc[ k ].tp       = ldIf< uint2 >( a.throughput, px, py, ok, make_uint2( 0u, 0u ) );
-                cc[ k ].skyMetal = ( uint32_t )ldIf< uint8_t >( a.isSky, px, py, ok, ( uint8_t )0 ) | ( ( ( uint32_t )ldIf< uint16_t >( a.metRough, px, py, ok, ( uint16_t )0 ) & 0xffu ) << 8 );
+                cc[ k ].sky      = ldIf< uint8_t >( a.isSky, px, py, ok, ( uint8_t )0 );
+                cc[ k ].metRough = ldIf< uint16_t >( a.metRough, px, py, ok, ( uint16_t )0 );
             }
         }
 #pragma unroll
@@ -124,7 +127,8 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             const int  gx = xBase - STEP + c, gy = yBase + ( r - 1 ) * STEP;
             const bool ok = e < NPX && rows.in( gx, gy );
             raw[ it ].n  = ldIf< uint32_t >( a.normal, gx, gy, ok, 0u );
-            raw[ it ].dm = ( uint32_t )ldIf< uint16_t >( a.depth, gx, gy, ok, ( uint16_t )0 ) | ( ( uint32_t )ldIf< uint16_t >( a.metRough, gx, gy, ok, ( uint16_t )0 ) << 16 );
+            raw[ it ].depth = ldIf< uint16_t >( a.depth, gx, gy, ok, ( uint16_t )0 );
+            raw[ it ].mr    = ldIf< uint16_t >( a.metRough, gx, gy, ok, ( uint16_t )0 );
             raw[ it ].d  = ldIf< uint2 >( a.srcDiff, gx, gy, ok, make_uint2( 0u, 0u ) );
             raw[ it ].s  = ldIf< uint32_t >( a.srcSpec, gx, gy, ok, 0u );
             raw[ it ].i  = ldIf< uint32_t >( a.srcIndir, gx, gy, ok, 0u );
@@ -142,10 +146,10 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &raw[ it ].d.x ) );
             const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &raw[ it ].d.y ) );
             const float3 sp = decodeE5( raw[ it ].s ), in = decodeE5( raw[ it ].i );
-            sA[ e ] = make_float4( n.x, n.y, n.z, h2f( ( uint16_t )( raw[ it ].dm & 0xffffu ) ) );
+            sA[ e ] = make_float4( n.x, n.y, n.z, h2f( raw[ it ].depth ) );
             sB[ e ] = make_float4( rg.x, rg.y, bv.x, bv.y );
             sC[ e ] = make_float4( sp.x, sp.y, sp.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
-            sD[ e ] = make_float4( in.x, in.y, in.z, unorm8ToFloatFast( raw[ it ].dm >> 24 ) );
+            sD[ e ] = make_float4( in.x, in.y, in.z, unorm8ToFloatFast( ( uint32_t )raw[ it ].mr >> 8 ) );
         }
     };
 
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         }
         else
         {
-            const float gradDepth = h2f( ( uint16_t )( cen[ k ].gh & 0xffffu ) );
+            const float gradDepth = h2f( cen[ k ].gradDepth );
             const float l         = cC.w;
 
             float sigmaL;
@@ -213,12 +217,12 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             }
             else
             {
-                sigmaL = h2f( ( uint16_t )cen[ k ].sigma );
+                sigmaL = h2f( cen[ k ].sigma );
             }
             const float kLum = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
 
             const float wRoughMultiplier  = saturatef( fmaf( roughness, 30.0f, -( float )a.iteration ) );
-            const float historyLengthSpec = h2f( ( uint16_t )( cen[ k ].gh >> 16 ) );
+            const float historyLengthSpec = __low2float( *reinterpret_cast< const __half2* >( &cen[ k ].histLen.y ) );
             const float alpha             = roughness * roughness;
             float       P                 = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
             P                             = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
@@ -283,13 +287,13 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         const uint2   tp     = cen[ k ].tp;
         const float2  tp01   = __half22float2( *reinterpret_cast< const __half2* >( &tp.x ) );
         const float3  throughput = make_float3( tp01.x, tp01.y, __low2float( *reinterpret_cast< const __half2* >( &tp.y ) ) );
-        const uint32_t sky   = cen[ k ].skyMetal & 0xffu;
+        const uint32_t sky   = cen[ k ].sky;
         if( ( u.debugShowFlags & ( 1u << 9 ) ) != 0 ) albedo = make_float3( 1.0f, 1.0f, 1.0f );
 
         float3 illuminated;
         if( sky == 0u )
         {
-            const float metallic = unorm8ToFloatFast( cen[ k ].skyMetal >> 8 );
+            const float metallic = unorm8ToFloatFast( ( uint32_t )cen[ k ].metRough & 0xffu );
             const float t  = saturatef( ( roughness - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
             const float sm = t * t * ( 3.0f - 2.0f * t );
             const float3 specular = fmix3( outSpec, outIndir, sm );

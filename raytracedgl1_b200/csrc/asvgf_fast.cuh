@@ -297,6 +297,9 @@ ASVGF_DEVICE float specAccumSpeedFast( float minFrames, float Amax, float roughn
     return clampf( 256.0f * f, minFrames, Amax );
 }
 
+#ifndef ASVGF_T_EAGER_HISTORY
+    #define ASVGF_T_EAGER_HISTORY 0
+#endif
 #ifndef ASVGF_T_MIN_CTAS
     #define ASVGF_T_MIN_CTAS 4 // 64 registers (100 B of spills): measured 0.485 ms vs 0.523 (3 CTAs, 80 regs) vs 0.602 (2 CTAs)
 #endif
@@ -349,11 +352,27 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
     const float bw[ 4 ] = { mulr( subr( 1.0f, subX ), subr( 1.0f, subY ) ), mulr( subX, subr( 1.0f, subY ) ),
                             mulr( subr( 1.0f, subX ), subY ), mulr( subX, subY ) };
 
-    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal );
-
-    // ---- history fetches of the consistent taps (all in flight together) ----
+    // ---- history fetches ----
     uint2    hDiff[ 4 ], hLen[ 4 ];
     uint32_t hMom[ 4 ], hSpec[ 4 ], hInd[ 4 ];
+#if ASVGF_T_EAGER_HISTORY
+    // issued for every tap inside the render area BEFORE the consistency tests: one serial memory round trip less
+    // (the tests need depth/normal of the same texels, then the sin/cos table); inconsistent taps are loaded in vain
+#pragma unroll
+    for( int t = 0; t < 4; t++ )
+    {
+        const int  x = pixPrevX + ( t & 1 ), y = pixPrevY + ( t >> 1 );
+        const bool ok = y >= 0 && y < u.H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
+        hDiff[ t ] = ldIf< uint2 >( a.diffHistory, x, y, ok, make_uint2( 0u, 0u ) );
+        hMom[ t ]  = ldIf< uint32_t >( a.momentsPrev, x, y, ok, 0u );
+        hLen[ t ]  = ldIf< uint2 >( a.histLenPrev, x, y, ok, make_uint2( 0u, 0u ) );
+        hSpec[ t ] = ldIf< uint32_t >( a.specPrev, x, y, ok, 0u );
+        hInd[ t ]  = ldIf< uint32_t >( a.indirPrev, x, y, ok, 0u );
+    }
+    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal );
+#else
+    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal );
+    // of the consistent taps only (all in flight together)
 #pragma unroll
     for( int t = 0; t < 4; t++ )
     {
@@ -365,6 +384,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
         hSpec[ t ] = ldIf< uint32_t >( a.specPrev, x, y, ok, 0u );
         hInd[ t ]  = ldIf< uint32_t >( a.indirPrev, x, y, ok, 0u );
     }
+#endif
     const bool   sppOk = rows.in( pixPrevX, pixPrevY );
     const float4 spp4  = ldIf< float4 >( a.surfPosPrev, pixPrevX, pixPrevY, sppOk, make_float4( 0.0f, 0.0f, 0.0f, 0.0f ) );
 

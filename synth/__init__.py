@@ -31,6 +31,8 @@ def lib():
                                             ctypes.c_uint32]
         L.asvgfSynthGenerate.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                          ctypes.POINTER(ctypes.c_void_p)]
+        L.asvgfSynthGenerateRows.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.c_uint32]
         _lib = L
     return _lib
 
@@ -53,4 +55,17 @@ def generate(width, height, frame, seed=DEFAULT_SEED, out=None):
         arrays[name] = a
         ptrs[layout.INDEX[name]] = a.ctypes.data
     lib().asvgfSynthGenerate(width, height, frame, seed, ptrs)
+    return arrays
+
+
+def generate_rows(width, height, frame, y0, y1, seed=DEFAULT_SEED):
+    """Rows [y0, y1) of every producer image of `frame` (what one rank of the band mode stores: band + halo)."""
+    arrays = {}
+    ptrs = (ctypes.c_void_p * layout.IMAGE_COUNT)()
+    for name in layout.PRODUCER_IMAGES:
+        dtype, shape = layout.image_numpy_shape(name, width, height)
+        a = np.zeros((y1 - y0,) + tuple(shape[1:]), dtype=dtype)
+        arrays[name] = a
+        ptrs[layout.INDEX[name]] = a.ctypes.data
+    lib().asvgfSynthGenerateRows(width, height, frame, seed, ptrs, y0, y1)
     return arrays

@@ -320,7 +320,8 @@ void asvgfSynthFillUniform( AsvgfGlobalUniform* u, uint32_t W, uint32_t H, uint3
 // images[i] = tightly packed host buffer for image index i (asvgf_layout.h) or NULL to skip.  Fills the INPUTS of
 // frame `frame`: Albedo, IsSky, Normal, MetallicRoughness, DepthWorld, DepthGrad, Motion, Unfiltered{Direct,Specular,
 // Indir}, SurfacePosition, ViewDirection, Throughput, GradientInputs, FwdLum.
-void asvgfSynthGenerate( uint32_t W, uint32_t H, uint32_t frame, uint32_t seed, void** images )
+// Rows [y0,y1) only: images[i] then holds just those rows (a band plus its halo, for the multi-GPU band mode).
+void asvgfSynthGenerateRows( uint32_t W, uint32_t H, uint32_t frame, uint32_t seed, void** images, uint32_t y0, uint32_t y1 )
 {
     Out o; for( int i = 0; i < ASVGF_IMAGE_COUNT; i++ ) o.p[ i ] = ( uint8_t* )images[ i ];
     const Camera cur = cameraAt( ( int )frame ), prev = cameraAt( ( int )frame - 1 );
@@ -329,13 +330,13 @@ void asvgfSynthGenerate( uint32_t W, uint32_t H, uint32_t frame, uint32_t seed, 
     const int    iW = ( int )W, iH = ( int )H;
 
 #pragma omp parallel for schedule( dynamic, 4 )
-    for( int cy = 0; cy < iH; cy++ )
+    for( int cy = ( int )y0; cy < ( int )y1; cy++ )
     {
         for( int cx = 0; cx < iW; cx++ )
         {
-            const size_t idx = ( size_t )cy * W + cx;
+            const size_t idx = ( size_t )( cy - ( int )y0 ) * W + cx;
             int x, y; reg( cx, cy, iW, x, y );
-            const size_t ridx = ( size_t )y * W + x;
+            const size_t ridx = ( size_t )( y - ( int )y0 ) * W + x;
             Shaded s = shade( cx, cy, iW, iH, frame, frame, seed );
             const Hit& h = s.h;
 
@@ -415,6 +416,11 @@ void asvgfSynthGenerate( uint32_t W, uint32_t H, uint32_t frame, uint32_t seed, 
             }
         }
     }
+}
+
+void asvgfSynthGenerate( uint32_t W, uint32_t H, uint32_t frame, uint32_t seed, void** images )
+{
+    asvgfSynthGenerateRows( W, H, frame, seed, images, 0, H );
 }
 
 } // extern "C"

@@ -165,3 +165,30 @@ def test_two_bands_bit_identical_to_single_gpu():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
+
+
+@pytest.mark.gpu
+def test_banded_denoiser_single_rank_equals_plain_denoiser():
+    """world = 1: the per-pass schedule over externally bound (torch) images must give exactly what
+    asvgfGradientSamples + asvgfDenoise give on library-owned images."""
+    import synth
+    from raytracedgl1_b200 import denoiser as dn
+    W, H = 192, 108
+    b = bands.BandedDenoiser(W, H, 4, rank=0, world=1, device=0)
+    d = dn.Denoiser(W, H, 4)
+    try:
+        for f in range(3):
+            fi = f & 1
+            g = synth.generate(W, H, f)
+            u = synth.uniform(W, H, f)
+            for name, arr in g.items():
+                b.upload(name, fi, arr)
+                d.upload(name, fi, arr)
+            b.frame(fi, u)
+            d.gradient_samples(fi, u)
+            d.denoise(fi, u)
+            d.synchronize()
+            for name in ("PreFinal", "HistogramInput", "DiffColorHistory", "GradientPrevPix", "DISPingGradient", "SpecAccumColor"):
+                assert np.array_equal(b.download_own(name, fi), d.download(name, fi)), (f, name)
+    finally:
+        b.close(); d.close()
