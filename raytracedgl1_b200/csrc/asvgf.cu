@@ -9,6 +9,7 @@
 #include "asvgf_fast.cuh"
 #include "asvgf_atrous_tiled.cuh"
 #include "asvgf_atrous_pair.cuh"
+#include "asvgf_atrous_ws.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -166,6 +167,10 @@ struct AsvgfDenoiser_T
     bool      haveLut     = false;
     uint64_t  launchCount = 0;
     bool      atrousPair  = false; // ASVGF_ATROUS=pair selects the packed-f32x2 a-trous kernel (measured slower: the pass is smem-pipe bound)
+    // a-trous kernel: 0 = k_atrous_t2 (vectorised staging + pair filter, one tile per CTA), 1 = k_atrous_ws (same, warp-specialised
+    // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop); ASVGF_ATROUS=t2|ws|tiled|pair
+    int       atrousMode  = 0;
+    int       smCount     = 0;
     int       atrousTilesPerCta = 1; // ASVGF_ATROUS_TILES: tiles one CTA walks with the next tile's loads in flight (measured: 1, 2, 4 equal; 8+ slower)
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
@@ -359,8 +364,75 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         else k_atrous< false, false ><<< grid, kBlock, 0, s >>>( a, u );
         return launchCheck( d, "k_atrous" );
     }
-    // dilated tiles: 64 columns x 16 rows spaced `step` apart; grid.y enumerates (band of 16*step rows, residue)
     const int  rows  = d.ownEnd - d.ownBegin;
+    // the warp-specialised kernel moves four pixels per load: it needs W % 4 == 0 and 16-byte aligned rows
+    auto vec16 = [ & ]( const Img& im ) { return ( ( uintptr_t )im.p % 16 ) == 0 && ( im.pitch % 16 ) == 0; };
+    const bool wsOk = ( d.W % 4 ) == 0 && step <= 32 && vec16( a.normal ) && vec16( a.depth ) && vec16( a.metRough ) && vec16( a.srcDiff ) && vec16( a.srcSpec ) &&
+                      vec16( a.srcIndir ) && vec16( a.depthGrad ) && vec16( a.filteredVariance ) && vec16( a.histLen );
+    if( d.atrousMode == 0 && !pair && wsOk )
+    {
+        const int    th      = atrousWsTileH( step );
+        const int    rowSets = ( ( rows + th * step - 1 ) / ( th * step ) ) * step;
+        const int    tilesX  = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
+        const size_t smemT2  = atrousT2SmemBytes( step );
+        const dim3   grid( ( unsigned )tilesX, ( unsigned )rowSets, 1 );
+        auto launchT2 = [ & ]( auto kernel ) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smemT2 );
+            if( e != cudaSuccess ) return e;
+            kernel<<< grid, kT2Threads, smemT2, s >>>( a, u );
+            return cudaSuccess;
+        };
+        cudaError_t e = cudaErrorInvalidValue;
+#define ASVGF_T2_CASE( S ) \
+    case S: e = last ? launchT2( k_atrous_t2< S, false, true > ) : launchT2( k_atrous_t2< S, false, false > ); break;
+        switch( step )
+        {
+            case 1: e = launchT2( k_atrous_t2< 1, true, false > ); break; // iteration 0 is never the last
+            ASVGF_T2_CASE( 2 )
+            ASVGF_T2_CASE( 4 )
+            ASVGF_T2_CASE( 8 )
+            ASVGF_T2_CASE( 16 )
+            ASVGF_T2_CASE( 32 )
+            default: break;
+        }
+#undef ASVGF_T2_CASE
+        if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_t2)" );
+        return launchCheck( d, "k_atrous_t2" );
+    }
+    if( d.atrousMode == 1 && !pair && wsOk )
+    {
+        // warp-specialised persistent kernel: one CTA per SM walks the dilated tiles round-robin
+        const int    th      = atrousWsTileH( step );
+        const int    rowSets = ( ( rows + th * step - 1 ) / ( th * step ) ) * step;
+        const int    tilesX  = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
+        const size_t smemWs  = atrousWsSmemBytes( step );
+        a.tilesPerCta        = rowSets;
+        const int nTiles     = tilesX * rowSets;
+        const dim3 grid( ( unsigned )( nTiles < d.smCount ? nTiles : d.smCount ), 1, 1 );
+        auto launchWs = [ & ]( auto kernel ) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smemWs );
+            if( e != cudaSuccess ) return e;
+            kernel<<< grid, kWsThreads, smemWs, s >>>( a, u );
+            return cudaSuccess;
+        };
+        cudaError_t e = cudaErrorInvalidValue;
+#define ASVGF_WS_CASE( S ) \
+    case S: e = last ? launchWs( k_atrous_ws< S, false, true > ) : launchWs( k_atrous_ws< S, false, false > ); break;
+        switch( step )
+        {
+            case 1: e = launchWs( k_atrous_ws< 1, true, false > ); break; // iteration 0 is never the last
+            ASVGF_WS_CASE( 2 )
+            ASVGF_WS_CASE( 4 )
+            ASVGF_WS_CASE( 8 )
+            ASVGF_WS_CASE( 16 )
+            ASVGF_WS_CASE( 32 )
+            default: break;
+        }
+#undef ASVGF_WS_CASE
+        if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_ws)" );
+        return launchCheck( d, "k_atrous_ws" );
+    }
+    // dilated tiles: 64 columns x 16 rows spaced `step` apart; grid.y enumerates (band of 16*step rows, residue)
     const int  bands = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
     const int  tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
     a.tilesPerCta     = pair ? 1 : d.atrousTilesPerCta;
@@ -458,7 +530,11 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     AsvgfDenoiser_T* d = new( std::nothrow ) AsvgfDenoiser_T();
     if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
     d->info = *pInfo; d->device = device;
-    if( const char* e = std::getenv( "ASVGF_ATROUS" ) ) d->atrousPair = std::strcmp( e, "pair" ) == 0;
+    if( const char* e = std::getenv( "ASVGF_ATROUS" ) )
+    {
+        d->atrousPair = std::strcmp( e, "pair" ) == 0;
+        d->atrousMode = std::strcmp( e, "ws" ) == 0 ? 1 : std::strcmp( e, "t2" ) == 0 ? 0 : 2;
+    }
     if( const char* e = std::getenv( "ASVGF_ATROUS_TILES" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 64 ) d->atrousTilesPerCta = n; }
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
@@ -494,6 +570,8 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     AsvgfResult r = acquireLut( device, &d->lut );
     if( r != ASVGF_SUCCESS ) { delete d; return r; }
     d->haveLut = true;
+    if( cudaDeviceGetAttribute( &d->smCount, cudaDevAttrMultiProcessorCount, device ) != cudaSuccess || d->smCount <= 0 ) d->smCount = 148;
+    if( const char* e = std::getenv( "ASVGF_WS_CTAS" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 4096 ) d->smCount = n; }
 
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
     {

@@ -52,6 +52,32 @@ def test_per_pass_parity_from_identical_state(size):
         p.close()
 
 
+@pytest.mark.parametrize("variant", ["t2", "ws", "tiled", "pair"])
+def test_atrous_kernel_variants(variant, monkeypatch):
+    """Every a-trous kernel the library can select (ASVGF_ATROUS, read by asvgfCreate): the default one-tile-per-CTA
+    pair filter (t2), the warp-specialised persistent kernel (ws), the scalar tiled kernel and the packed-f32x2 one.
+    Per-pass parity of the four a-trous iterations plus a 5-iteration handle (stride 16 tile geometry)."""
+    monkeypatch.setenv("ASVGF_ATROUS", variant)
+    for W, H, iters in ((320, 180, 4), (512, 288, 5)):
+        p = Pair(W, H, iterations=iters)
+        try:
+            for frame in range(3):
+                fi = frame & 1
+                u = p.feed_inputs(frame, fi)
+                for ps in range(0, 8 + iters):
+                    p.sync_state_to_cuda()
+                    p.oracle.run_pass(ps, fi, u)
+                    p.cuda.denoise_pass(ps, fi, u)
+                    p.cuda.synchronize()
+                    if ps < 8:
+                        continue
+                    names = ["PreFinal", "HistogramInput"] if ps == 7 + iters else None
+                    res = p.compare(fi, names, whole_frame=False) if names else p.compare(fi, whole_frame=False)
+                    assert_all_ok(res, "%s %dx%d frame %d pass %d %s" % (variant, W, H, frame, ps, _summary(res)))
+        finally:
+            p.close()
+
+
 def test_literal_kernels_parity():
     """ASVGF_CREATE_LITERAL_KERNELS: the one-thread-per-pixel kernels that restate the shaders expression by
     expression stay available for A/B numerics checks; they must agree with the oracle too, and the production
