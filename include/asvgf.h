@@ -130,6 +130,33 @@ ASVGF_API AsvgfResult asvgfDenoise( AsvgfDenoiser denoiser, AsvgfStream stream, 
 ASVGF_API AsvgfResult asvgfDenoisePass( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                         const AsvgfGlobalUniform* pUniform, uint32_t pass );
 
+/* ---- the two dispatches that consume the denoiser's outputs right after it ---- */
+
+/* = ImageComposition::PrepareForRaster -> ProcessCheckerboard (Source/ImageComposition.cpp:87-92, 157-222), shader
+   CmCheckerboard.comp:43-78 restricted to the denoiser's own image: ASVGF_IMAGE_PRE_FINAL -> ASVGF_IMAGE_FINAL, with
+   the cross-shaped resolve where ASVGF_IMAGE_THROUGHPUT.a marks a split (reflect/refract) pixel.  The shader's two
+   other image pairs (ScreenEmisRT, AcidFogRT) belong to the rasteriser / fog producers and are not part of this
+   library.  Enqueues only. */
+ASVGF_API AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                                const AsvgfGlobalUniform* pUniform );
+
+/* = Tonemapping::CalculateExposure (Source/Tonemapping.cpp:59-175): the 256-bin log-luminance histogram of
+   ASVGF_IMAGE_HISTOGRAM_INPUT (CmLuminanceHistogram.comp:41-86) followed by the eye-adaptation update of
+   AsvgfTonemapping.avgLuminance, which also clears the histogram for the next frame (CmLuminanceAvg.comp:37-89).
+   Band handles histogram their owned rows only.  Enqueues only. */
+ASVGF_API AsvgfResult asvgfCalculateExposure( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                              const AsvgfGlobalUniform* pUniform );
+/* The two dispatches of asvgfCalculateExposure separately (parity tests look at the histogram in between). */
+ASVGF_API AsvgfResult asvgfLuminanceHistogram( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                               const AsvgfGlobalUniform* pUniform );
+ASVGF_API AsvgfResult asvgfLuminanceAverage( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                             const AsvgfGlobalUniform* pUniform );
+/* Device address of the handle's AsvgfTonemapping (= the reference's tonemapping buffer, Tonemapping.cpp:183-191; zero-initialised here),
+   and host copies of it enqueued on `stream`. */
+ASVGF_API AsvgfResult asvgfGetTonemappingBuffer( AsvgfDenoiser denoiser, void** ppDevice );
+ASVGF_API AsvgfResult asvgfUploadTonemapping( AsvgfDenoiser denoiser, AsvgfStream stream, const AsvgfTonemapping* pHost );
+ASVGF_API AsvgfResult asvgfDownloadTonemapping( AsvgfDenoiser denoiser, AsvgfStream stream, AsvgfTonemapping* pHost );
+
 /* Blocks the host until everything enqueued on `stream` has finished (= waiting for the frame fence,
    Source/VulkanDevice.cpp:791-796).  Surfaces asynchronous kernel faults as ASVGF_CUDA_ERROR. */
 ASVGF_API AsvgfResult asvgfSynchronize( AsvgfDenoiser denoiser, AsvgfStream stream );

@@ -42,6 +42,8 @@ enum AsvgfImageIndex
     ASVGF_IMAGE_VIEW_DIRECTION               = 18, /* R16G16B16A16_SFLOAT                         */
     ASVGF_IMAGE_THROUGHPUT                   = 20, /* R16G16B16A16_SFLOAT                         */
     ASVGF_IMAGE_PRE_FINAL                    = 21, /* B10G11R11_UFLOAT, regular layout  (OUTPUT)  */
+    ASVGF_IMAGE_FINAL                        = 22, /* B10G11R11_UFLOAT, regular layout: PreFinal after the checkerboard resolve
+                                                      (CmCheckerboard.comp; written by asvgfResolveCheckerboard)           */
     ASVGF_IMAGE_ACCUM_HISTORY_LENGTH         = 27, /* R16G16B16A16_SFLOAT                         */
     ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV    = 28,
     ASVGF_IMAGE_DIFF_TEMPORARY               = 29, /* E5                                          */
@@ -125,7 +127,11 @@ typedef struct AsvgfGlobalUniform
     float    renderHeight;         /*  656 */
     uint32_t frameId;              /*  660 */
     float    timeDelta;            /*  664 */
-    uint32_t _reserved2[ 13 ];     /*  668 */
+    float    minLogLuminance;      /*  668  exposure histogram range (CmLuminanceHistogram.comp, CmLuminanceAvg.comp) */
+    float    maxLogLuminance;      /*  672 */
+    float    luminanceWhitePoint;  /*  676  (not read by this library) */
+    uint32_t stopEyeAdaptation;    /*  680 */
+    uint32_t _reserved2[ 9 ];      /*  684 */
     float    cameraPosition[ 4 ];  /*  720 */
     float    cameraPositionPrev[ 4 ]; /* 736 */
     uint32_t debugShowFlags;       /*  752 */
@@ -141,9 +147,20 @@ typedef struct AsvgfGlobalUniform
     uint32_t _reserved6[ 276 ];    /*  992 */
 } AsvgfGlobalUniform;              /* 2096 */
 
+/* Byte-compatible with ShTonemapping (ShaderCommonC.h:344-348): the exposure state asvgfCalculateExposure keeps. */
+#define ASVGF_LUM_HISTOGRAM_BIN_COUNT 256 /* COMPUTE_LUM_HISTOGRAM_BIN_COUNT, ShaderCommonC.h:138 */
+typedef struct AsvgfTonemapping
+{
+    uint32_t histogram[ ASVGF_LUM_HISTOGRAM_BIN_COUNT ];
+    float    avgLuminance;
+} AsvgfTonemapping;
+
 #ifdef __cplusplus
 }
 static_assert( sizeof( AsvgfGlobalUniform ) == 2096, "must match ShGlobalUniform" );
+static_assert( offsetof( AsvgfGlobalUniform, minLogLuminance ) == 668, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, stopEyeAdaptation ) == 680, "layout" );
+static_assert( sizeof( AsvgfTonemapping ) == 1028, "must match ShTonemapping" );
 static_assert( offsetof( AsvgfGlobalUniform, viewPrev ) == 128, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, projectionPrev ) == 320, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, lightmapScreenCoverage ) == 644, "layout" );

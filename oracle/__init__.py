@@ -42,6 +42,13 @@ def lib():
         L.asvgfOracleRunPass.argtypes = [vp, u32, u32, ctypes.POINTER(layout.GlobalUniform)]
         L.asvgfOracleGradientSamples.argtypes = [vp, u32, ctypes.POINTER(layout.GlobalUniform)]
         L.asvgfOracleDenoise.argtypes = [vp, u32, ctypes.POINTER(layout.GlobalUniform)]
+        puni = ctypes.POINTER(layout.GlobalUniform)
+        L.asvgfOracleResolveCheckerboard.argtypes = [vp, u32, puni]
+        L.asvgfOracleLuminanceHistogram.argtypes = [vp, u32, puni]
+        L.asvgfOracleLuminanceAverage.argtypes = [vp, puni]
+        L.asvgfOracleCalculateExposure.argtypes = [vp, u32, puni]
+        L.asvgfOracleGetTonemapping.argtypes = [vp]
+        L.asvgfOracleGetTonemapping.restype = ctypes.POINTER(layout.Tonemapping)
         L.asvgfOracleEncodeE5B9G9R9.restype = u32
         L.asvgfOracleEncodeE5B9G9R9.argtypes = [f32, f32, f32]
         L.asvgfOracleDecodeE5B9G9R9.argtypes = [u32, ctypes.POINTER(f32)]
@@ -104,6 +111,23 @@ class Oracle:
 
     def denoise(self, frame_index, uniform):
         lib().asvgfOracleDenoise(self._h, frame_index, ctypes.byref(uniform))
+
+    def resolve_checkerboard(self, frame_index, uniform):
+        lib().asvgfOracleResolveCheckerboard(self._h, frame_index, ctypes.byref(uniform))
+
+    def luminance_histogram(self, frame_index, uniform):
+        lib().asvgfOracleLuminanceHistogram(self._h, frame_index, ctypes.byref(uniform))
+
+    def luminance_average(self, uniform):
+        lib().asvgfOracleLuminanceAverage(self._h, ctypes.byref(uniform))
+
+    def calculate_exposure(self, frame_index, uniform):
+        lib().asvgfOracleCalculateExposure(self._h, frame_index, ctypes.byref(uniform))
+
+    @property
+    def tonemapping(self):
+        """The oracle's own AsvgfTonemapping (a live ctypes view: histogram[256], avgLuminance)."""
+        return lib().asvgfOracleGetTonemapping(self._h).contents
 
 
 def set_threads(n):

@@ -393,6 +393,7 @@ struct AsvgfOracle_T
 {
     uint32_t W = 0, H = 0, iterations = 4;
     Img      img[ ASVGF_IMAGE_COUNT ];
+    AsvgfTonemapping tm = {}; // the reference's tonemapping buffer (ShTonemapping, Tonemapping.cpp:183-191)
 
     // Framebuffers.cpp:35-50: images with a _PREV twin are addressed as (index + frameIndex) / (index - frameIndex)
     static int swapKind( uint32_t i ) // 0 none, 1 = cur of a pair, 2 = prev of a pair
@@ -438,7 +439,7 @@ int bytesPerPixelOf( uint32_t i )
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: return 16;
         case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV:
         case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR: case ASVGF_IMAGE_UNFILTERED_INDIR:
-        case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR:
+        case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR:
         case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV:
         case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR:
         case ASVGF_IMAGE_SPEC_PONG_COLOR: case ASVGF_IMAGE_INDIR_ACCUM: case ASVGF_IMAGE_INDIR_ACCUM_PREV:
@@ -1209,6 +1210,81 @@ void atrous( AsvgfOracle_T& o, uint32_t fi, const Ctx& c, uint32_t iteration )
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Checkerboard resolve of the denoiser's output, CmCheckerboard.comp:43-78 (PreFinal -> Final; the shader's two other
+// image pairs, ScreenEmisRT and AcidFogRT, come from other producers and are outside this path)
+// ---------------------------------------------------------------------------------------------------------------
+void resolveCheckerboard( AsvgfOracle_T& o, uint32_t fi, const Ctx& c )
+{
+    Img& preFinal   = o.get( ASVGF_IMAGE_PRE_FINAL, fi );
+    Img& throughput = o.get( ASVGF_IMAGE_THROUGHPUT, fi );
+    Img& final_     = o.get( ASVGF_IMAGE_FINAL, fi );
+    const int sep   = getCheckerboardSeparatorX( c );
+#pragma omp parallel for schedule( static )
+    for( int y = 0; y < c.H; y++ )
+    {
+        for( int x = 0; x < c.W; x++ )
+        {
+            const ivec2 pix = { x, y };
+            const ivec2 cb  = getCheckerboardPix( c, pix );                    // :55
+            vec3        hdr = unpackUfloat111110( fetchU32( preFinal, pix ) ); // :62
+            if( fetchRGBA16F( throughput, cb ).w > 0.5f )                      // needResolveCheckerboard, ShaderCommonGLSLFunc.h:434-444
+            {
+                const float fl = ( cb.x == 0 || cb.x == sep ) ? 0.0f : 1.0f;               // !isLeftOutOfBounds  :29-34
+                const float fr = ( cb.x == sep || cb.x == ( int )c.u->renderWidth ) ? 0.0f : 1.0f; // !isRightOutOfBounds :36-41
+                const vec3 l = unpackUfloat111110( fetchU32( preFinal, { x - 1, y } ) ), r = unpackUfloat111110( fetchU32( preFinal, { x + 1, y } ) );
+                const vec3 d = unpackUfloat111110( fetchU32( preFinal, { x, y + 1 } ) ), t = unpackUfloat111110( fetchU32( preFinal, { x, y - 1 } ) );
+                auto cross = [ & ]( float vl, float vr, float vd, float vt ) { return 0.25f * vl * fl + 0.25f * vr * fr + 0.25f * vd + 0.25f * vt; }; // :45-49
+                const vec3 k = { cross( l.x, r.x, d.x, t.x ), cross( l.y, r.y, d.y, t.y ), cross( l.z, r.z, d.z, t.z ) };
+                hdr          = mix3( hdr, k, 0.5f );                           // :51
+            }
+            storeU32( final_, pix, packUfloat111110( hdr ) );                  // :73
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exposure: CmLuminanceHistogram.comp:38-86 and CmLuminanceAvg.comp:37-89 (Tonemapping.cpp:59-175).
+// Pin: log2 / exp2 / exp, whose GLSL precision is implementation-defined, are the correctly rounded fp32 values
+// (evaluated in double, rounded once) -- the same convention as the sin/cos of the normal codec.
+// ---------------------------------------------------------------------------------------------------------------
+uint32_t getColorBin( float inputLum, float minLogLuminance, float maxLogLuminance ) // CmLuminanceHistogram.comp:38-55
+{
+    const float inverseLogLuminanceRange = 1.0f / ( maxLogLuminance - minLogLuminance );
+    if( inputLum < 0.001f ) return 0; // LUMINANCE_EPS
+    const float lg           = ( float )std::log2( ( double )inputLum );
+    const float logLuminance = fminf( fmaxf( ( lg - minLogLuminance ) * inverseLogLuminanceRange, 0.0f ), 1.0f ); // clamp; NaN -> 0 (pinned)
+    return ( uint32_t )f2i( logLuminance * 254.0f + 1.0f );
+}
+void luminanceHistogram( AsvgfOracle_T& o, uint32_t fi, const Ctx& c )
+{
+    Img& in = o.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
+    for( int y = 0; y < c.H; y++ )
+        for( int x = 0; x < c.W; x++ ) o.tm.histogram[ getColorBin( fetchR16F( in, { x, y } ), c.u->minLogLuminance, c.u->maxLogLuminance ) ]++;
+}
+void luminanceAverage( AsvgfOracle_T& o, const Ctx& c )
+{
+    uint32_t       finalWeightedCount = 0;
+    const uint32_t countInBin0        = o.tm.histogram[ 0 ];
+    for( uint32_t i = 0; i < ASVGF_LUM_HISTOGRAM_BIN_COUNT; i++ )
+    {
+        finalWeightedCount += o.tm.histogram[ i ] * i; // :43-59 (uint arithmetic; the tree reduction is order-independent)
+        o.tm.histogram[ i ] = 0;                       // :48, for the next frame
+    }
+    if( c.u->stopEyeAdaptation != 0 ) return;          // :64-67
+    const float minLogLuminance = c.u->minLogLuminance, maxLogLuminance = c.u->maxLogLuminance;
+    const float logLuminanceRange = maxLogLuminance - minLogLuminance;
+    const float pixelCount        = c.u->renderWidth * c.u->renderHeight;
+    const float blackPixelCount   = ( float )countInBin0;
+    const float weightedLogAverage   = ( ( float )finalWeightedCount / fmaxf( pixelCount - blackPixelCount, 1.0f ) ) - 1.0f;
+    const float weightedAvgLuminance = ( float )std::exp2( ( double )( weightedLogAverage / 254.0f * logLuminanceRange + minLogLuminance ) );
+    const float lastFrameLuminance   = o.tm.avgLuminance;
+    const float tau = 1.1f;
+    const float t   = 1.0f - ( float )std::exp( ( double )( -c.u->timeDelta * tau ) );
+    const float adaptedLuminance = lastFrameLuminance + ( weightedAvgLuminance - lastFrameLuminance ) * t;
+    o.tm.avgLuminance = fminf( adaptedLuminance, ( float )std::exp2( ( double )maxLogLuminance ) );
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1262,6 +1338,7 @@ int asvgfOracleGetImage( AsvgfOracle o, uint32_t index, uint32_t frameIndex, voi
 void asvgfOracleResetHistory( AsvgfOracle o )
 {
     for( auto& im : o->img ) std::fill( im.d.begin(), im.d.end(), 0 );
+    o->tm = AsvgfTonemapping{};
 }
 
 void asvgfOracleRunPass( AsvgfOracle o, uint32_t pass, uint32_t frameIndex, const AsvgfGlobalUniform* u )
@@ -1282,6 +1359,28 @@ void asvgfOracleDenoise( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUn
 {
     for( uint32_t p = 1; p < 8 + o->iterations; p++ ) asvgfOracleRunPass( o, p, frameIndex, u );
 }
+
+void asvgfOracleResolveCheckerboard( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u ) // ImageComposition.cpp:157-222
+{
+    Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };
+    resolveCheckerboard( *o, frameIndex, c );
+}
+void asvgfOracleLuminanceHistogram( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u )
+{
+    Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };
+    luminanceHistogram( *o, frameIndex, c );
+}
+void asvgfOracleLuminanceAverage( AsvgfOracle o, const AsvgfGlobalUniform* u )
+{
+    Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };
+    luminanceAverage( *o, c );
+}
+void asvgfOracleCalculateExposure( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u ) // Tonemapping.cpp:59-175
+{
+    asvgfOracleLuminanceHistogram( o, frameIndex, u );
+    asvgfOracleLuminanceAverage( o, u );
+}
+AsvgfTonemapping* asvgfOracleGetTonemapping( AsvgfOracle o ) { return &o->tm; }
 
 uint32_t asvgfOracleEncodeE5B9G9R9( float r, float g, float b ) { return encodeE5B9G9R9( { r, g, b } ); }
 void     asvgfOracleDecodeE5B9G9R9( uint32_t p, float* rgb ) { vec3 v = decodeE5B9G9R9( p ); rgb[ 0 ] = v.x; rgb[ 1 ] = v.y; rgb[ 2 ] = v.z; }

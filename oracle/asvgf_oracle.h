@@ -36,6 +36,14 @@ void asvgfOracleRunPass( AsvgfOracle o, uint32_t pass, uint32_t frameIndex, cons
 void asvgfOracleGradientSamples( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
 void asvgfOracleDenoise( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
 
+/* the two dispatches after the denoiser: CmCheckerboard.comp (PreFinal -> Final) and
+   CmLuminanceHistogram.comp + CmLuminanceAvg.comp on the oracle's own AsvgfTonemapping state */
+void asvgfOracleResolveCheckerboard( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
+void asvgfOracleLuminanceHistogram( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
+void asvgfOracleLuminanceAverage( AsvgfOracle o, const AsvgfGlobalUniform* u );
+void asvgfOracleCalculateExposure( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
+AsvgfTonemapping* asvgfOracleGetTonemapping( AsvgfOracle o );
+
 /* helper primitives exposed for unit tests */
 uint32_t asvgfOracleEncodeE5B9G9R9( float r, float g, float b );
 void     asvgfOracleDecodeE5B9G9R9( uint32_t packed, float* rgb );

@@ -10,6 +10,7 @@
 #include "asvgf_atrous_tiled.cuh"
 #include "asvgf_atrous_pair.cuh"
 #include "asvgf_atrous_ws.cuh"
+#include "asvgf_post.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -61,7 +62,7 @@ bool describe( uint32_t i, ImageDesc* d )
         case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV: case ASVGF_IMAGE_DIFF_COLOR_HISTORY: case ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE:
         case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: *d = { ASVGF_FORMAT_R16G16B16A16_SFLOAT, 8, false }; return true;
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: *d = { ASVGF_FORMAT_R32G32B32A32_SFLOAT, 16, false }; return true;
-        case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
+        case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
         case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR:
         case ASVGF_IMAGE_UNFILTERED_INDIR: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR: case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV:
         case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR: case ASVGF_IMAGE_SPEC_PONG_COLOR:
@@ -171,6 +172,10 @@ struct AsvgfDenoiser_T
     // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop); ASVGF_ATROUS=t2|ws|tiled|pair
     int       atrousMode  = 0;
     int       smCount     = 0;
+    // exposure state (= the reference's tonemapping buffer) and the tables of the histogram pass
+    AsvgfTonemapping* tm       = nullptr;
+    float*            log2Half = nullptr; // correctly rounded log2 of every fp16 bit pattern
+    uint8_t*          binTable = nullptr; // histogram bin of every fp16 bit pattern for the current uniform
     int       atrousTilesPerCta = 1; // ASVGF_ATROUS_TILES: tiles one CTA walks with the next tile's loads in flight (measured: 1, 2, 4 equal; 8+ slower)
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
@@ -464,6 +469,51 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     return launchCheck( d, pair ? "k_atrous_pair" : "k_atrous_tiled" );
 }
 
+AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
+{
+    NEED( ASVGF_IMAGE_PRE_FINAL, ASVGF_IMAGE_THROUGHPUT, ASVGF_IMAGE_FINAL );
+    ResolveArgs a;
+    a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.final_ = d.get( ASVGF_IMAGE_FINAL, fi );
+    k_checkerboard_resolve<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_checkerboard_resolve" );
+}
+
+LumArgs lumArgs( const AsvgfDenoiser_T& d, uint32_t fi, const AsvgfGlobalUniform& g )
+{
+    LumArgs a;
+    a.histogramInput = d.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
+    a.log2Half = d.log2Half; a.binTable = d.binTable; a.tm = d.tm;
+    a.minLogLuminance = g.minLogLuminance; a.maxLogLuminance = g.maxLogLuminance; a.timeDelta = g.timeDelta;
+    a.pixelCount = g.renderWidth * g.renderHeight; // CmLuminanceAvg.comp:68
+    a.stopEyeAdaptation = g.stopEyeAdaptation;
+    return a;
+}
+
+AsvgfResult runLuminanceHistogram( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, const AsvgfGlobalUniform& g )
+{
+    NEED( ASVGF_IMAGE_HISTOGRAM_INPUT );
+    const LumArgs a = lumArgs( d, fi, g );
+    k_lum_bin_table<<< 256, 256, 0, s >>>( a );
+    AsvgfResult r = launchCheck( d, "k_lum_bin_table" );
+    if( r != ASVGF_SUCCESS ) return r;
+    const size_t smem   = 65536 + ( kLumThreads / 32 ) * 256 * sizeof( uint32_t );
+    const long   groups = ( long )( d.ownEnd - d.ownBegin ) * ( ( d.W + 7 ) / 8 );
+    long         ctas   = ( groups + kLumThreads - 1 ) / kLumThreads;
+    if( ctas > 2L * d.smCount ) ctas = 2L * d.smCount;
+    if( ctas < 1 ) ctas = 1;
+    cudaError_t e = cudaFuncSetAttribute( k_lum_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
+    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_lum_histogram)" );
+    k_lum_histogram<<< ( unsigned )ctas, kLumThreads, smem, s >>>( a, u );
+    return launchCheck( d, "k_lum_histogram" );
+}
+
+AsvgfResult runLuminanceAverage( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const AsvgfGlobalUniform& g )
+{
+    const LumArgs a = lumArgs( d, fi, g );
+    k_lum_average<<< 1, 256, 0, s >>>( a );
+    return launchCheck( d, "k_lum_average" );
+}
+
 AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
 {
     if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL )
@@ -571,6 +621,33 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     if( r != ASVGF_SUCCESS ) { delete d; return r; }
     d->haveLut = true;
     if( cudaDeviceGetAttribute( &d->smCount, cudaDevAttrMultiProcessorCount, device ) != cudaSuccess || d->smCount <= 0 ) d->smCount = 148;
+    {
+        // CmLuminanceHistogram.comp:50 takes log2 of an fp16 texel: 65536 possible arguments.  GLSL leaves the precision of
+        // log2 to the implementation; the pin (shared with the oracle) is the correctly rounded fp32 value.
+        std::vector< float > table( 65536 );
+        for( uint32_t h = 0; h < 65536; h++ )
+        {
+            const uint32_t sign = h >> 15, e = ( h >> 10 ) & 31u, m = h & 1023u;
+            double         v;
+            if( e == 0 ) v = std::ldexp( ( double )m, -24 );
+            else if( e == 31 ) v = m ? std::nan( "" ) : HUGE_VAL;
+            else v = std::ldexp( 1.0 + ( double )m / 1024.0, ( int )e - 15 );
+            if( sign ) v = -v;
+            table[ h ] = ( float )std::log2( v );
+        }
+        cudaError_t e = cudaMalloc( ( void** )&d->log2Half, 65536 * sizeof( float ) );
+        if( e == cudaSuccess ) e = cudaMalloc( ( void** )&d->binTable, 65536 );
+        if( e == cudaSuccess ) e = cudaMalloc( ( void** )&d->tm, sizeof( AsvgfTonemapping ) );
+        if( e == cudaSuccess ) e = cudaMemcpy( d->log2Half, table.data(), 65536 * sizeof( float ), cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemset( d->tm, 0, sizeof( AsvgfTonemapping ) );
+        if( e != cudaSuccess )
+        {
+            AsvgfResult rr = cudaFail( e, "cudaMalloc(tonemapping)" );
+            std::string msg = g_lastError;
+            asvgfDestroy( d );
+            return fail( rr, msg );
+        }
+    }
     if( const char* e = std::getenv( "ASVGF_WS_CTAS" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 4096 ) d->smCount = n; }
 
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
@@ -614,6 +691,9 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
         if( d->owned[ i ] && d->img[ i ].p ) cudaFree( d->img[ i ].p );
     if( d->haveLut ) releaseLut( d->device );
+    if( d->log2Half ) cudaFree( d->log2Half );
+    if( d->binTable ) cudaFree( d->binTable );
+    if( d->tm ) cudaFree( d->tm );
     delete d;
     return ASVGF_SUCCESS;
 }
@@ -713,6 +793,58 @@ AsvgfResult asvgfDenoisePass( AsvgfDenoiser d, AsvgfStream stream, uint32_t fram
     if( r != ASVGF_SUCCESS ) return r;
     DeviceGuard guard( d->device );
     return runPass( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), pass );
+}
+
+AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    DeviceGuard guard( d->device );
+    return runResolveCheckerboard( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ) );
+}
+
+AsvgfResult asvgfLuminanceHistogram( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    DeviceGuard guard( d->device );
+    return runLuminanceHistogram( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), *pUniform );
+}
+
+AsvgfResult asvgfLuminanceAverage( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    DeviceGuard guard( d->device );
+    return runLuminanceAverage( *d, ( cudaStream_t )stream, frameIndex, *pUniform );
+}
+
+AsvgfResult asvgfCalculateExposure( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
+{
+    AsvgfResult r = asvgfLuminanceHistogram( d, stream, frameIndex, pUniform ); // Tonemapping.cpp:59-115
+    if( r != ASVGF_SUCCESS ) return r;
+    return asvgfLuminanceAverage( d, stream, frameIndex, pUniform );           // Tonemapping.cpp:117-175
+}
+
+AsvgfResult asvgfGetTonemappingBuffer( AsvgfDenoiser d, void** ppDevice )
+{
+    if( !d || !ppDevice ) return fail( ASVGF_WRONG_ARGUMENT, "null argument" );
+    *ppDevice = d->tm;
+    return ASVGF_SUCCESS;
+}
+AsvgfResult asvgfUploadTonemapping( AsvgfDenoiser d, AsvgfStream stream, const AsvgfTonemapping* pHost )
+{
+    if( !d || !pHost ) return fail( ASVGF_WRONG_ARGUMENT, "null argument" );
+    DeviceGuard guard( d->device );
+    CUDA_TRY( cudaMemcpyAsync( d->tm, pHost, sizeof( AsvgfTonemapping ), cudaMemcpyHostToDevice, ( cudaStream_t )stream ) );
+    return ASVGF_SUCCESS;
+}
+AsvgfResult asvgfDownloadTonemapping( AsvgfDenoiser d, AsvgfStream stream, AsvgfTonemapping* pHost )
+{
+    if( !d || !pHost ) return fail( ASVGF_WRONG_ARGUMENT, "null argument" );
+    DeviceGuard guard( d->device );
+    CUDA_TRY( cudaMemcpyAsync( pHost, d->tm, sizeof( AsvgfTonemapping ), cudaMemcpyDeviceToHost, ( cudaStream_t )stream ) );
+    return ASVGF_SUCCESS;
 }
 
 AsvgfResult asvgfSynchronize( AsvgfDenoiser d, AsvgfStream stream )

@@ -1,0 +1,179 @@
+// asvgf_post.cuh -- the two dispatches that consume the denoiser's outputs, sm_100a.
+//
+//   k_checkerboard_resolve ... CmCheckerboard.comp:43-78 (PreFinal -> Final)
+//   k_lum_bin_table .......... getColorBin of CmLuminanceHistogram.comp:38-55 for every fp16 bit pattern
+//   k_lum_histogram .......... CmLuminanceHistogram.comp:61-86
+//   k_lum_average ............ CmLuminanceAvg.comp:37-89
+//
+// Both are integer/bit-exact against the oracle.  The histogram is HBM-bound (2 B per pixel): HistogramInput is fp16, so
+// the bin of a texel is a function of its 16 bits; a 64 KB table of bins (rebuilt per call from the uniform's
+// log-luminance range and a correctly rounded log2 table) sits in shared memory and a pixel costs one byte lookup and
+// one warp-aggregated shared-memory atomic.
+#pragma once
+
+#include "../../include/asvgf_layout.h"
+#include "asvgf_atrous_tiled.cuh"
+
+namespace asvgf
+{
+
+struct ResolveArgs
+{
+    Img preFinal, throughput, final_;
+};
+
+// one thread per REGULAR pixel; arithmetic in the shader's order (products by 0.25 / 0.5 are exact, the three sums round)
+__global__ void __launch_bounds__( kBlockW* kBlockH ) k_checkerboard_resolve( const __grid_constant__ ResolveArgs a, const __grid_constant__ Uniform u )
+{
+    const int x = blockIdx.x * kBlockW + threadIdx.x;
+    const int y = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
+    if( x >= u.W || y >= u.yEnd ) return;
+    const Rows rows = rowsOf( a.preFinal );
+    const int  sep  = u.W / 2;
+    const int  isOdd = ( x + y % 2 ) % 2;                 // ShaderCommonGLSLFunc.h:311-329
+    const int  cbx   = isOdd * sep + x / 2;
+    const uint32_t centre = __ldg( at< uint32_t >( a.preFinal, x, y ) );
+    const uint16_t split  = __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.throughput, cbx, y ) ) + 3 ); // .a
+    uint32_t out = centre;
+    if( h2f( split ) > 0.5f ) // wasSplit, ShaderCommonGLSLFunc.h:434-444
+    {
+        const float3 c = unpackUfloat111110( centre );
+        const float  fl = ( cbx == 0 || cbx == sep ) ? 0.0f : 1.0f;     // !isLeftOutOfBounds
+        const float  fr = ( cbx == sep || cbx == u.W ) ? 0.0f : 1.0f;   // !isRightOutOfBounds
+        const float3 l = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x - 1, y, rows.in( x - 1, y ), 0u ) );
+        const float3 r = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x + 1, y, rows.in( x + 1, y ), 0u ) );
+        const float3 d = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x, y + 1, rows.in( x, y + 1 ), 0u ) );
+        const float3 t = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x, y - 1, rows.in( x, y - 1 ), 0u ) );
+        auto cross = [ & ]( float vl, float vr, float vd, float vt ) {
+            return addr( addr( addr( mulr( mulr( 0.25f, vl ), fl ), mulr( mulr( 0.25f, vr ), fr ) ), mulr( 0.25f, vd ) ), mulr( 0.25f, vt ) );
+        };
+        const float3 k = make_float3( cross( l.x, r.x, d.x, t.x ), cross( l.y, r.y, d.y, t.y ), cross( l.z, r.z, d.z, t.z ) );
+        out = packUfloat111110( make_float3( mixr( c.x, k.x, 0.5f ), mixr( c.y, k.y, 0.5f ), mixr( c.z, k.z, 0.5f ) ) );
+    }
+    *atW< uint32_t >( a.final_, x, y ) = out;
+}
+
+// ---- exposure ----
+struct LumArgs
+{
+    Img              histogramInput;
+    const float*     log2Half;   // 65536 entries: correctly rounded log2 of every fp16 bit pattern (host-built)
+    uint8_t*         binTable;   // 65536 entries, rebuilt per call
+    AsvgfTonemapping* tm;
+    float            minLogLuminance, maxLogLuminance, timeDelta, pixelCount;
+    uint32_t         stopEyeAdaptation;
+};
+
+// getColorBin (CmLuminanceHistogram.comp:38-55) of every fp16 bit pattern
+__global__ void __launch_bounds__( 256 ) k_lum_bin_table( const __grid_constant__ LumArgs a )
+{
+    const uint32_t h = blockIdx.x * 256u + threadIdx.x;
+    if( h >= 65536u ) return;
+    const float lum = h2f( ( uint16_t )h );
+    uint32_t    bin;
+    if( lum < 0.001f ) bin = 0u; // LUMINANCE_EPS; NaN falls through like the shader's comparison
+    else
+    {
+        const float inv = divr( 1.0f, subr( a.maxLogLuminance, a.minLogLuminance ) );
+        const float t   = fminf( fmaxf( mulr( subr( __ldg( a.log2Half + h ), a.minLogLuminance ), inv ), 0.0f ), 1.0f ); // clamp = min(max(x,0),1), NaN -> 0
+        bin             = ( uint32_t )f2i( addr( mulr( t, 254.0f ), 1.0f ) );
+    }
+    a.binTable[ h ] = ( uint8_t )bin;
+}
+
+constexpr int kLumThreads = 256;
+
+__global__ void __launch_bounds__( kLumThreads ) k_lum_histogram( const __grid_constant__ LumArgs a, const __grid_constant__ Uniform u )
+{
+    extern __shared__ __align__( 16 ) uint8_t lumSmem[];
+    uint8_t*  sTable = lumSmem;                                            // 64 KB
+    uint32_t* sHist  = reinterpret_cast< uint32_t* >( lumSmem + 65536 );   // one 256-bin histogram per warp
+    constexpr int WARPS = kLumThreads / 32;
+    for( int i = threadIdx.x; i < 65536 / 16; i += kLumThreads ) reinterpret_cast< uint4* >( sTable )[ i ] = __ldg( reinterpret_cast< const uint4* >( a.binTable ) + i );
+    for( int i = threadIdx.x; i < WARPS * 256; i += kLumThreads ) sHist[ i ] = 0u;
+    __syncthreads();
+
+    uint32_t* myHist = sHist + ( threadIdx.x >> 5 ) * 256;
+    auto count = [ & ]( uint32_t bin, bool valid ) {
+        // lanes with the same bin elect one of them to add their number: no same-address serialisation on flat images
+        const uint32_t active = __ballot_sync( 0xffffffffu, valid );
+        if( valid )
+        {
+            const uint32_t peers = __match_any_sync( active, bin );
+            if( ( threadIdx.x & 31 ) == ( uint32_t )( __ffs( peers ) - 1 ) ) atomicAdd( myHist + bin, ( uint32_t )__popc( peers ) );
+        }
+    };
+
+    // rows of 8-texel groups (one uint4 per lane), dealt to the CTAs round-robin
+    const int  rows = u.yEnd - u.yBegin;
+    const int  gpr  = ( u.W + 7 ) / 8;
+    const long total = ( long )rows * gpr;
+    const bool vec  = ( a.histogramInput.pitch % 16 ) == 0 && ( ( uintptr_t )a.histogramInput.p0 % 16 ) == 0;
+    const long span = ( ( total + kLumThreads - 1 ) / kLumThreads ) * kLumThreads; // whole warps stay converged for the ballots
+    for( long g = ( long )blockIdx.x * kLumThreads + threadIdx.x; g < span; g += ( long )gridDim.x * kLumThreads )
+    {
+        const bool in = g < total;
+        const int  r = in ? ( int )( g / gpr ) : 0, x0 = in ? ( int )( g - ( long )r * gpr ) * 8 : 0, y = u.yBegin + r;
+        uint32_t   w[ 4 ] = { 0u, 0u, 0u, 0u };
+        const bool full = in && x0 + 8 <= u.W && vec;
+        if( full )
+        {
+            const uint4 v = __ldg( reinterpret_cast< const uint4* >( at< uint16_t >( a.histogramInput, x0, y ) ) );
+            w[ 0 ] = v.x; w[ 1 ] = v.y; w[ 2 ] = v.z; w[ 3 ] = v.w;
+        }
+        else if( in )
+        {
+#pragma unroll
+            for( int k = 0; k < 8; k++ )
+                if( x0 + k < u.W ) w[ k >> 1 ] |= ( uint32_t )__ldg( at< uint16_t >( a.histogramInput, x0 + k, y ) ) << ( 16 * ( k & 1 ) );
+        }
+#pragma unroll
+        for( int k = 0; k < 8; k++ )
+        {
+            const uint32_t h = ( w[ k >> 1 ] >> ( 16 * ( k & 1 ) ) ) & 0xffffu;
+            count( sTable[ h ], in && x0 + k < u.W );
+        }
+    }
+    __syncthreads();
+    // CmLuminanceHistogram.comp:82-85: the work group's bins go to the global histogram
+    for( int b = threadIdx.x; b < 256; b += kLumThreads )
+    {
+        uint32_t s = 0u;
+#pragma unroll
+        for( int wv = 0; wv < WARPS; wv++ ) s += sHist[ wv * 256 + b ];
+        if( s ) atomicAdd( a.tm->histogram + b, s );
+    }
+}
+
+// CmLuminanceAvg.comp:37-89, one work group of 256.  exp2 / exp are evaluated in double and rounded to fp32 (the pin
+// "correctly rounded fp32" the oracle uses for transcendental functions whose GLSL precision is implementation-defined).
+__global__ void __launch_bounds__( 256 ) k_lum_average( const __grid_constant__ LumArgs a )
+{
+    __shared__ uint32_t s[ 256 ];
+    const uint32_t i = threadIdx.x;
+    const uint32_t countInLocalBin = a.tm->histogram[ i ];
+    s[ i ] = countInLocalBin * i;
+    __syncthreads();
+    a.tm->histogram[ i ] = 0u; // for the next frame
+    for( uint32_t cutoff = 128u; cutoff > 0u; cutoff >>= 1 )
+    {
+        if( i < cutoff ) s[ i ] += s[ i + cutoff ];
+        __syncthreads();
+    }
+    if( i == 0 )
+    {
+        if( a.stopEyeAdaptation != 0u ) return;
+        const float logLuminanceRange = subr( a.maxLogLuminance, a.minLogLuminance );
+        const float blackPixelCount   = ( float )countInLocalBin;
+        const float weightedLogAverage = subr( divr( ( float )s[ 0 ], fmaxf( subr( a.pixelCount, blackPixelCount ), 1.0f ) ), 1.0f );
+        const float e = addr( mulr( divr( weightedLogAverage, 254.0f ), logLuminanceRange ), a.minLogLuminance );
+        const float weightedAvgLuminance = ( float )exp2( ( double )e );
+        const float lastFrameLuminance   = a.tm->avgLuminance;
+        const float tau = 1.1f;
+        const float t   = subr( 1.0f, ( float )exp( ( double )mulr( -a.timeDelta, tau ) ) );
+        const float adaptedLuminance = addr( lastFrameLuminance, mulr( subr( weightedAvgLuminance, lastFrameLuminance ), t ) );
+        a.tm->avgLuminance = fminf( adaptedLuminance, ( float )exp2( ( double )a.maxLogLuminance ) );
+    }
+}
+
+} // namespace asvgf

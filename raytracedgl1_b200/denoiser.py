@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "asvgfCreate", "asvgfDestroy", "asvgfGetImageInfo", "asvgfGetImage", "asvgfBindExternalImage", "asvgfUploadImage",
     "asvgfDownloadImage", "asvgfResetHistory", "asvgfGradientSamples", "asvgfDenoise", "asvgfDenoisePass",
     "asvgfSynchronize", "asvgfGetLaunchCount", "asvgfPassName", "asvgfPassBytesPerPixel", "asvgfResultString",
-    "asvgfLastErrorMessage",
+    "asvgfLastErrorMessage", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
+    "asvgfLuminanceAverage", "asvgfGetTonemappingBuffer", "asvgfUploadTonemapping", "asvgfDownloadTonemapping",
 ]
 
 
@@ -67,6 +68,11 @@ def lib():
         L.asvgfDenoise.argtypes = [vp, vp, u32, puni]
         L.asvgfDenoisePass.argtypes = [vp, vp, u32, puni, u32]
         L.asvgfSynchronize.argtypes = [vp, vp]
+        for name in ("asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram", "asvgfLuminanceAverage"):
+            getattr(L, name).argtypes = [vp, vp, u32, puni]
+        L.asvgfGetTonemappingBuffer.argtypes = [vp, ctypes.POINTER(vp)]
+        L.asvgfUploadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
+        L.asvgfDownloadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
         L.asvgfGetLaunchCount.argtypes = [vp]
         L.asvgfGetLaunchCount.restype = ctypes.c_uint64
         L.asvgfPassName.argtypes = [u32]
@@ -167,6 +173,32 @@ class Denoiser:
 
     def denoise_pass(self, p, frame_index, uniform, stream=0):
         _check(lib().asvgfDenoisePass(self._h, stream, frame_index, ctypes.byref(uniform), p), "asvgfDenoisePass")
+
+    # ---- the two dispatches after the denoiser ----
+    def resolve_checkerboard(self, frame_index, uniform, stream=0):
+        """= ImageComposition::PrepareForRaster (Source/ImageComposition.cpp:87-92): PreFinal -> Final."""
+        _check(lib().asvgfResolveCheckerboard(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfResolveCheckerboard")
+
+    def calculate_exposure(self, frame_index, uniform, stream=0):
+        """= Tonemapping::CalculateExposure (Source/Tonemapping.cpp:59-175): histogram + eye adaptation."""
+        _check(lib().asvgfCalculateExposure(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfCalculateExposure")
+
+    def luminance_histogram(self, frame_index, uniform, stream=0):
+        _check(lib().asvgfLuminanceHistogram(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfLuminanceHistogram")
+
+    def luminance_average(self, frame_index, uniform, stream=0):
+        _check(lib().asvgfLuminanceAverage(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfLuminanceAverage")
+
+    def tonemapping(self, stream=0):
+        """Host copy of the handle's AsvgfTonemapping (histogram[256], avgLuminance)."""
+        t = layout.Tonemapping()
+        _check(lib().asvgfDownloadTonemapping(self._h, stream, ctypes.byref(t)), "asvgfDownloadTonemapping")
+        self.synchronize(stream)
+        return t
+
+    def set_tonemapping(self, t, stream=0):
+        _check(lib().asvgfUploadTonemapping(self._h, stream, ctypes.byref(t)), "asvgfUploadTonemapping")
+        self.synchronize(stream)
 
     def synchronize(self, stream=0):
         _check(lib().asvgfSynchronize(self._h, stream), "asvgfSynchronize")

@@ -37,6 +37,7 @@ IMAGES = {
     "ViewDirection": (18, R16G16B16A16_SFLOAT, False, "in"),
     "Throughput": (20, R16G16B16A16_SFLOAT, False, "in"),
     "PreFinal": (21, B10G11R11_UFLOAT, False, "out"),
+    "Final": (22, B10G11R11_UFLOAT, False, "out"),  # PreFinal after the checkerboard resolve (CmCheckerboard.comp)
     "AccumHistoryLength": (27, R16G16B16A16_SFLOAT, False, "state"),
     "AccumHistoryLength_Prev": (28, R16G16B16A16_SFLOAT, False, "state"),
     "DiffTemporary": (29, R32_UINT, False, "scratch"),
@@ -120,7 +121,9 @@ class GlobalUniform(ctypes.Structure):
         ("_reserved1", ctypes.c_uint32),
         ("renderWidth", ctypes.c_float), ("renderHeight", ctypes.c_float),
         ("frameId", ctypes.c_uint32), ("timeDelta", ctypes.c_float),
-        ("_reserved2", ctypes.c_uint32 * 13),
+        ("minLogLuminance", ctypes.c_float), ("maxLogLuminance", ctypes.c_float),
+        ("luminanceWhitePoint", ctypes.c_float), ("stopEyeAdaptation", ctypes.c_uint32),
+        ("_reserved2", ctypes.c_uint32 * 9),
         ("cameraPosition", ctypes.c_float * 4), ("cameraPositionPrev", ctypes.c_float * 4),
         ("debugShowFlags", ctypes.c_uint32),
         ("_reserved3", ctypes.c_uint32 * 44),
@@ -135,6 +138,15 @@ class GlobalUniform(ctypes.Structure):
 
 
 assert ctypes.sizeof(GlobalUniform) == 2096
+assert GlobalUniform.minLogLuminance.offset == 668 and GlobalUniform.stopEyeAdaptation.offset == 680
+
+
+class Tonemapping(ctypes.Structure):
+    """Byte-compatible with ShTonemapping (Source/Generated/ShaderCommonC.h:344-348)."""
+    _fields_ = [("histogram", ctypes.c_uint32 * 256), ("avgLuminance", ctypes.c_float)]
+
+
+assert ctypes.sizeof(Tonemapping) == 1028
 assert GlobalUniform.renderWidth.offset == 652 and GlobalUniform.antiFireflyEnabled.offset == 988
 
 

@@ -315,6 +315,8 @@ void asvgfSynthFillUniform( AsvgfGlobalUniform* u, uint32_t W, uint32_t H, uint3
     u->cameraPositionPrev[ 0 ] = prev.pos.x; u->cameraPositionPrev[ 1 ] = prev.pos.y; u->cameraPositionPrev[ 2 ] = prev.pos.z; u->cameraPositionPrev[ 3 ] = 1.0f;
     u->gradientMultDiffuse = 0.5f; u->gradientMultIndirect = 0.2f; u->gradientMultSpecular = 0.5f; // RTGL1.h:680-686 defaults
     u->antiFireflyEnabled = 1; u->lightmapScreenCoverage = 0.0f; u->debugShowFlags = 0;
+    // exposure range as VulkanDevice.cpp:205-210 derives it from ev100Min = 0, ev100Max = 10: log2( 2^ev * 12.5 / 100 )
+    u->minLogLuminance = -3.0f; u->maxLogLuminance = 7.0f; u->luminanceWhitePoint = 10.0f; u->stopEyeAdaptation = 0;
 }
 
 // images[i] = tightly packed host buffer for image index i (asvgf_layout.h) or NULL to skip.  Fills the INPUTS of

@@ -1,0 +1,198 @@
+"""The two dispatches that consume the denoiser's outputs: checkerboard resolve
+(CmCheckerboard.comp, PreFinal -> Final) and exposure (CmLuminanceHistogram.comp + CmLuminanceAvg.comp).
+
+CPU part: analytic known-answer tests of the oracle.  GPU part: bit-exact parity of the CUDA path (C ABI) against it."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+import oracle as oracle_mod
+import synth
+from raytracedgl1_b200 import layout
+
+
+def _pack111110(r, g, b):
+    return oracle_mod.lib().asvgfOraclePackUfloat111110(r, g, b)
+
+
+def _bin(lum, lo, hi):
+    """getColorBin restated with numpy fp32 (CmLuminanceHistogram.comp:38-55)."""
+    lum = np.float32(lum)
+    if lum < np.float32(0.001):
+        return 0
+    inv = np.float32(1.0) / (np.float32(hi) - np.float32(lo))
+    t = (np.float32(math.log2(float(lum))) - np.float32(lo)) * inv
+    t = min(max(t, np.float32(0.0)), np.float32(1.0))
+    return int(np.float32(t * np.float32(254.0) + np.float32(1.0)))
+
+
+def test_oracle_histogram_known_answers():
+    W, H = 64, 36
+    o = oracle_mod.Oracle(W, H)
+    try:
+        u = synth.uniform(W, H, 0)
+        img = o.image("HistogramInput", 0)
+        img[...] = 0
+        img[0, :] = np.float16(0.125)     # exactly 2^minLog -> t = 0 -> bin 1
+        img[1, :] = np.float16(128.0)     # exactly 2^maxLog -> t = 1 -> bin 255
+        img[2, :] = np.float16(65504.0)   # above the range -> clamped to bin 255
+        img[3, :] = np.float16(0.0005)    # below LUMINANCE_EPS -> bin 0
+        img[4, :] = np.float16(4.0)       # log2 = 2 -> t = 0.5 -> uint(0.5*254 + 1) = 128
+        img[5, :] = np.float16(np.inf)    # fp16 overflow of the composed luminance -> bin 255
+        o.luminance_histogram(0, u)
+        h = np.array(o.tonemapping.histogram)
+        assert h.sum() == W * H
+        assert h[1] == W and h[255] == 3 * W and h[128] == W and h[0] == W * H - 5 * W
+        # every fp16 value against the numpy restatement
+        vals = np.arange(0, 0x7c01, 37, dtype=np.uint16).view(np.float16)
+        o.reset_history()
+        img = o.image("HistogramInput", 0)
+        flat = img.reshape(-1)
+        flat[:] = 0
+        flat[:len(vals)] = vals[:flat.size]
+        n = min(len(vals), flat.size)
+        o.luminance_histogram(0, u)
+        want = np.zeros(256, dtype=np.int64)
+        for v in flat:
+            want[_bin(v, u.minLogLuminance, u.maxLogLuminance)] += 1
+        assert n > 800 and np.array_equal(np.array(o.tonemapping.histogram), want)
+    finally:
+        o.close()
+
+
+def test_oracle_average_known_answers():
+    W, H = 64, 36
+    o = oracle_mod.Oracle(W, H)
+    try:
+        u = synth.uniform(W, H, 0)
+        o.image("HistogramInput", 0)[...] = np.float16(4.0)  # every pixel in bin 128
+        o.tonemapping.avgLuminance = 1.0
+        o.calculate_exposure(0, u)
+        tm = o.tonemapping
+        assert not any(tm.histogram)  # cleared for the next frame (CmLuminanceAvg.comp:48)
+        # weightedLogAverage = 128 - 1 = 127 -> 2^(127/254*10 - 3) = 4; one step of the 1.1/s adaptation from 1
+        t = 1.0 - math.exp(-(1.0 / 60.0) * 1.1)
+        assert abs(tm.avgLuminance - (1.0 + (4.0 - 1.0) * t)) < 1e-6
+        # converges to the scene luminance and never exceeds 2^maxLog
+        for _ in range(2000):
+            o.calculate_exposure(0, u)
+        assert abs(o.tonemapping.avgLuminance - 4.0) < 1e-3
+        u.stopEyeAdaptation = 1
+        before = o.tonemapping.avgLuminance
+        o.image("HistogramInput", 0)[...] = np.float16(100.0)
+        o.calculate_exposure(0, u)
+        assert o.tonemapping.avgLuminance == before and not any(o.tonemapping.histogram)
+        # all-black frame: pixelCount - blackPixelCount clamps to 1, weighted average -1 -> below the range
+        u.stopEyeAdaptation = 0
+        o.image("HistogramInput", 0)[...] = 0
+        o.tonemapping.avgLuminance = 0.0
+        o.calculate_exposure(0, u)
+        t1 = 2.0 ** ((-1.0 / 254.0) * 10.0 - 3.0)
+        assert abs(o.tonemapping.avgLuminance - t1 * t) < 1e-6
+    finally:
+        o.close()
+
+
+def test_oracle_resolve_known_answers():
+    W, H = 16, 8
+    o = oracle_mod.Oracle(W, H)
+    try:
+        u = synth.uniform(W, H, 0)
+        pf = o.image("PreFinal", 0)
+        tp = o.image("Throughput", 0)
+        rng = np.random.default_rng(3)
+        vals = rng.integers(0, 64, size=(H, W, 3)).astype(np.float32)  # small integers: exactly representable in uf11/uf10
+        for y in range(H):
+            for x in range(W):
+                pf[y, x] = _pack111110(*vals[y, x])
+        tp[...] = 0
+        o.resolve_checkerboard(0, u)
+        assert np.array_equal(o.image("Final", 0), pf)  # no split pixel: pass-through
+        tp[..., 3] = np.float16(1.0)                   # every pixel split
+        o.resolve_checkerboard(0, u)
+        fin = layout.decode_b10g11r11(o.image("Final", 0))
+        out = np.zeros(4, dtype=np.int32)
+        sep = W // 2
+        for (x, y) in ((5, 3), (0, 0), (W - 1, H - 1), (1, 2)):
+            odd = (x + y % 2) % 2
+            cbx = odd * sep + x // 2
+            fl = 0.0 if cbx in (0, sep) else 1.0
+            fr = 0.0 if cbx in (sep, W) else 1.0
+            g = lambda xx, yy: vals[yy, xx] if 0 <= xx < W and 0 <= yy < H else np.zeros(3, np.float32)
+            cross = 0.25 * g(x - 1, y) * fl + 0.25 * g(x + 1, y) * fr + 0.25 * g(x, y + 1) + 0.25 * g(x, y - 1)
+            want = 0.5 * vals[y, x] + 0.5 * cross
+            # uf11 (6-bit mantissa) / uf10 (5-bit) quantisation of the stored result
+            assert np.all(np.abs(fin[y, x] - want) <= np.maximum(want, 1e-3) * np.array([2.0 ** -6, 2.0 ** -6, 2.0 ** -5])), (x, y)
+        del out
+    finally:
+        o.close()
+
+
+def test_uniform_and_tonemapping_layout():
+    assert layout.GlobalUniform.minLogLuminance.offset == 668
+    assert layout.GlobalUniform.maxLogLuminance.offset == 672
+    assert layout.GlobalUniform.stopEyeAdaptation.offset == 680
+    assert ctypes.sizeof(layout.Tonemapping) == 1028 and layout.Tonemapping.avgLuminance.offset == 1024
+    assert layout.INDEX["Final"] == 22
+
+
+# ---------------------------------------------------------------- GPU parity ----------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(320, 180), (322, 182), (1280, 720)])
+def test_post_passes_parity(size):
+    """After a denoised frame: Final bit-identical, histogram bit-identical, avgLuminance identical to 1e-6 relative
+    (its exp2/exp run in double on both sides), over several frames so that the adaptation state carries."""
+    from _harness import Pair
+    W, H = size
+    p = Pair(W, H)
+    try:
+        rng = np.random.default_rng(11)
+        for frame in range(3):
+            def mutate(g):
+                # mark a third of the pixels as split (reflect/refract), RaygenPrimary writes 1 there
+                g["Throughput"][..., 3] = (rng.random((H, W)) < 0.33).astype(np.float16)
+            fi, u = p.run_frame(frame, mutate=mutate)
+            p.sync_state_to_cuda()  # both sides continue from the oracle's PreFinal / HistogramInput
+            p.oracle.resolve_checkerboard(fi, u)
+            p.cuda.resolve_checkerboard(fi, u)
+            p.cuda.synchronize()
+            assert np.array_equal(p.oracle.image("Final", fi), p.cuda.download("Final", fi)), "Final frame %d" % frame
+            p.oracle.luminance_histogram(fi, u)
+            p.cuda.luminance_histogram(fi, u)
+            got = p.cuda.tonemapping()
+            want = p.oracle.tonemapping
+            assert sum(want.histogram) == W * H
+            assert list(got.histogram) == list(want.histogram), "histogram frame %d" % frame
+            p.oracle.luminance_average(u)
+            p.cuda.luminance_average(fi, u)
+            got = p.cuda.tonemapping()
+            want = p.oracle.tonemapping
+            assert not any(got.histogram)
+            assert abs(got.avgLuminance - want.avgLuminance) <= 1e-6 * abs(want.avgLuminance), (got.avgLuminance, want.avgLuminance)
+            assert want.avgLuminance > 0
+    finally:
+        p.close()
+
+
+@pytest.mark.gpu
+def test_histogram_every_half_pattern_and_flat_image():
+    """Every fp16 bit pattern as input (negatives, denormals, inf, NaN) and a flat image (all lanes in one bin: the
+    warp-aggregated atomic path) give the oracle's histogram exactly."""
+    from _harness import Pair
+    W, H = 512, 128  # 65536 texels
+    p = Pair(W, H)
+    try:
+        u = synth.uniform(W, H, 0)
+        allbits = np.arange(65536, dtype=np.uint16).view(np.float16).reshape(H, W)
+        for img in (allbits, np.full((H, W), 3.0, dtype=np.float16)):
+            p.oracle.reset_history()
+            p.oracle.image("HistogramInput", 0)[...] = img
+            p.cuda.upload("HistogramInput", 0, np.ascontiguousarray(img))
+            p.cuda.set_tonemapping(layout.Tonemapping())
+            p.oracle.luminance_histogram(0, u)
+            p.cuda.luminance_histogram(0, u)
+            assert list(p.cuda.tonemapping().histogram) == list(p.oracle.tonemapping.histogram)
+    finally:
+        p.close()
