@@ -346,6 +346,21 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     pass_ms = [sum(evs[i][k].elapsed_time(evs[i][k + 1]) for i in range(pp_steps)) / pp_steps for k in range(len(passes))]
 
+    # ---- the two dispatches that consume the frame right after the denoiser: reported next to
+    # the metric, not part of it ----
+    post_ms = {}
+    fi_last = (args.warmup + args.steps + pp_steps - 1) & 1
+    u_last = uniforms[(args.warmup + args.steps + pp_steps - 1) % n_frames]
+    for name, call in (("k_checkerboard_resolve", d.resolve_checkerboard), ("k_lum_histogram+k_lum_average", d.calculate_exposure)):
+        call(fi_last, u_last, stream=sh)
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        pe[0].record(stream)
+        for _ in range(10):
+            call(fi_last, u_last, stream=sh)
+        pe[1].record(stream)
+        torch.cuda.synchronize()
+        post_ms[name] = pe[0].elapsed_time(pe[1]) / 10
+
     # ---- end to end through the C ABI with host buffers ----
     e2e_steps = max(3, min(args.steps, 20))
     # Pipelined the way a caller with host-resident G-buffers would: the upload of frame i+1 (copy stream) overlaps the
@@ -404,7 +419,7 @@ def run_ours(args, rank, world, local_rank):
         chain_bpp = sum(bpp)
         per_pass = []
         for k, p in enumerate(passes):
-            name = dn.lib().asvgfPassName(p).decode()
+            name = dn.lib().asvgfPassKernelName(p, N).decode()
             gbs = bpp[k] * W * H / (pass_ms[k] * 1e-3) / 1e9 if pass_ms[k] > 0 else 0.0
             per_pass.append({"pass": p, "kernel": name, "ms": round(pass_ms[k], 5), "bytes_per_px": bpp[k],
                              "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
@@ -439,6 +454,10 @@ def run_ours(args, rank, world, local_rank):
                                    "frac": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9 / peak,
                                    "frac_of_8000_nominal": chain_bpp * W * H / (frame_ms * 1e-3) / 1e9 / 8000.0}},
             "passes": per_pass,
+            # PreFinal -> Final (12 B/px algorithmic: 4 read, 4 written, Throughput.a 2, + neighbours from cache) and the
+            # exposure histogram + adaptation (2 B/px): the next dispatches of the reference's frame, timed separately
+            "post": [{"kernel": k, "ms": round(v, 5),
+                      "achieved_gbs": round((10.0 if "resolve" in k else 2.0) * W * H / (v * 1e-3) / 1e9, 1)} for k, v in post_ms.items()],
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(W, H, N, None)
@@ -465,30 +484,73 @@ def run_bands(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, H, N, desc = WORKLOADS[args.workload]
-    bd = bands.BandedDenoiser(W, H, N, rank=rank, world=world, device=local_rank, halo_rows=48)
-    s0, s1 = bd.plan.stored if world > 1 else (0, H)
     n_frames = max(2, min(args.frames, 8) // 2 * 2)
     swappable = {n for n in layout.PRODUCER_IMAGES if n + "_Prev" in layout.IMAGES}
-    resident, uniforms = [], []
-    for f in range(n_frames):
-        g = synth.generate_rows(W, H, f, s0, s1)
-        dev = {}
-        for name in layout.PRODUCER_IMAGES:
-            _, pitch, _, _, rows = bd.d.image(name, 0)
-            a = g[name]
-            row_bytes = a.nbytes // rows
-            dt = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
-            dt[:, :row_bytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(rows, row_bytes)))
-            dev[name] = (dt, pitch)
-        resident.append(dev)
-        uniforms.append(synth.uniform(W, H, f))
+    uniforms = [synth.uniform(W, H, f) for f in range(n_frames)]
 
-    def step(i):
-        f, fi = i % n_frames, i & 1
-        for name in layout.PRODUCER_IMAGES:
-            t, pitch = resident[f][name]
-            bd.d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
-        bd.frame(fi, uniforms[f])
+    def build(boundaries):
+        """One rank's band handle + its band-plus-halo rows of the cycled synthetic sequence, resident in HBM."""
+        bd = bands.BandedDenoiser(W, H, N, rank=rank, world=world, device=local_rank, apron=(args.band_schedule == "apron"),
+                                  boundaries=boundaries)
+        s0, s1 = bd.plan.stored if world > 1 else (0, H)
+        resident = []
+        for f in range(n_frames):
+            g = synth.generate_rows(W, H, f, s0, s1)
+            dev = {}
+            for name in layout.PRODUCER_IMAGES:
+                _, pitch, _, _, rows = bd.d.image(name, 0)
+                a = g[name]
+                row_bytes = a.nbytes // rows
+                dt = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
+                dt[:, :row_bytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(rows, row_bytes)))
+                dev[name] = (dt, pitch)
+            resident.append(dev)
+        return bd, resident
+
+    def make_step(bd, resident):
+        def step(i, events=None):
+            f, fi = i % n_frames, i & 1
+            for name in layout.PRODUCER_IMAGES:
+                t, pitch = resident[f][name]
+                bd.d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
+            bd.frame(fi, uniforms[f], events=events)
+        return step
+
+    def kernel_and_exchange_ms(step, first, frames=4):
+        evs = []
+        for i in range(frames):
+            step(first + i, events=evs)
+        torch.cuda.synchronize()
+        return (sum(a.elapsed_time(b) for k, a, b in evs if k == "pass") / frames,
+                sum(a.elapsed_time(b) for k, a, b in evs if k == "exchange") / frames)
+
+    # Rows are not equally expensive (sky pixels skip the a-trous taps, disoccluded ones take the longer variance path),
+    # so equal-height bands leave the cheap ranks waiting in the exchanges.  The band boundaries are therefore taken from
+    # a measured cost profile: run a few frames on equal bands, gather each rank's own kernel time, re-split so that the
+    # bands carry equal time (cost per row constant inside each old band), rebuild, and repeat once.
+    boundaries = bands.band_rows(H, world)
+    calibration = []
+    bd, resident = build(boundaries)
+    step = make_step(bd, resident)
+    if world > 1 and args.band_balance == "measured":
+        for _ in range(2):
+            for i in range(4):
+                step(i)
+            own_ms, _ = kernel_and_exchange_ms(step, 4)
+            t = torch.tensor([own_ms], device="cuda", dtype=torch.float64)
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            band_ms = [float(x[0]) for x in every]
+            calibration.append({"band_rows": list(boundaries), "kernel_ms": [round(x, 4) for x in band_ms]})
+            new = bands.rebalanced_rows(boundaries, band_ms, bd.plan.halo)
+            if new == boundaries:
+                break
+            boundaries = new
+            bd.close()
+            del bd, resident, step
+            torch.cuda.empty_cache()
+            bd, resident = build(boundaries)
+            step = make_step(bd, resident)
 
     def barrier():
         if world > 1:
@@ -511,8 +573,19 @@ def run_bands(args, rank, world, local_rank):
     launches = bd.d.launch_count - launches0
     barrier()
     total_ms = e0.elapsed_time(e1)
+    # where a rank's time goes: its own kernels vs waiting in the exchanges (content makes bands unequally expensive)
+    own_ms, exch_ms = kernel_and_exchange_ms(step, args.warmup + args.steps)
+    split = [[own_ms, exch_ms]]
+    rank_ms = [total_ms / args.steps]
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        rank_ms = [float(x[0]) / args.steps for x in every]
+        t2 = torch.tensor([own_ms, exch_ms], device="cuda", dtype=torch.float64)
+        every2 = [torch.zeros_like(t2) for _ in range(world)]
+        dist.all_gather(every2, t2)
+        split = [[float(x[0]), float(x[1])] for x in every2]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t[0])
         ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
@@ -529,11 +602,14 @@ def run_bands(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": W, "height": H, "atrous_iterations": N,
-                       "parallelism": "%d horizontal bands (rows multiple of 3), 48-row halo, %d neighbour exchanges per frame "
-                                      "(torch.distributed batch_isend_irecv, NCCL)" % (world, len(exchanges) if world > 1 else 0),
+                       "parallelism": "%d horizontal bands (rows multiple of 3), %d-row halo, %s schedule: %d neighbour exchanges per frame "
+                                      "(torch.distributed batch_isend_irecv, NCCL)" % (world, bd.plan.halo, "apron" if bd.apron else "per-pass",
+                                                                                       len(exchanges) if world > 1 else 0),
                        "sequence": "%d consecutive synthetic frames, cycled" % n_frames,
                        "l2": "no flush: the frame's images exceed the 126 MB L2", "algorithmic_bytes_per_px": chain_bpp},
             "clocks": clocks, "e2e": None, "gpu_launches": launches,
+            "rank_ms_per_step": [round(x, 4) for x in rank_ms], "band_rows": list(boundaries), "band_calibration": calibration,
+            "rank_kernel_ms_and_exchange_ms": [[round(a, 4), round(b, 4)] for a, b in split],
             "roofline": {"bound": "hbm", "kernel": "whole chain", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
                          "frac": gbs / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus"},
             "cpu_baseline": None,
@@ -553,6 +629,10 @@ def main():
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=32, help="distinct synthetic frames in the cycled sequence (even)")
+    ap.add_argument("--band-balance", default="measured", choices=["measured", "equal"],
+                    help="band workloads: boundaries from a measured per-band cost profile, or equal heights")
+    ap.add_argument("--band-schedule", default="apron", choices=["apron", "per-pass"],
+                    help="band workloads: redundant apron rows + 2 exchanges per frame, or one exchange before each pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

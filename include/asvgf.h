@@ -51,6 +51,9 @@ typedef enum AsvgfCreateFlagBits
 {
     ASVGF_CREATE_EXPORT_DEBUG_MASK = 1u << 0, /* temporal pass also writes ASVGF_IMAGE_DEBUG_MASK               */
     ASVGF_CREATE_EXTERNAL_IMAGES   = 1u << 1, /* allocate nothing: every image comes from asvgfBindExternalImage */
+    ASVGF_CREATE_BAND_APRON        = 1u << 3, /* band handles: every pass also computes the rows beyond the band that the
+                                                 later passes of the frame will read (asvgfBandApronRows), so one frame
+                                                 needs two halo exchanges instead of one before each pass            */
     ASVGF_CREATE_LITERAL_KERNELS   = 1u << 2  /* run the literal one-thread-per-pixel kernels (precise powf/expf, no
                                                  tiling): slow, closest to the shader text; for A/B numerics checks  */
 } AsvgfCreateFlagBits;
@@ -161,10 +164,16 @@ ASVGF_API AsvgfResult asvgfDownloadTonemapping( AsvgfDenoiser denoiser, AsvgfStr
    Source/VulkanDevice.cpp:791-796).  Surfaces asynchronous kernel faults as ASVGF_CUDA_ERROR. */
 ASVGF_API AsvgfResult asvgfSynchronize( AsvgfDenoiser denoiser, AsvgfStream stream );
 
+/* ASVGF_CREATE_BAND_APRON: rows (full-resolution rows; gradient rows for the gradient a-trous passes) a pass computes
+   beyond the owned band.  For ASVGF_PASS_GRADIENT_SAMPLES (computed on owned rows only) it is the depth in gradient
+   rows of the one exchange of ASVGF_IMAGE_DIS_PING_GRADIENT that follows it.  -1 for a bad iteration count. */
+ASVGF_API int32_t     asvgfBandApronRows( uint32_t atrousIterations, uint32_t pass );
+
 /* Number of CUDA kernels this handle has launched since creation. */
 ASVGF_API uint64_t    asvgfGetLaunchCount( AsvgfDenoiser denoiser );
 /* Name of the kernel that implements a pass and its algorithmic HBM bytes per full-resolution pixel. */
 ASVGF_API const char* asvgfPassName( uint32_t pass );
+ASVGF_API const char* asvgfPassKernelName( uint32_t pass, uint32_t atrousIterations ); /* default kernel choice per iteration */
 ASVGF_API double      asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations );
 ASVGF_API const char* asvgfResultString( AsvgfResult result );
 ASVGF_API const char* asvgfLastErrorMessage( void ); /* thread-local detail of the last failure */

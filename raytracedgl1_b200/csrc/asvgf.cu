@@ -12,6 +12,7 @@
 #include "asvgf_atrous_ws.cuh"
 #include "asvgf_post.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -169,9 +170,12 @@ struct AsvgfDenoiser_T
     uint64_t  launchCount = 0;
     bool      atrousPair  = false; // ASVGF_ATROUS=pair selects the packed-f32x2 a-trous kernel (measured slower: the pass is smem-pipe bound)
     // a-trous kernel: 0 = k_atrous_t2 (vectorised staging + pair filter, one tile per CTA), 1 = k_atrous_ws (same, warp-specialised
-    // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop); ASVGF_ATROUS=t2|ws|tiled|pair
-    int       atrousMode  = 0;
+    // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop), 3 = auto: the measured best per iteration
+    // (k_atrous_tiled for the plain iterations, k_atrous_t2 for the composing one: 0.21/0.19/0.20/0.25 ms at 4K against
+    // 0.22/0.21/0.21/0.25 all-t2 and 0.21/0.19/0.20/0.30 all-tiled); ASVGF_ATROUS=auto|t2|ws|tiled|pair
+    int       atrousMode  = 3;
     int       smCount     = 0;
+    int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
     // exposure state (= the reference's tonemapping buffer) and the tables of the histogram pass
     AsvgfTonemapping* tm       = nullptr;
     float*            log2Half = nullptr; // correctly rounded log2 of every fp16 bit pattern
@@ -244,9 +248,9 @@ AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi,
     a.disHistory = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi ); a.motion = d.get( ASVGF_IMAGE_MOTION, fi );
     a.gradientInputsPrev = d.get( ASVGF_IMAGE_GRADIENT_INPUTS_PREV, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
     a.indirAccumPrev = d.get( ASVGF_IMAGE_INDIR_ACCUM_PREV, fi ); a.fwdLum = d.get( ASVGF_IMAGE_FWD_LUM, fi );
-    a.gyBegin = d.gownBegin; a.gyEnd = d.gownEnd;
-    if( literal( d ) ) k_gradient_samples<<< gridFor( a.disPing.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
-    else k_gradient_samples_fast<<< gridFor( a.disPing.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
+    if( literal( d ) ) k_gradient_samples<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
+    else k_gradient_samples_fast<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_gradient_samples" );
 }
 
@@ -258,9 +262,9 @@ AsvgfResult runGradientAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, 
     a.src = d.get( even ? ASVGF_IMAGE_DIS_PING_GRADIENT : ASVGF_IMAGE_DIS_PONG_GRADIENT, fi );
     a.dst = d.get( even ? ASVGF_IMAGE_DIS_PONG_GRADIENT : ASVGF_IMAGE_DIS_PING_GRADIENT, fi );
     a.history = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi );
-    a.iteration = ( int32_t )iteration; a.gyBegin = d.gownBegin; a.gyEnd = d.gownEnd;
-    if( literal( d ) ) k_gradient_atrous<<< gridFor( a.dst.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
-    else k_gradient_atrous_fast<<< gridFor( a.dst.w, d.gownEnd - d.gownBegin ), kBlock, 0, s >>>( a, u );
+    a.iteration = ( int32_t )iteration; a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
+    if( literal( d ) ) k_gradient_atrous<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
+    else k_gradient_atrous_fast<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_gradient_atrous" );
 }
 
@@ -286,8 +290,8 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.outIndirAccum = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi ); a.outMask = d.get( ASVGF_IMAGE_DEBUG_MASK, fi );
     a.lut = d.lut;
     a.writeMask = ( ( d.info.flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) && a.outMask.p ) ? 1 : 0;
-    if( literal( d ) ) k_temporal<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
-    else k_temporal_fast<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_temporal<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    else k_temporal_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_temporal" );
 }
 
@@ -298,10 +302,10 @@ AsvgfResult runAntiFirefly( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, con
     AntiFireflyArgs a;
     a.src[ 0 ] = d.get( ASVGF_IMAGE_DIFF_TEMPORARY, fi ); a.src[ 1 ] = d.get( ASVGF_IMAGE_SPEC_ACCUM_COLOR, fi ); a.src[ 2 ] = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi );
     a.dst[ 0 ] = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SPEC_PING_COLOR, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_INDIR_PING, fi );
-    if( literal( d ) ) k_antifirefly<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_antifirefly<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     else
     {
-        const dim3 grid( ( unsigned )( ( d.W + kAfTile - 1 ) / kAfTile ), ( unsigned )( ( d.ownEnd - d.ownBegin + kAfTile - 1 ) / kAfTile ), 3 );
+        const dim3 grid( ( unsigned )( ( d.W + kAfTile - 1 ) / kAfTile ), ( unsigned )( ( u.yEnd - u.yBegin + kAfTile - 1 ) / kAfTile ), 3 );
         k_antifirefly_fast<<< grid, kAfThreads, 0, s >>>( a, u );
     }
     return launchCheck( d, "k_antifirefly" );
@@ -315,8 +319,8 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.color = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
     a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
     a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
-    if( literal( d ) ) k_variance<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
-    else k_variance_fast<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    if( literal( d ) ) k_variance<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    else k_variance_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_variance" );
 }
 
@@ -363,18 +367,18 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     const size_t smem = pair ? atrousPairSmemBytes( step ) : atrousTiledSmemBytes( step );
     if( literal( d ) || step > 32 )
     {
-        const dim3 grid = gridFor( ( int )d.W, d.ownEnd - d.ownBegin );
+        const dim3 grid = gridFor( ( int )d.W, u.yEnd - u.yBegin );
         if( iteration == 0 ) k_atrous< true, false ><<< grid, kBlock, 0, s >>>( a, u );
         else if( last ) k_atrous< false, true ><<< grid, kBlock, 0, s >>>( a, u );
         else k_atrous< false, false ><<< grid, kBlock, 0, s >>>( a, u );
         return launchCheck( d, "k_atrous" );
     }
-    const int  rows  = d.ownEnd - d.ownBegin;
+    const int  rows  = u.yEnd - u.yBegin;
     // the warp-specialised kernel moves four pixels per load: it needs W % 4 == 0 and 16-byte aligned rows
     auto vec16 = [ & ]( const Img& im ) { return ( ( uintptr_t )im.p % 16 ) == 0 && ( im.pitch % 16 ) == 0; };
     const bool wsOk = ( d.W % 4 ) == 0 && step <= 32 && vec16( a.normal ) && vec16( a.depth ) && vec16( a.metRough ) && vec16( a.srcDiff ) && vec16( a.srcSpec ) &&
                       vec16( a.srcIndir ) && vec16( a.depthGrad ) && vec16( a.filteredVariance ) && vec16( a.histLen );
-    if( d.atrousMode == 0 && !pair && wsOk )
+    if( ( d.atrousMode == 0 || ( d.atrousMode == 3 && last ) ) && !pair && wsOk )
     {
         const int    th      = atrousWsTileH( step );
         const int    rowSets = ( ( rows + th * step - 1 ) / ( th * step ) ) * step;
@@ -474,7 +478,7 @@ AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t
     NEED( ASVGF_IMAGE_PRE_FINAL, ASVGF_IMAGE_THROUGHPUT, ASVGF_IMAGE_FINAL );
     ResolveArgs a;
     a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.final_ = d.get( ASVGF_IMAGE_FINAL, fi );
-    k_checkerboard_resolve<<< gridFor( ( int )d.W, d.ownEnd - d.ownBegin ), kBlock, 0, s >>>( a, u );
+    k_checkerboard_resolve<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_checkerboard_resolve" );
 }
 
@@ -497,9 +501,9 @@ AsvgfResult runLuminanceHistogram( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t 
     AsvgfResult r = launchCheck( d, "k_lum_bin_table" );
     if( r != ASVGF_SUCCESS ) return r;
     const size_t smem   = 65536 + ( kLumThreads / 32 ) * 256 * sizeof( uint32_t );
-    const long   groups = ( long )( d.ownEnd - d.ownBegin ) * ( ( d.W + 7 ) / 8 );
+    const long   groups = ( long )( u.yEnd - u.yBegin ) * ( ( d.W + 7 ) / 8 );
     long         ctas   = ( groups + kLumThreads - 1 ) / kLumThreads;
-    if( ctas > 2L * d.smCount ) ctas = 2L * d.smCount;
+    if( ctas > 3L * d.smCount ) ctas = 3L * d.smCount; // 73 KB of shared memory per CTA: three per SM
     if( ctas < 1 ) ctas = 1;
     cudaError_t e = cudaFuncSetAttribute( k_lum_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
     if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_lum_histogram)" );
@@ -514,7 +518,65 @@ AsvgfResult runLuminanceAverage( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi
     return launchCheck( d, "k_lum_average" );
 }
 
-AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
+// ASVGF_CREATE_BAND_APRON: rows beyond the owned band that a pass computes redundantly, so that every later pass of the
+// frame finds its inputs without a halo exchange.  A pass that reads +-r rows needs its producer to be valid r rows
+// further out: a-trous i reads +-2^i (CmSVGFAtrous.comp:61,126-140), iteration 0 and the variance pass +-1
+// (CmSVGFAtrous_Iter0.comp:121, CmSVGFEstimateVariance.comp:59), anti-firefly +-2 (CmAntiFirefly.comp:31); the temporal
+// pass reads the gradient image at row/3, gradient a-trous i reads +-2^i gradient rows (CmASVGFGradientAtrous.comp:57-60).
+// Gradient samples are computed on owned rows only (their output is exchanged once, asvgfBandApronRows(.., SAMPLES) deep).
+int apronRows( uint32_t iterations, uint32_t pass )
+{
+    int extA[ ASVGF_MAX_ATROUS_ITERATIONS ] = {};
+    for( int i = ( int )iterations - 1; i >= 1; i-- ) extA[ i - 1 ] = extA[ i ] + ( 1 << i );
+    const int extV = extA[ 0 ] + 1, extF = extV + 1, extT = extF + 2;
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_ATROUS_0 + iterations ) return extA[ pass - ASVGF_PASS_ATROUS_0 ];
+    if( pass == ASVGF_PASS_VARIANCE ) return extV;
+    if( pass == ASVGF_PASS_ANTIFIREFLY ) return extF;
+    if( pass == ASVGF_PASS_TEMPORAL ) return extT;
+    int g = ( extT + 2 ) / 3; // gradient rows the temporal pass touches beyond the band
+    if( pass == ASVGF_PASS_GRADIENT_ATROUS_3 ) return g;
+    for( int i = 3; i >= 1; i-- )
+    {
+        g += 1 << i;
+        if( pass == ( uint32_t )( ASVGF_PASS_GRADIENT_ATROUS_0 + i - 1 ) ) return g;
+    }
+    if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return g + 1; // depth of the one exchange of its output
+    return 0;
+}
+
+AsvgfResult runPassRows( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass );
+
+AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u0, uint32_t pass )
+{
+    if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL )
+    {
+        for( uint32_t i = 0; i < ASVGF_GRADIENT_ATROUS_ITERATIONS; i++ )
+        {
+            AsvgfResult r = runPass( d, s, fi, u0, ASVGF_PASS_GRADIENT_ATROUS_0 + i );
+            if( r != ASVGF_SUCCESS ) return r;
+        }
+        return ASVGF_SUCCESS;
+    }
+    Uniform u = u0;
+    d.passGyBegin = d.gownBegin; d.passGyEnd = d.gownEnd;
+    if( ( d.info.flags & ASVGF_CREATE_BAND_APRON ) && d.info.bandRowEnd != 0 )
+    {
+        const int ext = apronRows( d.iterations, pass );
+        if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 )
+        {
+            d.passGyBegin = std::max( d.grow0, d.gownBegin - ext );
+            d.passGyEnd   = std::min( d.grow0 + d.grows, d.gownEnd + ext );
+        }
+        else if( pass != ASVGF_PASS_GRADIENT_SAMPLES )
+        {
+            u.yBegin = std::max( d.row0, d.ownBegin - ext );
+            u.yEnd   = std::min( d.row0 + d.rows, d.ownEnd + ext );
+        }
+    }
+    return runPassRows( d, s, fi, u, pass );
+}
+
+AsvgfResult runPassRows( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
 {
     if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL )
     {
@@ -583,7 +645,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     if( const char* e = std::getenv( "ASVGF_ATROUS" ) )
     {
         d->atrousPair = std::strcmp( e, "pair" ) == 0;
-        d->atrousMode = std::strcmp( e, "ws" ) == 0 ? 1 : std::strcmp( e, "t2" ) == 0 ? 0 : 2;
+        d->atrousMode = std::strcmp( e, "ws" ) == 0 ? 1 : std::strcmp( e, "t2" ) == 0 ? 0 : std::strcmp( e, "auto" ) == 0 ? 3 : 2;
     }
     if( const char* e = std::getenv( "ASVGF_ATROUS_TILES" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 64 ) d->atrousTilesPerCta = n; }
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
@@ -869,6 +931,13 @@ const char* asvgfPassName( uint32_t pass )
     return "?";
 }
 
+// kernel the default configuration launches for a pass of an N-iteration chain (the composing a-trous iteration runs k_atrous_t2)
+const char* asvgfPassKernelName( uint32_t pass, uint32_t atrousIterations )
+{
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass + 1 == ASVGF_PASS_ATROUS_0 + atrousIterations ) return "k_atrous_t2";
+    return asvgfPassName( pass );
+}
+
 // Algorithmic HBM bytes per full-resolution pixel: unique reads + writes in the reference's storage formats
 // (BASELINE.md section 3).
 double asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations )
@@ -881,6 +950,12 @@ double asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations )
     if( pass == ASVGF_PASS_VARIANCE ) return 30.0;
     if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_ATROUS_0 + atrousIterations ) return pass + 1 == ASVGF_PASS_ATROUS_0 + atrousIterations ? 55.0 : 52.0;
     return 0.0;
+}
+
+int32_t asvgfBandApronRows( uint32_t atrousIterations, uint32_t pass )
+{
+    if( atrousIterations < 2 || atrousIterations > ASVGF_MAX_ATROUS_ITERATIONS ) return -1;
+    return apronRows( atrousIterations, pass );
 }
 
 const char* asvgfResultString( AsvgfResult r )

@@ -109,30 +109,43 @@ __global__ void __launch_bounds__( kLumThreads ) k_lum_histogram( const __grid_c
     const int  gpr  = ( u.W + 7 ) / 8;
     const long total = ( long )rows * gpr;
     const bool vec  = ( a.histogramInput.pitch % 16 ) == 0 && ( ( uintptr_t )a.histogramInput.p0 % 16 ) == 0;
-    const long span = ( ( total + kLumThreads - 1 ) / kLumThreads ) * kLumThreads; // whole warps stay converged for the ballots
-    for( long g = ( long )blockIdx.x * kLumThreads + threadIdx.x; g < span; g += ( long )gridDim.x * kLumThreads )
+    // four groups per thread in flight (the pass is latency-bound otherwise: ncu showed 22 % issue, 6 % DRAM with one)
+    constexpr int UNR = 4;
+    const long stride = ( long )gridDim.x * kLumThreads;
+    const long span   = ( ( total + stride * UNR - 1 ) / ( stride * UNR ) ) * ( stride * UNR ); // whole warps stay converged for the ballots
+    for( long g0 = ( long )blockIdx.x * kLumThreads + threadIdx.x; g0 < span; g0 += stride * UNR )
     {
-        const bool in = g < total;
-        const int  r = in ? ( int )( g / gpr ) : 0, x0 = in ? ( int )( g - ( long )r * gpr ) * 8 : 0, y = u.yBegin + r;
-        uint32_t   w[ 4 ] = { 0u, 0u, 0u, 0u };
-        const bool full = in && x0 + 8 <= u.W && vec;
-        if( full )
+        uint32_t w[ UNR ][ 4 ];
+        int      x0s[ UNR ];
+        bool     ins[ UNR ];
+#pragma unroll
+        for( int q = 0; q < UNR; q++ )
         {
-            const uint4 v = __ldg( reinterpret_cast< const uint4* >( at< uint16_t >( a.histogramInput, x0, y ) ) );
-            w[ 0 ] = v.x; w[ 1 ] = v.y; w[ 2 ] = v.z; w[ 3 ] = v.w;
+            const long g  = g0 + q * stride;
+            const bool in = g < total;
+            const int  r = in ? ( int )( g / gpr ) : 0, x0 = in ? ( int )( g - ( long )r * gpr ) * 8 : 0, y = u.yBegin + r;
+            ins[ q ] = in; x0s[ q ] = x0;
+            w[ q ][ 0 ] = w[ q ][ 1 ] = w[ q ][ 2 ] = w[ q ][ 3 ] = 0u;
+            if( in && x0 + 8 <= u.W && vec )
+            {
+                const uint4 v = __ldg( reinterpret_cast< const uint4* >( at< uint16_t >( a.histogramInput, x0, y ) ) );
+                w[ q ][ 0 ] = v.x; w[ q ][ 1 ] = v.y; w[ q ][ 2 ] = v.z; w[ q ][ 3 ] = v.w;
+            }
+            else if( in )
+            {
+#pragma unroll
+                for( int k = 0; k < 8; k++ )
+                    if( x0 + k < u.W ) w[ q ][ k >> 1 ] |= ( uint32_t )__ldg( at< uint16_t >( a.histogramInput, x0 + k, y ) ) << ( 16 * ( k & 1 ) );
+            }
         }
-        else if( in )
-        {
+#pragma unroll
+        for( int q = 0; q < UNR; q++ )
 #pragma unroll
             for( int k = 0; k < 8; k++ )
-                if( x0 + k < u.W ) w[ k >> 1 ] |= ( uint32_t )__ldg( at< uint16_t >( a.histogramInput, x0 + k, y ) ) << ( 16 * ( k & 1 ) );
-        }
-#pragma unroll
-        for( int k = 0; k < 8; k++ )
-        {
-            const uint32_t h = ( w[ k >> 1 ] >> ( 16 * ( k & 1 ) ) ) & 0xffffu;
-            count( sTable[ h ], in && x0 + k < u.W );
-        }
+            {
+                const uint32_t h = ( w[ q ][ k >> 1 ] >> ( 16 * ( k & 1 ) ) ) & 0xffffu;
+                count( sTable[ h ], ins[ q ] && x0s[ q ] + k < u.W );
+            }
     }
     __syncthreads();
     // CmLuminanceHistogram.comp:82-85: the work group's bins go to the global histogram

@@ -21,12 +21,13 @@ SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND = ran
 CREATE_EXPORT_DEBUG_MASK = 1 << 0
 CREATE_EXTERNAL_IMAGES = 1 << 1
 CREATE_LITERAL_KERNELS = 1 << 2
+CREATE_BAND_APRON = 1 << 3
 
 EXPORTED_SYMBOLS = [
     "asvgfCreate", "asvgfDestroy", "asvgfGetImageInfo", "asvgfGetImage", "asvgfBindExternalImage", "asvgfUploadImage",
     "asvgfDownloadImage", "asvgfResetHistory", "asvgfGradientSamples", "asvgfDenoise", "asvgfDenoisePass",
     "asvgfSynchronize", "asvgfGetLaunchCount", "asvgfPassName", "asvgfPassBytesPerPixel", "asvgfResultString",
-    "asvgfLastErrorMessage", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
+    "asvgfLastErrorMessage", "asvgfPassKernelName", "asvgfBandApronRows", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
     "asvgfLuminanceAverage", "asvgfGetTonemappingBuffer", "asvgfUploadTonemapping", "asvgfDownloadTonemapping",
 ]
 
@@ -77,6 +78,10 @@ def lib():
         L.asvgfGetLaunchCount.restype = ctypes.c_uint64
         L.asvgfPassName.argtypes = [u32]
         L.asvgfPassName.restype = ctypes.c_char_p
+        L.asvgfBandApronRows.argtypes = [u32, u32]
+        L.asvgfBandApronRows.restype = ctypes.c_int32
+        L.asvgfPassKernelName.argtypes = [u32, u32]
+        L.asvgfPassKernelName.restype = ctypes.c_char_p
         L.asvgfPassBytesPerPixel.argtypes = [u32, u32]
         L.asvgfPassBytesPerPixel.restype = ctypes.c_double
         L.asvgfResultString.argtypes = [ctypes.c_int]
@@ -97,6 +102,11 @@ def _check(code, where):
 
 def pass_bytes_per_pixel(p, iterations=4):
     return lib().asvgfPassBytesPerPixel(p, iterations)
+
+
+def band_apron_rows(iterations, p):
+    """ASVGF_CREATE_BAND_APRON: rows a pass computes beyond the owned band (gradient rows for the gradient passes)."""
+    return lib().asvgfBandApronRows(iterations, p)
 
 
 def chain_bytes_per_pixel(iterations=4, with_gradient_samples=True):

@@ -51,6 +51,43 @@ def test_schedule_matches_the_dispatch_order_and_reaches():
     assert bands.physical_name("Motion", 1) == "Motion" and bands.physical_name("IndirAccum_Prev", 0) == "IndirAccum_Prev"
 
 
+def test_cost_weighted_band_rows():
+    """Bands of equal summed cost instead of equal height (measured load balancing of bench.py --band-balance measured)."""
+    H = 4320
+    assert bands.band_rows(H, 4, np.ones(H)) == bands.band_rows(H, 4)
+    cost = np.r_[np.full(H // 2, 3.0), np.full(H // 2, 3.9)]          # the 8K synthetic scene: bottom half 30 % dearer
+    b = bands.band_rows(H, 2, cost)
+    assert b[0] == 0 and b[2] == H and b[1] % 3 == 0 and b[1] > H // 2
+    assert abs(cost[:b[1]].sum() - cost[b[1]:].sum()) <= 3 * cost.max() * 1.01
+    assert bands.rebalanced_rows([0, 2160, 4320], [3.0, 3.9]) == b
+    r = bands.rebalanced_rows([0, 1080, 2160, 3240, 4320], [0.1, 0.1, 5.0, 5.0], min_rows=66)
+    assert all(r[k + 1] - r[k] >= 66 and r[k] % 3 == 0 for k in range(4)) and r[-1] == H
+    p = bands.BandPlan(H, 2, 1, halo_rows=66, boundaries=b)
+    assert p.own == (b[1], H) and p.stored == (b[1] - 66, H)
+    with pytest.raises(ValueError):
+        bands.BandPlan(H, 2, 0, halo_rows=66, boundaries=[0, 2000, H])   # 2000 is not a multiple of 3
+    with pytest.raises(ValueError):
+        bands.band_rows(H, 2, np.ones(H - 1))
+
+
+def test_apron_extents_and_schedule():
+    """ASVGF_CREATE_BAND_APRON: the rows each pass computes beyond the band are the summed reaches of the passes after
+    it, and the apron schedule keeps only two exchanges: previous-frame state before, gradient samples after pass 0."""
+    from raytracedgl1_b200 import denoiser as dn
+    rows = {p: dn.band_apron_rows(4, p) for p in range(12)}
+    assert [rows[p] for p in (11, 10, 9, 8)] == [0, 8, 12, 14]             # a-trous 3..0: +8, +4, +2 (CmSVGFAtrous.comp:61)
+    assert (rows[layout.PASS_VARIANCE], rows[layout.PASS_ANTIFIREFLY], rows[layout.PASS_TEMPORAL]) == (15, 16, 18)
+    assert [rows[p] for p in (4, 3, 2, 1)] == [6, 14, 18, 20]              # gradient a-trous 3..0, gradient rows (18/3, +8, +4, +2)
+    assert rows[layout.PASS_GRADIENT_SAMPLES] == 21
+    assert dn.band_apron_rows(5, layout.PASS_TEMPORAL) == 34 and dn.band_apron_rows(1, 0) == -1
+    rows_of = lambda p: dn.band_apron_rows(4, p)  # noqa: E731
+    s = bands.frame_schedule_apron(4, rows_of)
+    assert [x[1] for x in s if x[0] == "pass"] == list(range(12))
+    ex = [i for i, x in enumerate(s) if x[0] == "exchange"]
+    assert ex == [0, 2] and s[2][1] == [(["DISPingGradient"], 21, True)]
+    assert bands.apron_halo_rows(4, rows_of) == 66 and bands.apron_halo_rows(5, lambda p: dn.band_apron_rows(5, p)) % 3 == 0
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -101,7 +138,7 @@ def test_halo_exchange_gloo(world):
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
-def _nccl_worker(rank, world, port, W, H, frames, q):
+def _nccl_worker(rank, world, port, W, H, frames, apron, boundaries, q):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -110,7 +147,7 @@ def _nccl_worker(rank, world, port, W, H, frames, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        band = bands.BandedDenoiser(W, H, 4, rank=rank, world=world, device=rank, halo_rows=48)
+        band = bands.BandedDenoiser(W, H, 4, rank=rank, world=world, device=rank, apron=apron, boundaries=boundaries)
         whole = bands.BandedDenoiser(W, H, 4, rank=0, world=1, device=rank) if rank == 0 else None
         ok, detail = True, []
         for f in range(frames):
@@ -150,7 +187,8 @@ def _nccl_worker(rank, world, port, W, H, frames, q):
 
 
 @pytest.mark.gpu
-def test_two_bands_bit_identical_to_single_gpu():
+@pytest.mark.parametrize("apron,boundaries", [(True, None), (False, None), (True, [0, 150, 360]), (False, [0, 231, 360])])
+def test_two_bands_bit_identical_to_single_gpu(apron, boundaries):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
@@ -158,7 +196,7 @@ def test_two_bands_bit_identical_to_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, 640, 360, 4, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, 640, 360, 4, apron, boundaries, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
