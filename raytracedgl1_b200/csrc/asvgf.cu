@@ -170,10 +170,10 @@ struct AsvgfDenoiser_T
     uint64_t  launchCount = 0;
     bool      atrousPair  = false; // ASVGF_ATROUS=pair selects the packed-f32x2 a-trous kernel (measured slower: the pass is smem-pipe bound)
     // a-trous kernel: 0 = k_atrous_t2 (vectorised staging + pair filter, one tile per CTA), 1 = k_atrous_ws (same, warp-specialised
-    // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop), 3 = auto: the measured best per iteration
-    // (k_atrous_tiled for the plain iterations, k_atrous_t2 for the composing one: 0.21/0.19/0.20/0.25 ms at 4K against
-    // 0.22/0.21/0.21/0.25 all-t2 and 0.21/0.19/0.20/0.30 all-tiled); ASVGF_ATROUS=auto|t2|ws|tiled|pair
-    int       atrousMode  = 3;
+    // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop; default: 0.20/0.19/0.19/0.23 ms at 4K with
+    // 64 x 8 tiles at four CTAs per SM, against 0.22/0.21/0.21/0.25 for t2), 3 = auto: tiled for the plain iterations, t2
+    // for the composing one; ASVGF_ATROUS=tiled|t2|ws|auto|pair
+    int       atrousMode  = 2;
     int       smCount     = 0;
     int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
     // exposure state (= the reference's tonemapping buffer) and the tables of the histogram pass
@@ -444,7 +444,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     // dilated tiles: 64 columns x 16 rows spaced `step` apart; grid.y enumerates (band of 16*step rows, residue)
     const int  bands = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
     const int  tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-    a.tilesPerCta     = pair ? 1 : d.atrousTilesPerCta;
+    a.tilesPerCta     = ( pair || !kAtMultiTile ) ? 1 : d.atrousTilesPerCta;
     const dim3 grid( ( unsigned )( ( tilesX + a.tilesPerCta - 1 ) / a.tilesPerCta ), ( unsigned )( bands * step ), 1 );
     auto launch = [ & ]( auto kernel ) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
@@ -931,10 +931,10 @@ const char* asvgfPassName( uint32_t pass )
     return "?";
 }
 
-// kernel the default configuration launches for a pass of an N-iteration chain (the composing a-trous iteration runs k_atrous_t2)
+// kernel the default configuration launches for a pass of an N-iteration chain
 const char* asvgfPassKernelName( uint32_t pass, uint32_t atrousIterations )
 {
-    if( pass >= ASVGF_PASS_ATROUS_0 && pass + 1 == ASVGF_PASS_ATROUS_0 + atrousIterations ) return "k_atrous_t2";
+    ( void )atrousIterations; // every a-trous iteration runs k_atrous_tiled by default
     return asvgfPassName( pass );
 }
 

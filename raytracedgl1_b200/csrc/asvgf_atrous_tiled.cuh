@@ -5,9 +5,10 @@
 // runs 2200 instructions per pixel with DRAM at 6 %; profiles/r01_v1_*, r01_v2_*):
 //
 //  * DILATED TILE.  For stride s a pixel only ever touches rows y, y+-s.  A CTA therefore owns 64 contiguous columns of
-//    16 rows spaced s apart (rows y0+r, y0+r+s, ...; the s residues r go to s different CTAs).  Its halo is one dilated
-//    row above/below and s columns left/right, so the read amplification is (18/16)*((64+2s)/64) = 1.16..1.41 for
+//    8 rows spaced s apart (rows y0+r, y0+r+s, ...; the s residues r go to s different CTAs).  Its halo is one dilated
+//    row above/below and s columns left/right, so the read amplification is (10/8)*((64+2s)/64) = 1.29..1.56 for
 //    every stride instead of the (1+2s/T)^2 of a square tile, and every global access is still a full-line row segment.
+//    (64 x 8 keeps a tile at 41-51 KB of shared memory and 64 registers per thread: four CTAs = 32 warps per SM.)
 //  * DECODE ONCE.  Each tile pixel is unpacked once on the way into shared memory -- normal through the exact sin/cos
 //    table, E5B9G9R9 and fp16 to fp32, luminance -- into four float4 planes, so a tap costs four conflict-free
 //    LDS.128 and no conversions.  The stride is a template parameter: every tap address is an immediate offset.
@@ -21,18 +22,29 @@
 
 #include "asvgf_fast.cuh"
 
+#include <type_traits>
+
 namespace asvgf
 {
 
+// Tile height / CTAs per SM.  Measured at 4K (ms per iteration, plain / composing), one tile per CTA:
+//   16 rows, 2 CTAs/SM (128 regs, 16 warps/SM): 0.22 / 0.25      8 rows, 3 CTAs/SM (80 regs): 0.21 / 0.23
+//    8 rows, 4 CTAs/SM ( 64 regs, 32 warps/SM): 0.19 / 0.23     16 rows, 2 x 512 threads (64 regs): 0.20 / 0.23
+// The pass is bound by issue latency (a long dependent chain per tap), so the warps per SM matter more than the 11 %
+// of extra halo rows the shorter tile stages.
 #ifndef ASVGF_AT_TILE_H
-    #define ASVGF_AT_TILE_H 16
+    #define ASVGF_AT_TILE_H 8
 #endif
 #ifndef ASVGF_AT_THREADS
     #define ASVGF_AT_THREADS 256
 #endif
 #ifndef ASVGF_AT_MIN_CTAS
-    #define ASVGF_AT_MIN_CTAS 2
+    #define ASVGF_AT_MIN_CTAS 4
 #endif
+#ifndef ASVGF_AT_MULTI_TILE
+    #define ASVGF_AT_MULTI_TILE 0 // 1: a CTA walks a.tilesPerCta tiles with the next tile's loads in flight (measured equal to one tile per CTA)
+#endif
+constexpr bool kAtMultiTile = ASVGF_AT_MULTI_TILE != 0;
 constexpr int kAtTileW   = 64;               // columns per CTA
 constexpr int kAtTileH   = ASVGF_AT_TILE_H;  // dilated rows per CTA
 constexpr int kAtThreads = ASVGF_AT_THREADS; // 4 pixels per thread
@@ -91,11 +103,12 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
     // tile's HBM latency is exposed.
     const int band  = blockIdx.y / STEP, res = blockIdx.y - band * STEP;
     const int yBase = u.yBegin + band * ( kAtTileH * STEP ) + res;
-    const int xFirst = blockIdx.x * a.tilesPerCta * kAtTileW;
+    const int nTilesCta = kAtMultiTile ? a.tilesPerCta : 1;
+    const int xFirst = blockIdx.x * nTilesCta * kAtTileW;
     const Rows rows = rowsOf( a.depth );
 
     AtrousRaw raw[ NIT ];
-    AtrousCentre< ITER0, LAST > cen[ PIX ], cenNext[ PIX ];
+    AtrousCentre< ITER0, LAST > cen[ PIX ], cenNext[ kAtMultiTile ? PIX : 1 ];
 
     auto issue = [ & ]( int xBase, AtrousCentre< ITER0, LAST >( &cc )[ PIX ] )
     {
@@ -154,19 +167,22 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
     };
 
     issue( xFirst, cen );
-  for( int t = 0; t < a.tilesPerCta; t++ )
+  for( int t = 0; t < nTilesCta; t++ )
   {
     const int xBase = xFirst + t * kAtTileW;
     if( xBase >= u.W ) break;
-    if( t > 0 )
+    if( kAtMultiTile && t > 0 )
     {
         __syncthreads(); // every warp is done reading the previous tile
 #pragma unroll
-        for( int k = 0; k < PIX; k++ ) cen[ k ] = cenNext[ k ];
+        for( int k = 0; k < PIX; k++ ) cen[ k ] = cenNext[ kAtMultiTile ? k : 0 ];
     }
     commit();
     __syncthreads();
-    if( t + 1 < a.tilesPerCta && xBase + kAtTileW < u.W ) issue( xBase + kAtTileW, cenNext ); // in flight during the arithmetic below
+    if constexpr( kAtMultiTile )
+    {
+        if( t + 1 < nTilesCta && xBase + kAtTileW < u.W ) issue( xBase + kAtTileW, cenNext ); // in flight during the arithmetic below
+    }
 
     const int       sep   = u.W / 2;
     constexpr float LOG2E = 1.4426950408889634f;
@@ -222,48 +238,77 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             const float kLum = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
 
             const float wRoughMultiplier  = saturatef( fmaf( roughness, 30.0f, -( float )a.iteration ) );
+            const float wR10              = wRoughMultiplier * 10.0f;
             const float historyLengthSpec = __low2float( *reinterpret_cast< const __half2* >( &cen[ k ].histLen.y ) );
             const float alpha             = roughness * roughness;
             float       P                 = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
             P                             = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
-            const float invK1 = frcp( fmaxf( gradDepth, 0.01f ) ), invK2 = frcp( fmaxf( gradDepth * 2.0f, 0.01f ) );
+            // 1/max(g,.01) = min(1/g,100) and 1/max(2g,.01) = min(.5/g,100) from one MUFU (g >= 0; 1/0 = inf), pre-scaled by
+            // sqrt(log2 e) so that -wZ*wZ is already the base-2 exponent
+            constexpr float SQRT_LOG2E = 1.2011224087864498f;
+            const float rgd   = frcp( gradDepth );
+            const float invK1 = SQRT_LOG2E * fminf( rgd, 100.0f ), invK2 = SQRT_LOG2E * fminf( 0.5f * rgd, 100.0f );
 
-            // log2 of the wavelet weight per tap, -inf for taps outside the checkerboarded render area
-            // (ShaderCommonGLSLFunc.h:345-366): taps never cross x = W/2 or leave the frame
-            const int   ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
-            const float lkx[ 3 ] = { px - STEP >= ax0 ? -1.0f : NINF, 0.0f, px + STEP < ax1 ? -1.0f : NINF };
-            const float lky[ 3 ] = { py - STEP >= 0 ? -1.0f : NINF, 0.0f, py + STEP < u.H ? -1.0f : NINF };
+            // taps outside the checkerboarded render area (ShaderCommonGLSLFunc.h:345-366: they never cross x = W/2 or
+            // leave the frame) get exponent -inf; interior pixels take the loop whose wavelet weights are immediates
+            const int  ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+            const bool okL = px - STEP >= ax0, okR = px + STEP < ax1, okT = py - STEP >= 0, okB = py + STEP < u.H;
+            const float PINF = __uint_as_float( 0x7f800000u );
 
             float weightSum = 1.0f, weightSumSpec = 1.0f, weightSumIndir = 1.0f;
 
-#pragma unroll
-            for( int yy = -1; yy <= 1; yy++ )
+            auto taps = [ & ]( auto interiorTag )
             {
+                constexpr bool INTERIOR = decltype( interiorTag )::value;
 #pragma unroll
-                for( int xx = -1; xx <= 1; xx++ )
+                for( int yy = -1; yy <= 1; yy++ )
                 {
-                    if( xx == 0 && yy == 0 ) continue;
-                    const int    qe = ce + yy * TW + xx * STEP;
-                    const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
+#pragma unroll
+                    for( int xx = -1; xx <= 1; xx++ )
+                    {
+                        if( xx == 0 && yy == 0 ) continue;
+                        const int    qe = ce + yy * TW + xx * STEP;
+                        const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
 
-                    const float nN = fmaxf( 0.0f, fmaf( cA.z, qA.z, fmaf( cA.y, qA.y, cA.x * qA.x ) ) );
-                    const float L  = fmaxf( flg2( nN ), -126.0f );
-                    const float wZ = fabsf( depth - qA.w ) * ( ( xx != 0 && yy != 0 ) ? invK2 : invK1 );
-                    const float e0    = fmaf( 128.0f, L, lkx[ xx + 1 ] + lky[ yy + 1 ] );
-                    const float eBase = fmaf( wZ * -LOG2E, wZ, e0 );
-                    const float eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
-                    const float wBase = fex2( eBase );
-                    const float wDiff = ex2ApproxDenorm( eDiff );
-                    const float rfac  = fmaxf( 0.0f, fmaf( fabsf( roughness - qD.w ), -10.0f, 1.0f ) ) * wRoughMultiplier;
-                    const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
+                        const float nN = fmaxf( 0.0f, fmaf( cA.z, qA.z, fmaf( cA.y, qA.y, cA.x * qA.x ) ) );
+                        const float L  = fmaxf( flg2( nN ), -126.0f );
+                        const float wZ = fabsf( depth - qA.w ) * ( ( xx != 0 && yy != 0 ) ? invK2 : invK1 );
+                        float       lk = ( xx != 0 && yy != 0 ) ? -2.0f : -1.0f; // log2 of the wavelet weight
+                        if( !INTERIOR )
+                        {
+                            const bool in = ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true );
+                            lk            = in ? lk : NINF;
+                        }
+                        const float e0    = fmaf( 128.0f, L, lk );
+                        const float eBase = fmaf( -wZ, wZ, e0 );
+                        const float eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
+                        const float wBase = fex2( eBase );
+                        const float wDiff = fex2( eDiff );
+                        float       rfac; // max(0, 1 - 10|dr|) * wRough, both factors in [0,1]
+                        asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( roughness - qD.w ) ), "f"( -wR10 ), "f"( wRoughMultiplier ) );
+                        const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
 
-                    outDiff.x = fmaf( qB.x, wDiff, outDiff.x ); outDiff.y = fmaf( qB.y, wDiff, outDiff.y ); outDiff.z = fmaf( qB.z, wDiff, outDiff.z );
-                    outSpec.x = fmaf( qC.x, wSpec, outSpec.x ); outSpec.y = fmaf( qC.y, wSpec, outSpec.y ); outSpec.z = fmaf( qC.z, wSpec, outSpec.z );
-                    outIndir.x = fmaf( qD.x, wBase, outIndir.x ); outIndir.y = fmaf( qD.y, wBase, outIndir.y ); outIndir.z = fmaf( qD.z, wBase, outIndir.z );
-                    outVariance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, outVariance ); // (var*w)*w: inf*denormal stays inf, like the shader
-                    weightSum += wDiff; weightSumSpec += wSpec; weightSumIndir += wBase;
+                        outDiff.x = fmaf( qB.x, wDiff, outDiff.x ); outDiff.y = fmaf( qB.y, wDiff, outDiff.y ); outDiff.z = fmaf( qB.z, wDiff, outDiff.z );
+                        outSpec.x = fmaf( qC.x, wSpec, outSpec.x ); outSpec.y = fmaf( qC.y, wSpec, outSpec.y ); outSpec.z = fmaf( qC.z, wSpec, outSpec.z );
+                        outIndir.x = fmaf( qD.x, wBase, outIndir.x ); outIndir.y = fmaf( qD.y, wBase, outIndir.y ); outIndir.z = fmaf( qD.z, wBase, outIndir.z );
+                        weightSum += wDiff; weightSumSpec += wSpec; weightSumIndir += wBase;
+                        // (var*w)*w: MUFU.EX2 flushes a denormal weight to zero where the shader's exp() keeps it, which only
+                        // shows when the tap's fp16 variance is +inf (inf*denormal = inf, inf*0 = NaN): only that case pays
+                        // for the denormal-preserving exponential
+                        if( qB.w == PINF )
+                        {
+                            const float wd = ex2ApproxDenorm( eDiff );
+                            outVariance    = fmaf( __fmul_rn( qB.w, wd ), wd, outVariance );
+                        }
+                        else
+                        {
+                            outVariance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, outVariance );
+                        }
+                    }
                 }
-            }
+            };
+            if( okL && okR && okT && okB ) taps( std::true_type{} );
+            else taps( std::false_type{} );
             const float inv = frcp( weightSum ), invSpec = frcp( weightSumSpec ), invIndir = frcp( weightSumIndir );
             outDiff     = make_float3( outDiff.x * inv, outDiff.y * inv, outDiff.z * inv );
             outVariance = outVariance * ( inv * inv );
