@@ -378,12 +378,13 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     auto vec16 = [ & ]( const Img& im ) { return ( ( uintptr_t )im.p % 16 ) == 0 && ( im.pitch % 16 ) == 0; };
     const bool wsOk = ( d.W % 4 ) == 0 && step <= 32 && vec16( a.normal ) && vec16( a.depth ) && vec16( a.metRough ) && vec16( a.srcDiff ) && vec16( a.srcSpec ) &&
                       vec16( a.srcIndir ) && vec16( a.depthGrad ) && vec16( a.filteredVariance ) && vec16( a.histLen );
-    if( ( d.atrousMode == 0 || ( d.atrousMode == 3 && last ) ) && !pair && wsOk )
+    if( ( d.atrousMode == 0 || d.atrousMode == 4 || ( d.atrousMode == 3 && last ) ) && !pair && wsOk )
     {
-        const int    th      = atrousWsTileH( step );
+        const bool   t3      = d.atrousMode == 4; // 64 x 8 tiles, single pixels, four CTAs per SM
+        const int    th      = t3 ? kT3TileH : atrousWsTileH( step );
         const int    rowSets = ( ( rows + th * step - 1 ) / ( th * step ) ) * step;
         const int    tilesX  = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-        const size_t smemT2  = atrousT2SmemBytes( step );
+        const size_t smemT2  = atrousT2SmemBytes( step, th );
         const dim3   grid( ( unsigned )tilesX, ( unsigned )rowSets, 1 );
         auto launchT2 = [ & ]( auto kernel ) -> cudaError_t {
             cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smemT2 );
@@ -392,11 +393,12 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
             return cudaSuccess;
         };
         cudaError_t e = cudaErrorInvalidValue;
+#define ASVGF_T2_KERNEL( S, I0, L ) ( t3 ? launchT2( k_atrous_t2< S, I0, L, kT3TileH, false, kT3MinCtas > ) : launchT2( k_atrous_t2< S, I0, L, atrousWsTileH( S ), true, ASVGF_T2_MIN_CTAS > ) )
 #define ASVGF_T2_CASE( S ) \
-    case S: e = last ? launchT2( k_atrous_t2< S, false, true > ) : launchT2( k_atrous_t2< S, false, false > ); break;
+    case S: e = last ? ASVGF_T2_KERNEL( S, false, true ) : ASVGF_T2_KERNEL( S, false, false ); break;
         switch( step )
         {
-            case 1: e = launchT2( k_atrous_t2< 1, true, false > ); break; // iteration 0 is never the last
+            case 1: e = ASVGF_T2_KERNEL( 1, true, false ); break; // iteration 0 is never the last
             ASVGF_T2_CASE( 2 )
             ASVGF_T2_CASE( 4 )
             ASVGF_T2_CASE( 8 )
@@ -405,6 +407,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
             default: break;
         }
 #undef ASVGF_T2_CASE
+#undef ASVGF_T2_KERNEL
         if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_t2)" );
         return launchCheck( d, "k_atrous_t2" );
     }
@@ -578,15 +581,6 @@ AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Unif
 
 AsvgfResult runPassRows( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
 {
-    if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL )
-    {
-        for( uint32_t i = 0; i < ASVGF_GRADIENT_ATROUS_ITERATIONS; i++ )
-        {
-            AsvgfResult r = runGradientAtrous( d, s, fi, u, i );
-            if( r != ASVGF_SUCCESS ) return r;
-        }
-        return ASVGF_SUCCESS;
-    }
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return runGradientSamples( d, s, fi, u );
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return runGradientAtrous( d, s, fi, u, pass - ASVGF_PASS_GRADIENT_ATROUS_0 );
     if( pass == ASVGF_PASS_TEMPORAL ) return runTemporal( d, s, fi, u );
@@ -645,7 +639,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     if( const char* e = std::getenv( "ASVGF_ATROUS" ) )
     {
         d->atrousPair = std::strcmp( e, "pair" ) == 0;
-        d->atrousMode = std::strcmp( e, "ws" ) == 0 ? 1 : std::strcmp( e, "t2" ) == 0 ? 0 : std::strcmp( e, "auto" ) == 0 ? 3 : 2;
+        d->atrousMode = std::strcmp( e, "ws" ) == 0 ? 1 : std::strcmp( e, "t2" ) == 0 ? 0 : std::strcmp( e, "auto" ) == 0 ? 3 : std::strcmp( e, "t3" ) == 0 ? 4 : 2;
     }
     if( const char* e = std::getenv( "ASVGF_ATROUS_TILES" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 64 ) d->atrousTilesPerCta = n; }
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;

@@ -529,6 +529,73 @@ __global__ void __launch_bounds__( kWsThreads, 1 ) k_atrous_ws( const __grid_con
     }
 }
 
+// One output pixel (dilated row j of tile column c) out of a staged tile: the eight taps one by one.
+template< int STEP, bool ITER0, bool LAST >
+ASVGF_DEVICE void atrousSingleUnit( const AtrousArgs& a, const Uniform& u, const float4* __restrict__ sA, const float4* __restrict__ sB, const float4* __restrict__ sC,
+                                    const float4* __restrict__ sD, const AtrousWsTile t, int j, int c, const uint2 cen )
+{
+    constexpr int HALO = atrousWsHalo( STEP ), GP = atrousWsGroupPitch( STEP ), RS = 4 * GP;
+    const int     sep  = u.W / 2;
+    const int px = t.xBase + c, py = t.yBase + j * STEP;
+    if( px >= u.W || py >= u.yEnd ) return;
+    const int x = c + HALO; // tile column
+    int       sx[ 3 ];      // in-row slots of columns x-STEP, x, x+STEP
+    sx[ 1 ] = ( x & 3 ) * GP + ( x >> 2 );
+    if( STEP >= 4 ) { sx[ 0 ] = sx[ 1 ] - STEP / 4; sx[ 2 ] = sx[ 1 ] + STEP / 4; }
+    else { sx[ 0 ] = ( ( x - STEP ) & 3 ) * GP + ( ( x - STEP ) >> 2 ); sx[ 2 ] = ( ( x + STEP ) & 3 ) * GP + ( ( x + STEP ) >> 2 ); }
+    const int row = ( j + 1 ) * RS, ce = row + sx[ 1 ];
+
+    AtrousComposeRaw raw;
+    if( LAST ) raw = atrousComposeLoad( a, u, px, py, true ); // in flight behind the taps
+
+    AtrousPx P;
+    {
+        const float4 cA = sA[ ce ], cB = sB[ ce ], cC = sC[ ce ], cD = sD[ ce ];
+        if( cA.w < 0.0f || cA.w > 10000.0f )
+        {
+            // Iter0.comp:208-216 writes zeros, CmSVGFAtrous.comp:96-99 passes the centre through
+            P.oD = ITER0 ? make_float3( 0.0f, 0.0f, 0.0f ) : make_float3( cB.x, cB.y, cB.z ); P.oV = ITER0 ? 0.0f : cB.w;
+            P.oS = ITER0 ? make_float3( 0.0f, 0.0f, 0.0f ) : make_float3( cC.x, cC.y, cC.z );
+            P.oI = ITER0 ? make_float3( 0.0f, 0.0f, 0.0f ) : make_float3( cD.x, cD.y, cD.z );
+            P.roughness = cD.w;
+        }
+        else
+        {
+            float sigma;
+            if( ITER0 ) // Iter0.comp:158-187: 3x3 Gaussian {1/4,1/8,1/16} of the variance (products by powers of two are exact)
+            {
+                float r = 0.0f;
+#pragma unroll
+                for( int yy = -1; yy <= 1; yy++ )
+#pragma unroll
+                    for( int xx = -1; xx <= 1; xx++ )
+                        r = fmaf( sB[ row + yy * RS + sx[ xx + 1 ] ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+                sigma = __fsqrt_rn( fmaxf( r, 0.0f ) );
+                *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( sigma );
+            }
+            else sigma = h2f( ( uint16_t )( cen.x >> 16 ) );
+            atrousWsSetup( P, cA, cB, cC, cD, cen, sigma, a.iteration );
+            const int  ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+            const bool okL = px - STEP >= ax0, okR = px + STEP < ax1, okT = py - STEP >= 0, okB = py + STEP < u.H;
+#pragma unroll
+            for( int yy = -1; yy <= 1; yy++ )
+#pragma unroll
+                for( int xx = -1; xx <= 1; xx++ )
+                {
+                    if( xx == 0 && yy == 0 ) continue;
+                    const int    qe = row + yy * RS + sx[ xx + 1 ];
+                    const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
+                    const bool   in = ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true );
+                    if( xx != 0 && yy != 0 ) atrousWsTap< true, true >( P, qA, qB, qC, qD, in );
+                    else atrousWsTap< false, true >( P, qA, qB, qC, qD, in );
+                }
+            atrousWsNormalise( P );
+        }
+    }
+    if( !LAST ) atrousWsStore( a, px, py, P );
+    else atrousCompose( a, u, px, py, P, raw );
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // k_atrous_t2: the same staged tile (4-pixel loads, quarter-row slots) and the same pair filter, but one tile per CTA
 // and every thread in both roles: stage, __syncthreads, filter.  Two CTAs per SM overlap one's staging with the
@@ -541,23 +608,26 @@ constexpr int kT2Threads = ASVGF_T2_THREADS;
 #ifndef ASVGF_T2_MIN_CTAS
     #define ASVGF_T2_MIN_CTAS 2
 #endif
-constexpr size_t atrousT2SmemBytes( int step ) { return ( size_t )( 4 * atrousWsGroupPitch( step ) ) * ( atrousWsTileH( step ) + 2 ) * kAtBytesPerTilePixel; }
+constexpr size_t atrousT2SmemBytes( int step, int tileH ) { return ( size_t )( 4 * atrousWsGroupPitch( step ) ) * ( tileH + 2 ) * kAtBytesPerTilePixel; }
+// "t3" = the t2 staging with 64 x 8 tiles and ONE pixel per tap loop at 64 registers: four CTAs (32 warps) per SM
+constexpr int kT3TileH = 8, kT3MinCtas = 4;
 
-template< int STEP, bool ITER0, bool LAST >
-__global__ void __launch_bounds__( kT2Threads, ASVGF_T2_MIN_CTAS ) k_atrous_t2( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
+// TH = dilated rows per tile, PAIR = a thread filters a vertical pixel pair (else single pixels), CTAS = CTAs per SM
+template< int STEP, bool ITER0, bool LAST, int TH, bool PAIR, int CTAS >
+__global__ void __launch_bounds__( kT2Threads, CTAS ) k_atrous_t2( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
     extern __shared__ __align__( 16 ) uint8_t smemRaw[];
     constexpr int HALO  = atrousWsHalo( STEP );
     constexpr int G     = atrousWsGroups( STEP );
     constexpr int GP    = atrousWsGroupPitch( STEP );
     constexpr int RS    = 4 * GP;
-    constexpr int TH    = atrousWsTileH( STEP );
     constexpr int TROWS = TH + 2;
     constexpr int NPX   = RS * TROWS;
     constexpr int TUNITS = TROWS * G;
     constexpr int NR    = ( TUNITS + kT2Threads - 1 ) / kT2Threads;
-    constexpr int UNITS = kAtTileW * ( TH / 2 );
+    constexpr int UNITS = PAIR ? kAtTileW * ( TH / 2 ) : kAtTileW * TH;
     constexpr int NU    = ( UNITS + kT2Threads - 1 ) / kT2Threads;
+    constexpr int PER   = PAIR ? 2 : 1; // output pixels per unit
     float4* sA = reinterpret_cast< float4* >( smemRaw ); // normal.xyz, depth
     float4* sB = sA + NPX;                               // diffuse rgb, variance
     float4* sC = sB + NPX;                               // specular rgb, luminance of the diffuse rgb
@@ -569,7 +639,7 @@ __global__ void __launch_bounds__( kT2Threads, ASVGF_T2_MIN_CTAS ) k_atrous_t2( 
     const int  tid  = threadIdx.x;
 
     // centre-only inputs of this thread's output pixels (fp16 bits), in flight behind the staging
-    uint2 cen[ NU ][ 2 ];
+    uint2 cen[ NU ][ PER ];
     int   ujp[ NU ], uc[ NU ];
 #pragma unroll
     for( int k = 0; k < NU; k++ )
@@ -581,9 +651,9 @@ __global__ void __launch_bounds__( kT2Threads, ASVGF_T2_MIN_CTAS ) k_atrous_t2( 
         const int c = ( c0 & ~31 ) + ( ( c0 & 7 ) << 2 ) + ( ( c0 >> 3 ) & 3 );
         ujp[ k ] = jp; uc[ k ] = c;
 #pragma unroll
-        for( int h = 0; h < 2; h++ )
+        for( int h = 0; h < PER; h++ )
         {
-            const int  px = t.xBase + c, py = t.yBase + ( 2 * jp + h ) * STEP;
+            const int  px = t.xBase + c, py = t.yBase + ( PER * jp + h ) * STEP;
             const bool ok = unit < UNITS && px < u.W && py < u.yEnd;
             const uint32_t gd = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
             const uint32_t sg = ITER0 ? 0u : ( uint32_t )ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
@@ -652,7 +722,8 @@ __global__ void __launch_bounds__( kT2Threads, ASVGF_T2_MIN_CTAS ) k_atrous_t2( 
     for( int k = 0; k < NU; k++ )
     {
         if( tid + k * kT2Threads >= UNITS ) break;
-        atrousPairUnit< STEP, ITER0, LAST >( a, u, sA, sB, sC, sD, t, ujp[ k ], uc[ k ], cen[ k ][ 0 ], cen[ k ][ 1 ] );
+        if constexpr( PAIR ) atrousPairUnit< STEP, ITER0, LAST >( a, u, sA, sB, sC, sD, t, ujp[ k ], uc[ k ], cen[ k ][ 0 ], cen[ k ][ PER - 1 ] );
+        else atrousSingleUnit< STEP, ITER0, LAST >( a, u, sA, sB, sC, sD, t, ujp[ k ], uc[ k ], cen[ k ][ 0 ] );
     }
 }
 

@@ -52,7 +52,7 @@ def test_per_pass_parity_from_identical_state(size):
         p.close()
 
 
-@pytest.mark.parametrize("variant", ["t2", "ws", "tiled", "pair"])
+@pytest.mark.parametrize("variant", ["t3", "t2", "ws", "tiled", "pair"])
 def test_atrous_kernel_variants(variant, monkeypatch):
     """Every a-trous kernel the library can select (ASVGF_ATROUS, read by asvgfCreate): the default one-tile-per-CTA
     pair filter (t2), the warp-specialised persistent kernel (ws), the scalar tiled kernel and the packed-f32x2 one.
