@@ -154,6 +154,15 @@ ASVGF_API AsvgfResult asvgfLuminanceHistogram( AsvgfDenoiser denoiser, AsvgfStre
                                                const AsvgfGlobalUniform* pUniform );
 ASVGF_API AsvgfResult asvgfLuminanceAverage( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                              const AsvgfGlobalUniform* pUniform );
+/* = Volumetric::ProcessScattering(cmd, frameIndex, uniform, ..., maxHistoryLength) (Source/Volumetric.cpp:71-195), shader
+   CmScatterAccum.comp:96-163: the frame's other temporal-reprojection pass.  Reprojects
+   ASVGF_IMAGE_SCATTERING_PREV / _HISTORY_PREV with the temporal pass's disocclusion tests and blends in this frame's
+   scattering sample: computed in place for volumeEnableType NONE and SIMPLE (:75-93), read from
+   ASVGF_IMAGE_SCATTER_CURRENT for VOLUMETRIC (the 3-D illumination-volume lookup of :41-73 is not image-space).
+   maxHistoryLength is the shader's push constant.  Enqueues only. */
+ASVGF_API AsvgfResult asvgfScatterAccumulate( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                              const AsvgfGlobalUniform* pUniform, float maxHistoryLength );
+
 /* Device address of the handle's AsvgfTonemapping (= the reference's tonemapping buffer, Tonemapping.cpp:183-191; zero-initialised here),
    and host copies of it enqueued on `stream`. */
 ASVGF_API AsvgfResult asvgfGetTonemappingBuffer( AsvgfDenoiser denoiser, void** ppDevice );

@@ -64,6 +64,10 @@ enum AsvgfImageIndex
     ASVGF_IMAGE_INDIR_PONG                   = 44,
     ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE     = 45, /* R16_SFLOAT                                  */
     ASVGF_IMAGE_HISTOGRAM_INPUT              = 46, /* R16_SFLOAT, regular layout        (OUTPUT)  */
+    ASVGF_IMAGE_SCATTERING                   = 48, /* R16G16B16A16_SFLOAT, regular layout: accumulated in-scattering rgb + transmittance (asvgfScatterAccumulate) */
+    ASVGF_IMAGE_SCATTERING_PREV              = 49,
+    ASVGF_IMAGE_SCATTERING_HISTORY           = 50, /* R16_SFLOAT, regular layout: its history length */
+    ASVGF_IMAGE_SCATTERING_HISTORY_PREV      = 51,
     ASVGF_IMAGE_GRADIENT_INPUTS              = 70, /* R16G16_SFLOAT                               */
     ASVGF_IMAGE_GRADIENT_INPUTS_PREV         = 71,
     ASVGF_IMAGE_DIS_PING_GRADIENT            = 72, /* R8G8B8A8_UNORM, 1/3 resolution              */
@@ -77,8 +81,16 @@ enum AsvgfImageIndex
                                     sample; stands in for the ray-traced step RtGradients.rgen:107-136            */
     ASVGF_IMAGE_DEBUG_MASK = 77, /* R8_UINT: bit0..3 per-tap isConsistent, bit4 weightSum>1e-4,
                                     bit5 weightSumVirtual>1e-4 (CmSVGFTemporalAccumulation.comp:159-176,202,282)  */
-    ASVGF_IMAGE_COUNT      = 78
+    ASVGF_IMAGE_SCATTER_CURRENT = 78, /* R16G16B16A16_SFLOAT, regular layout: this frame's scattering sample when
+                                    volumeEnableType == VOLUMETRIC; stands in for the 3-D illumination-volume lookup
+                                    volume_sampleDithered of CmScatterAccum.comp:41-73 (not an image-space operation) */
+    ASVGF_IMAGE_COUNT      = 79
 };
+
+/* ShGlobalUniform.volumeEnableType (ShaderCommonC.h:195-197) */
+#define ASVGF_VOLUME_ENABLE_NONE 0u
+#define ASVGF_VOLUME_ENABLE_SIMPLE 1u
+#define ASVGF_VOLUME_ENABLE_VOLUMETRIC 2u
 
 enum AsvgfFormat
 {
@@ -135,7 +147,10 @@ typedef struct AsvgfGlobalUniform
     float    cameraPosition[ 4 ];  /*  720 */
     float    cameraPositionPrev[ 4 ]; /* 736 */
     uint32_t debugShowFlags;       /*  752 */
-    uint32_t _reserved3[ 44 ];     /*  756 */
+    uint32_t _reserved3[ 19 ];     /*  756 */
+    uint32_t volumeEnableType;     /*  832  ASVGF_VOLUME_ENABLE_* (asvgfScatterAccumulate) */
+    float    volumeScattering;     /*  836 */
+    uint32_t _reserved3b[ 23 ];    /*  840 */
     float    jitterX;              /*  932 */
     float    jitterY;              /*  936 */
     uint32_t _reserved4[ 6 ];      /*  940 */
@@ -144,7 +159,8 @@ typedef struct AsvgfGlobalUniform
     float    gradientMultSpecular; /*  972 */
     uint32_t _reserved5[ 3 ];      /*  976 */
     uint32_t antiFireflyEnabled;   /*  988 */
-    uint32_t _reserved6[ 276 ];    /*  992 */
+    float    volumeAmbient[ 4 ];   /*  992 */
+    uint32_t _reserved6[ 272 ];    /* 1008 */
 } AsvgfGlobalUniform;              /* 2096 */
 
 /* Byte-compatible with ShTonemapping (ShaderCommonC.h:344-348): the exposure state asvgfCalculateExposure keeps. */
@@ -160,6 +176,8 @@ typedef struct AsvgfTonemapping
 static_assert( sizeof( AsvgfGlobalUniform ) == 2096, "must match ShGlobalUniform" );
 static_assert( offsetof( AsvgfGlobalUniform, minLogLuminance ) == 668, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, stopEyeAdaptation ) == 680, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, volumeEnableType ) == 832, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, volumeAmbient ) == 992, "layout" );
 static_assert( sizeof( AsvgfTonemapping ) == 1028, "must match ShTonemapping" );
 static_assert( offsetof( AsvgfGlobalUniform, viewPrev ) == 128, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, projectionPrev ) == 320, "layout" );

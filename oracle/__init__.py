@@ -47,6 +47,7 @@ def lib():
         L.asvgfOracleLuminanceHistogram.argtypes = [vp, u32, puni]
         L.asvgfOracleLuminanceAverage.argtypes = [vp, puni]
         L.asvgfOracleCalculateExposure.argtypes = [vp, u32, puni]
+        L.asvgfOracleScatterAccumulate.argtypes = [vp, u32, puni, f32]
         L.asvgfOracleGetTonemapping.argtypes = [vp]
         L.asvgfOracleGetTonemapping.restype = ctypes.POINTER(layout.Tonemapping)
         L.asvgfOracleEncodeE5B9G9R9.restype = u32
@@ -111,6 +112,9 @@ class Oracle:
 
     def denoise(self, frame_index, uniform):
         lib().asvgfOracleDenoise(self._h, frame_index, ctypes.byref(uniform))
+
+    def scatter_accumulate(self, frame_index, uniform, max_history_length):
+        lib().asvgfOracleScatterAccumulate(self._h, frame_index, ctypes.byref(uniform), max_history_length)
 
     def resolve_checkerboard(self, frame_index, uniform):
         lib().asvgfOracleResolveCheckerboard(self._h, frame_index, ctypes.byref(uniform))

@@ -403,12 +403,12 @@ struct AsvgfOracle_T
             case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_METALLIC_ROUGHNESS: case ASVGF_IMAGE_DEPTH_WORLD:
             case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH: case ASVGF_IMAGE_DIFF_ACCUM_COLOR:
             case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS: case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_INDIR_ACCUM:
-            case ASVGF_IMAGE_GRADIENT_INPUTS: return 1;
+            case ASVGF_IMAGE_GRADIENT_INPUTS: case ASVGF_IMAGE_SCATTERING: case ASVGF_IMAGE_SCATTERING_HISTORY: return 1;
             case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_METALLIC_ROUGHNESS_PREV: case ASVGF_IMAGE_DEPTH_WORLD_PREV:
             case ASVGF_IMAGE_SURFACE_POSITION_PREV: case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV:
             case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV:
             case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_INDIR_ACCUM_PREV:
-            case ASVGF_IMAGE_GRADIENT_INPUTS_PREV: return 2;
+            case ASVGF_IMAGE_GRADIENT_INPUTS_PREV: case ASVGF_IMAGE_SCATTERING_PREV: case ASVGF_IMAGE_SCATTERING_HISTORY_PREV: return 2;
             default: return 0;
         }
     }
@@ -431,11 +431,12 @@ int bytesPerPixelOf( uint32_t i )
         case ASVGF_IMAGE_IS_SKY: case ASVGF_IMAGE_GRADIENT_PREV_PIX: case ASVGF_IMAGE_DEBUG_MASK: return 1;
         case ASVGF_IMAGE_METALLIC_ROUGHNESS: case ASVGF_IMAGE_METALLIC_ROUGHNESS_PREV: case ASVGF_IMAGE_DEPTH_WORLD:
         case ASVGF_IMAGE_DEPTH_WORLD_PREV: case ASVGF_IMAGE_DEPTH_GRAD: case ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE:
-        case ASVGF_IMAGE_HISTOGRAM_INPUT: return 2;
+        case ASVGF_IMAGE_HISTOGRAM_INPUT: case ASVGF_IMAGE_SCATTERING_HISTORY: case ASVGF_IMAGE_SCATTERING_HISTORY_PREV: return 2;
         case ASVGF_IMAGE_MOTION: case ASVGF_IMAGE_VIEW_DIRECTION: case ASVGF_IMAGE_THROUGHPUT:
         case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH: case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV:
         case ASVGF_IMAGE_DIFF_COLOR_HISTORY: case ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE:
-        case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: return 8;
+        case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: case ASVGF_IMAGE_SCATTERING: case ASVGF_IMAGE_SCATTERING_PREV:
+        case ASVGF_IMAGE_SCATTER_CURRENT: return 8;
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: return 16;
         case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV:
         case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR: case ASVGF_IMAGE_UNFILTERED_INDIR:
@@ -1211,6 +1212,88 @@ void atrous( AsvgfOracle_T& o, uint32_t fi, const Ctx& c, uint32_t iteration )
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Volumetric scattering accumulation, CmScatterAccum.comp:96-163 (Volumetric::ProcessScattering, Volumetric.cpp:71-195):
+// the frame's other temporal-reprojection pass, same disocclusion tests as the temporal accumulation.
+// fializeScattering (:40-94): VOLUME_ENABLE_SIMPLE and NONE are restated; VOLUME_ENABLE_VOLUMETRIC samples a 3-D
+// illumination volume with a blue-noise dither (not an image-space operation) and is read from ASVGF_IMAGE_SCATTER_CURRENT.
+// Pin: exp() = correctly rounded fp32.
+// ---------------------------------------------------------------------------------------------------------------
+void scatterAccumulate( AsvgfOracle_T& o, uint32_t fi, const Ctx& c, float maxHistoryLength )
+{
+    Img& motion = o.get( ASVGF_IMAGE_MOTION, fi );
+    Img& depthW = o.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
+    Img& normalI = o.get( ASVGF_IMAGE_NORMAL, fi );
+    Img& depthPrevI = o.get( ASVGF_IMAGE_DEPTH_WORLD_PREV, fi );
+    Img& normalPrevI = o.get( ASVGF_IMAGE_NORMAL_PREV, fi );
+    Img& scatPrev = o.get( ASVGF_IMAGE_SCATTERING_PREV, fi );
+    Img& histPrev = o.get( ASVGF_IMAGE_SCATTERING_HISTORY_PREV, fi );
+    Img& scat = o.get( ASVGF_IMAGE_SCATTERING, fi );
+    Img& hist = o.get( ASVGF_IMAGE_SCATTERING_HISTORY, fi );
+    Img& current = o.get( ASVGF_IMAGE_SCATTER_CURRENT, fi );
+#pragma omp parallel for schedule( static )
+    for( int y = 0; y < c.H; y++ )
+    {
+        for( int x = 0; x < c.W; x++ )
+        {
+            const ivec2 pix = { x, y }; // a checkerboard pixel (:98-103)
+            const vec4  mv      = fetchRGBA16F( motion, pix );
+            const float motionZ = mv.z;
+            const float depth   = fetchR16F( depthW, pix );
+            const vec3  normal  = decodeNormal( fetchU32( normalI, pix ) );
+            const vec2  posPrev = getPrevScreenPos( c, { mv.x, mv.y }, pix ); // :112
+            const vec2  q       = { posPrev.x - 0.5f, posPrev.y - 0.5f };
+            const vec2  fl      = { floorf( q.x ), floorf( q.y ) };
+            const ivec2 pixPrev = { f2i( fl.x ), f2i( fl.y ) };
+            const vec2  subPix  = { q.x - fl.x, q.y - fl.y };
+            const float bw[ 2 ][ 2 ] = { { ( 1.0f - subPix.x ) * ( 1.0f - subPix.y ), subPix.x * ( 1.0f - subPix.y ) },
+                                         { ( 1.0f - subPix.x ) * subPix.y, subPix.x * subPix.y } };
+            vec4  accum      = { 0, 0, 0, 0 };
+            float historyLen = 0, weightSum = 0;
+            const ivec3 area = getCheckerboardedRenderArea( c, pix );
+            for( int yy = 0; yy <= 1; yy++ )
+                for( int xx = 0; xx <= 1; xx++ ) // :127-151
+                {
+                    const ivec2 xy         = { pixPrev.x + xx, pixPrev.y + yy };
+                    const float depthPrev  = fetchR16F( depthPrevI, xy );
+                    const vec3  normalPrev = decodeNormal( fetchU32( normalPrevI, xy ) );
+                    if( testPixInRenderArea( xy, area ) && testReprojectedDepth( depth, depthPrev, motionZ ) && testReprojectedNormal( normal, normalPrev ) )
+                    {
+                        const float w   = bw[ yy ][ xx ];
+                        const ivec2 reg = getRegularPixFromCheckerboardPix( c, xy );
+                        const vec4  sp  = fetchRGBA16F( scatPrev, reg );
+                        accum      = { accum.x + w * sp.x, accum.y + w * sp.y, accum.z + w * sp.z, accum.w + w * sp.w };
+                        historyLen = historyLen + w * fetchR16F( histPrev, reg );
+                        weightSum  = weightSum + w;
+                    }
+                }
+            historyLen = weightSum > 0.0001f ? historyLen / weightSum : 0.0f; // :154-155
+            accum      = weightSum > 0.0001f ? vec4{ accum.x / weightSum, accum.y / weightSum, accum.z / weightSum, accum.w / weightSum } : vec4{ 0, 0, 0, 0 };
+            historyLen = fminf( fmaxf( historyLen + 1.0f, 1.0f ), fmaxf( 1.0f, maxHistoryLength ) ); // :157
+
+            const ivec2 reg = getRegularPixFromCheckerboardPix( c, pix );
+            vec4        cur; // fializeScattering, :40-94
+            if( c.u->volumeEnableType == ASVGF_VOLUME_ENABLE_VOLUMETRIC ) cur = fetchRGBA16F( current, reg );
+            else if( c.u->volumeEnableType == ASVGF_VOLUME_ENABLE_SIMPLE )
+            {
+                const float virtualdepth = fetchR16F( depthW, getCheckerboardPix( c, reg ) );
+                const float density      = c.u->volumeScattering * 0.00005f;
+                if( !( virtualdepth > ASVGF_MAX_RAY_LENGTH ) )
+                {
+                    const float f = ( float )std::exp( ( double )( -virtualdepth * density ) );
+                    cur           = { c.u->volumeAmbient[ 0 ] * ( 1.0f - f ), c.u->volumeAmbient[ 1 ] * ( 1.0f - f ), c.u->volumeAmbient[ 2 ] * ( 1.0f - f ), f };
+                }
+                else cur = { 0, 0, 0, 1.0f };
+            }
+            else cur = { 0, 0, 0, 1.0f };
+            const float t = 1.0f / historyLen; // :158
+            accum         = { mixf( accum.x, cur.x, t ), mixf( accum.y, cur.y, t ), mixf( accum.z, cur.z, t ), mixf( accum.w, cur.w, t ) };
+            storeRGBA16F( scat, reg, accum );
+            storeR16F( hist, reg, historyLen );
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Checkerboard resolve of the denoiser's output, CmCheckerboard.comp:43-78 (PreFinal -> Final; the shader's two other
 // image pairs, ScreenEmisRT and AcidFogRT, come from other producers and are outside this path)
 // ---------------------------------------------------------------------------------------------------------------
@@ -1360,6 +1443,11 @@ void asvgfOracleDenoise( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUn
     for( uint32_t p = 1; p < 8 + o->iterations; p++ ) asvgfOracleRunPass( o, p, frameIndex, u );
 }
 
+void asvgfOracleScatterAccumulate( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u, float maxHistoryLength )
+{
+    Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };
+    scatterAccumulate( *o, frameIndex, c, maxHistoryLength );
+}
 void asvgfOracleResolveCheckerboard( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u ) // ImageComposition.cpp:157-222
 {
     Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };

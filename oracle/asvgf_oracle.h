@@ -43,6 +43,8 @@ void asvgfOracleLuminanceHistogram( AsvgfOracle o, uint32_t frameIndex, const As
 void asvgfOracleLuminanceAverage( AsvgfOracle o, const AsvgfGlobalUniform* u );
 void asvgfOracleCalculateExposure( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
 AsvgfTonemapping* asvgfOracleGetTonemapping( AsvgfOracle o );
+/* CmScatterAccum.comp: temporal accumulation of the volumetric scattering */
+void asvgfOracleScatterAccumulate( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u, float maxHistoryLength );
 
 /* helper primitives exposed for unit tests */
 uint32_t asvgfOracleEncodeE5B9G9R9( float r, float g, float b );

@@ -56,12 +56,14 @@ bool describe( uint32_t i, ImageDesc* d )
         case ASVGF_IMAGE_GRADIENT_PREV_PIX: *d = { ASVGF_FORMAT_R8_UINT, 1, true }; return true;
         case ASVGF_IMAGE_METALLIC_ROUGHNESS: case ASVGF_IMAGE_METALLIC_ROUGHNESS_PREV: *d = { ASVGF_FORMAT_R8G8_UNORM, 2, false }; return true;
         case ASVGF_IMAGE_DEPTH_WORLD: case ASVGF_IMAGE_DEPTH_WORLD_PREV: case ASVGF_IMAGE_DEPTH_GRAD:
-        case ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE: case ASVGF_IMAGE_HISTOGRAM_INPUT: *d = { ASVGF_FORMAT_R16_SFLOAT, 2, false }; return true;
+        case ASVGF_IMAGE_ATROUS_FILTERED_VARIANCE: case ASVGF_IMAGE_HISTOGRAM_INPUT: case ASVGF_IMAGE_SCATTERING_HISTORY:
+        case ASVGF_IMAGE_SCATTERING_HISTORY_PREV: *d = { ASVGF_FORMAT_R16_SFLOAT, 2, false }; return true;
         case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV: case ASVGF_IMAGE_GRADIENT_INPUTS:
         case ASVGF_IMAGE_GRADIENT_INPUTS_PREV: case ASVGF_IMAGE_FWD_LUM: *d = { ASVGF_FORMAT_R16G16_SFLOAT, 4, false }; return true;
         case ASVGF_IMAGE_MOTION: case ASVGF_IMAGE_VIEW_DIRECTION: case ASVGF_IMAGE_THROUGHPUT: case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH:
         case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV: case ASVGF_IMAGE_DIFF_COLOR_HISTORY: case ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE:
-        case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: *d = { ASVGF_FORMAT_R16G16B16A16_SFLOAT, 8, false }; return true;
+        case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: case ASVGF_IMAGE_SCATTERING: case ASVGF_IMAGE_SCATTERING_PREV: case ASVGF_IMAGE_SCATTER_CURRENT:
+            *d = { ASVGF_FORMAT_R16G16B16A16_SFLOAT, 8, false }; return true;
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: *d = { ASVGF_FORMAT_R32G32B32A32_SFLOAT, 16, false }; return true;
         case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
         case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR:
@@ -82,10 +84,12 @@ int swapKind( uint32_t i )
     {
         case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_METALLIC_ROUGHNESS: case ASVGF_IMAGE_DEPTH_WORLD: case ASVGF_IMAGE_SURFACE_POSITION:
         case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH: case ASVGF_IMAGE_DIFF_ACCUM_COLOR: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS:
-        case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_INDIR_ACCUM: case ASVGF_IMAGE_GRADIENT_INPUTS: return 1;
+        case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_INDIR_ACCUM: case ASVGF_IMAGE_GRADIENT_INPUTS: case ASVGF_IMAGE_SCATTERING:
+        case ASVGF_IMAGE_SCATTERING_HISTORY: return 1;
         case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_METALLIC_ROUGHNESS_PREV: case ASVGF_IMAGE_DEPTH_WORLD_PREV: case ASVGF_IMAGE_SURFACE_POSITION_PREV:
         case ASVGF_IMAGE_ACCUM_HISTORY_LENGTH_PREV: case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV:
-        case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_INDIR_ACCUM_PREV: case ASVGF_IMAGE_GRADIENT_INPUTS_PREV: return 2;
+        case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_INDIR_ACCUM_PREV: case ASVGF_IMAGE_GRADIENT_INPUTS_PREV:
+        case ASVGF_IMAGE_SCATTERING_PREV: case ASVGF_IMAGE_SCATTERING_HISTORY_PREV: return 2;
         default: return 0;
     }
 }
@@ -485,6 +489,22 @@ AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t
     return launchCheck( d, "k_checkerboard_resolve" );
 }
 
+AsvgfResult runScatterAccumulate( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, const AsvgfGlobalUniform& g, float maxHistoryLength )
+{
+    NEED( ASVGF_IMAGE_MOTION, ASVGF_IMAGE_DEPTH_WORLD, ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_DEPTH_WORLD_PREV, ASVGF_IMAGE_NORMAL_PREV, ASVGF_IMAGE_SCATTERING_PREV,
+          ASVGF_IMAGE_SCATTERING_HISTORY_PREV, ASVGF_IMAGE_SCATTERING, ASVGF_IMAGE_SCATTERING_HISTORY );
+    if( g.volumeEnableType == ASVGF_VOLUME_ENABLE_VOLUMETRIC ) NEED( ASVGF_IMAGE_SCATTER_CURRENT );
+    ScatterArgs a;
+    a.motion = d.get( ASVGF_IMAGE_MOTION, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi );
+    a.depthPrev = d.get( ASVGF_IMAGE_DEPTH_WORLD_PREV, fi ); a.normalPrev = d.get( ASVGF_IMAGE_NORMAL_PREV, fi );
+    a.scatPrev = d.get( ASVGF_IMAGE_SCATTERING_PREV, fi ); a.histPrev = d.get( ASVGF_IMAGE_SCATTERING_HISTORY_PREV, fi );
+    a.scat = d.get( ASVGF_IMAGE_SCATTERING, fi ); a.hist = d.get( ASVGF_IMAGE_SCATTERING_HISTORY, fi ); a.current = d.get( ASVGF_IMAGE_SCATTER_CURRENT, fi );
+    a.lut = d.lut; a.maxHistoryLength = maxHistoryLength; a.volumeScattering = g.volumeScattering; a.volumeEnableType = g.volumeEnableType;
+    for( int i = 0; i < 3; i++ ) a.volumeAmbient[ i ] = g.volumeAmbient[ i ];
+    k_scatter_accum<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_scatter_accum" );
+}
+
 LumArgs lumArgs( const AsvgfDenoiser_T& d, uint32_t fi, const AsvgfGlobalUniform& g )
 {
     LumArgs a;
@@ -857,6 +877,15 @@ AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser d, AsvgfStream stream, uint3
     if( r != ASVGF_SUCCESS ) return r;
     DeviceGuard guard( d->device );
     return runResolveCheckerboard( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ) );
+}
+
+AsvgfResult asvgfScatterAccumulate( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform, float maxHistoryLength )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    if( pUniform->volumeEnableType > ASVGF_VOLUME_ENABLE_VOLUMETRIC ) return fail( ASVGF_WRONG_ARGUMENT, "unknown volumeEnableType" );
+    DeviceGuard guard( d->device );
+    return runScatterAccumulate( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), *pUniform, maxHistoryLength );
 }
 
 AsvgfResult asvgfLuminanceHistogram( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )

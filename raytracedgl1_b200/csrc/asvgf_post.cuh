@@ -189,4 +189,107 @@ __global__ void __launch_bounds__( 256 ) k_lum_average( const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Volumetric scattering accumulation, CmScatterAccum.comp:96-163.  One thread per checkerboard
+// pixel; the 2x2 disocclusion gather is the temporal pass's (exact operation order: which taps count is an integer
+// decision), the blend is evaluated in the shader's order, so the fp16 outputs are bit-identical to the oracle's.
+// ------------------------------------------------------------------------------------------------------------
+struct ScatterArgs
+{
+    Img       motion, depth, normal, depthPrev, normalPrev, scatPrev, histPrev, scat, hist, current;
+    NormalLut lut;
+    float     maxHistoryLength, volumeScattering, volumeAmbient[ 3 ];
+    uint32_t  volumeEnableType;
+};
+
+__global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __grid_constant__ ScatterArgs a, const __grid_constant__ Uniform u )
+{
+    const int px = blockIdx.x * kBlockW + threadIdx.x;
+    const int py = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
+    if( px >= u.W || py >= u.yEnd ) return;
+    const Rows rows = rowsOf( a.depth );
+    const int  sep = u.W / 2, ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+
+    const uint2    mv = __ldg( at< uint2 >( a.motion, px, py ) );
+    const uint16_t dv = __ldg( at< uint16_t >( a.depth, px, py ) );
+    const uint32_t nv = __ldg( at< uint32_t >( a.normal, px, py ) );
+    const float2 mot01   = __half22float2( *reinterpret_cast< const __half2* >( &mv.x ) );
+    const float  motionZ = __low2float( *reinterpret_cast< const __half2* >( &mv.y ) );
+    const float  depth   = h2f( dv );
+    const float3 normal  = decodeNormal( a.lut, nv );
+
+    const float ppx = mulr( addr( mulr( addr( ( float )px, 0.5f ), u.invHalfW ), mot01.x ), u.halfW );        // getPrevScreenPos
+    const float ppy = mulr( addr( mulr( addr( ( float )py, 0.5f ), u.invH ), mot01.y ), u.renderHeight );
+    const float qx = subr( ppx, 0.5f ), qy = subr( ppy, 0.5f ), fx = floorf( qx ), fy = floorf( qy );
+    const int   bx = f2i( fx ), by = f2i( fy );
+    const float sx = subr( qx, fx ), sy = subr( qy, fy );
+    const float bw[ 4 ] = { mulr( subr( 1.0f, sx ), subr( 1.0f, sy ) ), mulr( sx, subr( 1.0f, sy ) ), mulr( subr( 1.0f, sx ), sy ), mulr( sx, sy ) };
+
+    uint32_t dz[ 4 ], en[ 4 ];
+    bool     in[ 4 ];
+#pragma unroll
+    for( int t = 0; t < 4; t++ )
+    {
+        const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
+        in[ t ] = y >= 0 && y < u.H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
+        dz[ t ] = ldIf< uint16_t >( a.depthPrev, x, y, in[ t ], ( uint16_t )0 );
+        en[ t ] = ldIf< uint32_t >( a.normalPrev, x, y, in[ t ], 0u );
+    }
+    float4 accum = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+    float  historyLen = 0.0f, weightSum = 0.0f;
+    const float az = fabsf( depth );
+#pragma unroll
+    for( int t = 0; t < 4; t++ )
+    {
+        const float3 nPrev = decodeNormal( a.lut, en[ t ] );
+        const float  num   = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
+        if( in[ t ] && quotientBelowTenth( num, az ) && dot3r( normal, nPrev ) > 0.95f )
+        {
+            const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
+            const int odd = x >= sep ? 1 : 0, rx = ( x - odd * sep ) * 2 + ( ( odd + y ) & 1 ); // getRegularPixFromCheckerboardPix
+            const uint2    sp = __ldg( at< uint2 >( a.scatPrev, rx, y ) );
+            const uint16_t hp = __ldg( at< uint16_t >( a.histPrev, rx, y ) );
+            const float2 s01 = __half22float2( *reinterpret_cast< const __half2* >( &sp.x ) ), s23 = __half22float2( *reinterpret_cast< const __half2* >( &sp.y ) );
+            const float  w = bw[ t ];
+            accum = make_float4( addr( accum.x, mulr( w, s01.x ) ), addr( accum.y, mulr( w, s01.y ) ), addr( accum.z, mulr( w, s23.x ) ), addr( accum.w, mulr( w, s23.y ) ) );
+            historyLen = addr( historyLen, mulr( w, h2f( hp ) ) );
+            weightSum  = addr( weightSum, w );
+        }
+    }
+    if( weightSum > 0.0001f )
+    {
+        historyLen = divr( historyLen, weightSum );
+        accum = make_float4( divr( accum.x, weightSum ), divr( accum.y, weightSum ), divr( accum.z, weightSum ), divr( accum.w, weightSum ) );
+    }
+    else
+    {
+        historyLen = 0.0f;
+        accum = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+    }
+    historyLen = fminf( fmaxf( addr( historyLen, 1.0f ), 1.0f ), fmaxf( 1.0f, a.maxHistoryLength ) );
+
+    const int odd = px >= sep ? 1 : 0, regX = ( px - odd * sep ) * 2 + ( ( odd + py ) & 1 );
+    float4 cur = make_float4( 0.0f, 0.0f, 0.0f, 1.0f ); // fializeScattering, CmScatterAccum.comp:40-94
+    if( a.volumeEnableType == ASVGF_VOLUME_ENABLE_VOLUMETRIC )
+    {
+        const uint2 c = __ldg( at< uint2 >( a.current, regX, py ) );
+        const float2 c01 = __half22float2( *reinterpret_cast< const __half2* >( &c.x ) ), c23 = __half22float2( *reinterpret_cast< const __half2* >( &c.y ) );
+        cur = make_float4( c01.x, c01.y, c23.x, c23.y );
+    }
+    else if( a.volumeEnableType == ASVGF_VOLUME_ENABLE_SIMPLE )
+    {
+        const float density = mulr( a.volumeScattering, 0.00005f );
+        if( !( depth > ASVGF_MAX_RAY_LENGTH ) ) // the regular pixel maps back to this checkerboard pixel: virtualdepth = depth
+        {
+            const float f = ( float )exp( ( double )mulr( -depth, density ) ); // pin: correctly rounded fp32
+            const float g = subr( 1.0f, f );
+            cur = make_float4( mulr( a.volumeAmbient[ 0 ], g ), mulr( a.volumeAmbient[ 1 ], g ), mulr( a.volumeAmbient[ 2 ], g ), f );
+        }
+    }
+    const float t = divr( 1.0f, historyLen );
+    const __half2 o0 = __floats2half2_rn( mixr( accum.x, cur.x, t ), mixr( accum.y, cur.y, t ) ), o1 = __floats2half2_rn( mixr( accum.z, cur.z, t ), mixr( accum.w, cur.w, t ) );
+    *atW< uint2 >( a.scat, regX, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
+    *atW< uint16_t >( a.hist, regX, py ) = f2h( historyLen );
+}
+
 } // namespace asvgf

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "asvgfSynchronize", "asvgfGetLaunchCount", "asvgfPassName", "asvgfPassBytesPerPixel", "asvgfResultString",
     "asvgfLastErrorMessage", "asvgfPassKernelName", "asvgfBandApronRows", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
     "asvgfLuminanceAverage", "asvgfGetTonemappingBuffer", "asvgfUploadTonemapping", "asvgfDownloadTonemapping",
+    "asvgfScatterAccumulate",
 ]
 
 
@@ -71,6 +72,7 @@ def lib():
         L.asvgfSynchronize.argtypes = [vp, vp]
         for name in ("asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram", "asvgfLuminanceAverage"):
             getattr(L, name).argtypes = [vp, vp, u32, puni]
+        L.asvgfScatterAccumulate.argtypes = [vp, vp, u32, puni, ctypes.c_float]
         L.asvgfGetTonemappingBuffer.argtypes = [vp, ctypes.POINTER(vp)]
         L.asvgfUploadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
         L.asvgfDownloadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
@@ -198,6 +200,11 @@ class Denoiser:
 
     def luminance_average(self, frame_index, uniform, stream=0):
         _check(lib().asvgfLuminanceAverage(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfLuminanceAverage")
+
+    def scatter_accumulate(self, frame_index, uniform, max_history_length, stream=0):
+        """= Volumetric::ProcessScattering (Source/Volumetric.cpp:71-195), CmScatterAccum.comp."""
+        _check(lib().asvgfScatterAccumulate(self._h, stream, frame_index, ctypes.byref(uniform), max_history_length),
+               "asvgfScatterAccumulate")
 
     def tonemapping(self, stream=0):
         """Host copy of the handle's AsvgfTonemapping (histogram[256], avgLuminance)."""

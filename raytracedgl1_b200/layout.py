@@ -58,6 +58,10 @@ IMAGES = {
     "IndirPong": (44, R32_UINT, False, "scratch"),
     "AtrousFilteredVariance": (45, R16_SFLOAT, False, "state"),
     "HistogramInput": (46, R16_SFLOAT, False, "out"),
+    "Scattering": (48, R16G16B16A16_SFLOAT, False, "state"),        # regular layout (CmScatterAccum.comp)
+    "Scattering_Prev": (49, R16G16B16A16_SFLOAT, False, "state"),
+    "ScatteringHistory": (50, R16_SFLOAT, False, "state"),
+    "ScatteringHistory_Prev": (51, R16_SFLOAT, False, "state"),
     "GradientInputs": (70, R16G16_SFLOAT, False, "in"),
     "GradientInputs_Prev": (71, R16G16_SFLOAT, False, "in"),
     "DISPingGradient": (72, R8G8B8A8_UNORM, True, "scratch"),
@@ -66,10 +70,11 @@ IMAGES = {
     "GradientPrevPix": (75, R8_UINT, True, "state"),
     "FwdLum": (76, R16G16_SFLOAT, False, "in"),
     "DebugMask": (77, R8_UINT, False, "out"),
+    "ScatterCurrent": (78, R16G16B16A16_SFLOAT, False, "in"),       # extension: the VOLUMETRIC-mode scattering sample
 }
 INDEX = {name: v[0] for name, v in IMAGES.items()}
 NAME_OF = {v[0]: name for name, v in IMAGES.items()}
-IMAGE_COUNT = 78
+IMAGE_COUNT = 79
 
 # images a G-buffer producer writes every frame (what synth generates / what the host uploads)
 PRODUCER_IMAGES = ["Albedo", "IsSky", "Normal", "MetallicRoughness", "DepthWorld", "DepthGrad", "Motion",
@@ -126,19 +131,23 @@ class GlobalUniform(ctypes.Structure):
         ("_reserved2", ctypes.c_uint32 * 9),
         ("cameraPosition", ctypes.c_float * 4), ("cameraPositionPrev", ctypes.c_float * 4),
         ("debugShowFlags", ctypes.c_uint32),
-        ("_reserved3", ctypes.c_uint32 * 44),
+        ("_reserved3", ctypes.c_uint32 * 19),
+        ("volumeEnableType", ctypes.c_uint32), ("volumeScattering", ctypes.c_float),
+        ("_reserved3b", ctypes.c_uint32 * 23),
         ("jitterX", ctypes.c_float), ("jitterY", ctypes.c_float),
         ("_reserved4", ctypes.c_uint32 * 6),
         ("gradientMultDiffuse", ctypes.c_float), ("gradientMultIndirect", ctypes.c_float),
         ("gradientMultSpecular", ctypes.c_float),
         ("_reserved5", ctypes.c_uint32 * 3),
         ("antiFireflyEnabled", ctypes.c_uint32),
-        ("_reserved6", ctypes.c_uint32 * 276),
+        ("volumeAmbient", ctypes.c_float * 4),
+        ("_reserved6", ctypes.c_uint32 * 272),
     ]
 
 
 assert ctypes.sizeof(GlobalUniform) == 2096
 assert GlobalUniform.minLogLuminance.offset == 668 and GlobalUniform.stopEyeAdaptation.offset == 680
+assert GlobalUniform.volumeEnableType.offset == 832 and GlobalUniform.volumeAmbient.offset == 992
 
 
 class Tonemapping(ctypes.Structure):

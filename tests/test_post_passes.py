@@ -130,7 +130,62 @@ def test_oracle_resolve_known_answers():
         o.close()
 
 
+def test_oracle_scatter_accumulation_known_answers():
+    """CmScatterAccum.comp on a static scene (zero motion): every tap is consistent, the history length counts
+    1, 2, 3, ... up to the push constant and the accumulated value is the running mean of the per-frame samples;
+    SIMPLE mode writes ambient * (1 - exp(-depth * density)) and the transmittance; sky pixels get (0,0,0,1)."""
+    W, H = 32, 16
+    o = oracle_mod.Oracle(W, H)
+    try:
+        u = synth.uniform(W, H, 0)
+        u.volumeEnableType = 2  # VOLUMETRIC: the sample comes from ScatterCurrent
+        for fi in (0, 1):
+            o.image("Motion", fi)[...] = 0
+            o.image("DepthWorld", fi)[...] = np.float16(10.0)
+            o.image("Normal", fi)[...] = oracle_mod.lib().asvgfOracleEncodeNormal(0.0, 0.0, 1.0)
+        samples = [1.0, 3.0, 5.0, 7.0, 9.0, 11.0]
+        mean = 0.0
+        for f, v in enumerate(samples):
+            fi = f & 1
+            o.image("ScatterCurrent", fi)[...] = np.float16(v)
+            o.scatter_accumulate(fi, u, 4.0)
+            n = min(f + 1, 4)
+            mean = mean + (v - mean) / n          # mix(accum, cur, 1/historyLen)
+            assert np.all(o.image("ScatteringHistory", fi) == np.float16(n)), f
+            got = o.image("Scattering", fi).astype(np.float32)
+            assert np.allclose(got, mean, rtol=2e-3), (f, got[0, 0], mean)
+            mean = float(np.float16(mean))        # the state is stored as fp16
+        # disocclusion: the depth jumps, no tap is consistent, history restarts at 1 with the current sample
+        o.image("DepthWorld", 0)[...] = np.float16(100.0)
+        o.image("ScatterCurrent", 0)[...] = np.float16(2.0)
+        o.scatter_accumulate(0, u, 4.0)
+        assert np.all(o.image("ScatteringHistory", 0) == np.float16(1.0)) and np.all(o.image("Scattering", 0) == np.float16(2.0))
+        # SIMPLE mode on fresh history
+        o.reset_history()
+        u.volumeEnableType = 1
+        u.volumeScattering = 2000.0
+        u.volumeAmbient[0], u.volumeAmbient[1], u.volumeAmbient[2] = 0.5, 0.25, 1.0
+        o.image("DepthWorld", 0)[...] = np.float16(10.0)
+        o.image("DepthWorld", 0)[0, :] = np.float16(20000.0)  # sky
+        o.scatter_accumulate(0, u, 8.0)
+        f = math.exp(-10.0 * 2000.0 * 0.00005)
+        got = o.image("Scattering", 0).astype(np.float32)
+        # row 0 of the checkerboard image is row 0 of the regular image
+        assert np.allclose(got[1:, :, 3], f, rtol=2e-3) and np.allclose(got[1:, :, 0], 0.5 * (1 - f), rtol=2e-3)
+        assert np.all(got[0, :, 3] == 1.0) and np.all(got[0, :, :3] == 0.0)
+        u.volumeEnableType = 0
+        o.reset_history()
+        o.scatter_accumulate(0, u, 8.0)
+        got = o.image("Scattering", 0).astype(np.float32)
+        assert np.all(got[..., 3] == 1.0) and np.all(got[..., :3] == 0.0)
+    finally:
+        o.close()
+
+
 def test_uniform_and_tonemapping_layout():
+    assert layout.GlobalUniform.volumeEnableType.offset == 832 and layout.GlobalUniform.volumeScattering.offset == 836
+    assert layout.GlobalUniform.volumeAmbient.offset == 992
+    assert (layout.INDEX["Scattering"], layout.INDEX["ScatteringHistory_Prev"]) == (48, 51)
     assert layout.GlobalUniform.minLogLuminance.offset == 668
     assert layout.GlobalUniform.maxLogLuminance.offset == 672
     assert layout.GlobalUniform.stopEyeAdaptation.offset == 680
@@ -172,6 +227,37 @@ def test_post_passes_parity(size):
             assert not any(got.histogram)
             assert abs(got.avgLuminance - want.avgLuminance) <= 1e-6 * abs(want.avgLuminance), (got.avgLuminance, want.avgLuminance)
             assert want.avgLuminance > 0
+    finally:
+        p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [2, 1, 0])
+def test_scatter_accumulation_parity(mode):
+    """CmScatterAccum.comp over a moving sequence (camera motion, disocclusions): Scattering and ScatteringHistory
+    bit-identical to the oracle every frame, state carried on both sides independently."""
+    from _harness import Pair
+    W, H = 322, 182
+    p = Pair(W, H)
+    try:
+        rng = np.random.default_rng(5)
+        for frame in range(5):
+            fi = frame & 1
+            u = p.feed_inputs(frame, fi)
+            u.volumeEnableType = mode
+            u.volumeScattering = 1500.0
+            u.volumeAmbient[0], u.volumeAmbient[1], u.volumeAmbient[2] = 0.7, 0.8, 1.0
+            cur = rng.random((H, W, 4)).astype(np.float16)
+            p.oracle.image("ScatterCurrent", fi)[...] = cur
+            p.cuda.upload("ScatterCurrent", fi, cur)
+            p.oracle.scatter_accumulate(fi, u, 16.0)
+            p.cuda.scatter_accumulate(fi, u, 16.0)
+            p.cuda.synchronize()
+            for name in ("Scattering", "ScatteringHistory"):
+                want, got = p.oracle.image(name, fi), p.cuda.download(name, fi)
+                assert np.array_equal(want.view(np.uint16), got.view(np.uint16)), (mode, frame, name, int((want.view(np.uint16) != got.view(np.uint16)).sum()))
+            if frame >= 2:
+                assert p.oracle.image("ScatteringHistory", fi).max() >= 3.0  # history does accumulate
     finally:
         p.close()
 
