@@ -255,7 +255,11 @@ struct TapTest
 };
 
 // the 2x2 consistency gather of CmSVGFTemporalAccumulation.comp:149-162 / :258-270 (exact)
-ASVGF_DEVICE uint32_t consistencyBits( const TemporalArgs& a, const Rows& rows, int bx, int by, int ax0, int ax1, int H, float depth, float motionZ, float3 normal )
+// encN = the centre pixel's packed normal: a tap whose packed normal has the same bits decodes to the same vector, and
+// dot(n, n) of a decoded (unit) normal is 1 up to rounding, i.e. > 0.95 -- so when all four taps match (flat surfaces,
+// most pixels) the eight sin/cos table gathers and the dot products are skipped; the result is identical by construction.
+ASVGF_DEVICE uint32_t consistencyBits( const TemporalArgs& a, const Rows& rows, int bx, int by, int ax0, int ax1, int H, float depth, float motionZ, float3 normal,
+                                       uint32_t encN )
 {
     uint32_t dz[ 4 ], en[ 4 ];
     bool     in[ 4 ];
@@ -265,23 +269,33 @@ ASVGF_DEVICE uint32_t consistencyBits( const TemporalArgs& a, const Rows& rows, 
         const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
         in[ t ] = y >= 0 && y < H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
         dz[ t ] = ldIf< uint16_t >( a.depthPrev, x, y, in[ t ], ( uint16_t )0 );
-        en[ t ] = ldIf< uint32_t >( a.normalPrev, x, y, in[ t ], 0u );
+        en[ t ] = ldIf< uint32_t >( a.normalPrev, x, y, in[ t ], encN ); // taps outside never count: let them match
     }
-    float2 sp[ 4 ], st[ 4 ];
-#pragma unroll
-    for( int t = 0; t < 4; t++ )
+    uint32_t    nOk = 15u;
+    if( ( en[ 0 ] != encN ) | ( en[ 1 ] != encN ) | ( en[ 2 ] != encN ) | ( en[ 3 ] != encN ) )
     {
-        sp[ t ] = __ldg( a.lut.phi + ( en[ t ] >> 16 ) );
-        st[ t ] = __ldg( a.lut.theta + ( en[ t ] & 0xffffu ) );
+        float2 sp[ 4 ], st[ 4 ];
+#pragma unroll
+        for( int t = 0; t < 4; t++ )
+        {
+            sp[ t ] = __ldg( a.lut.phi + ( en[ t ] >> 16 ) );
+            st[ t ] = __ldg( a.lut.theta + ( en[ t ] & 0xffffu ) );
+        }
+        nOk = 0u;
+#pragma unroll
+        for( int t = 0; t < 4; t++ )
+        {
+            const float3 nPrev = make_float3( mulr( sp[ t ].x, st[ t ].y ), mulr( sp[ t ].x, st[ t ].x ), sp[ t ].y );
+            nOk |= dot3r( normal, nPrev ) > 0.95f ? ( 1u << t ) : 0u;
+        }
     }
     uint32_t bits = 0;
     const float az = fabsf( depth );
 #pragma unroll
     for( int t = 0; t < 4; t++ )
     {
-        const float3 nPrev = make_float3( mulr( sp[ t ].x, st[ t ].y ), mulr( sp[ t ].x, st[ t ].x ), sp[ t ].y );
-        const float  num   = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
-        const bool   ok    = in[ t ] && dot3r( normal, nPrev ) > 0.95f && quotientBelowTenth( num, az );
+        const float num = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
+        const bool  ok  = in[ t ] && ( ( nOk >> t ) & 1u ) && quotientBelowTenth( num, az );
         bits |= ok ? ( 1u << t ) : 0u;
     }
     return bits;
@@ -369,9 +383,9 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
         hSpec[ t ] = ldIf< uint32_t >( a.specPrev, x, y, ok, 0u );
         hInd[ t ]  = ldIf< uint32_t >( a.indirPrev, x, y, ok, 0u );
     }
-    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal );
+    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal, nv32 );
 #else
-    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal );
+    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal, nv32 );
     // of the consistent taps only (all in flight together)
 #pragma unroll
     for( int t = 0; t < 4; t++ )
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
         // the same four texels as the first gather give the same test results (same centre depth/normal/motion)
         const uint32_t vbits = ( pixPrevSpecX == pixPrevX && pixPrevSpecY == pixPrevY )
                                    ? ( mask & 15u )
-                                   : consistencyBits( a, rows, pixPrevSpecX, pixPrevSpecY, ax0, ax1, u.H, depth, motionZ, normal );
+                                   : consistencyBits( a, rows, pixPrevSpecX, pixPrevSpecY, ax0, ax1, u.H, depth, motionZ, normal, nv32 );
         float weightSumVirtual = 0.0f;
 #pragma unroll
         for( int t = 0; t < 4; t++ )

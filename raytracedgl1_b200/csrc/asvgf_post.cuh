@@ -233,7 +233,16 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __g
         const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
         in[ t ] = y >= 0 && y < u.H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
         dz[ t ] = ldIf< uint16_t >( a.depthPrev, x, y, in[ t ], ( uint16_t )0 );
-        en[ t ] = ldIf< uint32_t >( a.normalPrev, x, y, in[ t ], 0u );
+        en[ t ] = ldIf< uint32_t >( a.normalPrev, x, y, in[ t ], nv ); // taps outside never count: let them match
+    }
+    // a tap with the centre's packed normal decodes to the same unit vector (dot = 1 > 0.95): when all four match, the
+    // sin/cos table gathers are skipped (same shortcut as the temporal pass, identical result by construction)
+    uint32_t nOk = 15u;
+    if( ( en[ 0 ] != nv ) | ( en[ 1 ] != nv ) | ( en[ 2 ] != nv ) | ( en[ 3 ] != nv ) )
+    {
+        nOk = 0u;
+#pragma unroll
+        for( int t = 0; t < 4; t++ ) nOk |= dot3r( normal, decodeNormal( a.lut, en[ t ] ) ) > 0.95f ? ( 1u << t ) : 0u;
     }
     float4 accum = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
     float  historyLen = 0.0f, weightSum = 0.0f;
@@ -241,9 +250,8 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __g
 #pragma unroll
     for( int t = 0; t < 4; t++ )
     {
-        const float3 nPrev = decodeNormal( a.lut, en[ t ] );
-        const float  num   = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
-        if( in[ t ] && quotientBelowTenth( num, az ) && dot3r( normal, nPrev ) > 0.95f )
+        const float num = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
+        if( in[ t ] && ( ( nOk >> t ) & 1u ) && quotientBelowTenth( num, az ) )
         {
             const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
             const int odd = x >= sep ? 1 : 0, rx = ( x - odd * sep ) * 2 + ( ( odd + y ) & 1 ); // getRegularPixFromCheckerboardPix
