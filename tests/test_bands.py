@@ -118,6 +118,22 @@ def _gloo_worker(rank, world, port, H, pitch, halo, q):
                 # rows beyond the exchanged depth stay untouched (zero)
                 if lo > s0:
                     ok &= bool((t.numpy()[:lo - s0] == 0).all())
+        # the apron schedule's frame-start exchange: full-resolution and gradient-resolution images in ONE batch,
+        # with unequal (cost-balanced) bands
+        b = [0] + [min(H, 3 * ((k * H // world + 20 * (k % 2)) // 3)) for k in range(1, world)] + [H]
+        plan2 = bands.BandPlan(H, world, rank, halo, boundaries=b)
+        specs, refs = [], []
+        for third, ref, depth in ((False, full, halo), (True, gfull, 7)):
+            (o0, o1), (s0, s1) = plan2.rows(third)
+            t = torch.zeros((s1 - s0, pitch), dtype=torch.uint8)
+            t[o0 - s0:o1 - s0] = torch.from_numpy(ref[o0:o1].copy())
+            specs.append(([t], depth, third))
+            refs.append((t, ref, depth, third))
+        bands.exchange_halos_multi(specs, plan2)
+        for t, ref, depth, third in refs:
+            (o0, o1), (s0, s1) = plan2.rows(third)
+            lo, hi = max(s0, o0 - depth), min(s1, o1 + depth)
+            ok &= bool(np.array_equal(t.numpy()[lo - s0:hi - s0], ref[lo:hi]))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
