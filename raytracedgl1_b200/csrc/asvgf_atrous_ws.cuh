@@ -1,21 +1,27 @@
-// asvgf_atrous_ws.cuh -- warp-specialised, persistent a-trous kernel (all iterations), sm_100a.
+// asvgf_atrous_ws.cuh -- the SELECTABLE a-trous kernels (ASVGF_ATROUS=ws|t2|t3), sm_100a.  The default is k_atrous_tiled
+// (asvgf_atrous_tiled.cuh); these share its arithmetic and its dilated tile (shaders CmSVGFAtrous_Iter0.comp:158-335 and
+// CmSVGFAtrous.comp:65-349) and explore how the tile is staged and how the SM is kept busy.  All three are parity-tested
+// (tests/test_parity_gpu.py::test_atrous_kernel_variants); DESIGN.md section 3 has the measurements and why none of
+// them beats the default yet.
 //
-// Same arithmetic and the same dilated tile as k_atrous_tiled (asvgf_atrous_tiled.cuh; shaders
-// CmSVGFAtrous_Iter0.comp:158-335 and CmSVGFAtrous.comp:65-349).  What changes is how the SM is kept busy.
-// ncu on k_atrous_tiled (profiles/r01_v3_*): 58 % issue-active, 50-56 % shared-memory pipe, 24 % occupancy -- neither
-// pipe is saturated; a CTA alternates between a load/decode phase that waits on HBM and a filter phase that issues
-// flat out, and with two CTAs per SM the phases only half overlap.  Here ONE persistent CTA per SM splits the roles:
+// Common to the three: STAGING in 4-pixel vector loads (uint4 / uint2 per lane) into QUARTER-ROW SLOTS (tile column x ->
+// slot (x & 3) * GP + (x >> 2)), which keeps the four stores of a staging lane and the LDS.128 of a filtering quarter
+// warp (lanes take columns 4 apart) conflict-free at every stride.
 //
-//   * PRODUCER warps stream tile t+1 from HBM (full-line row segments of the six tapped images), unpack every tile
-//     pixel once (normal through the exact sin/cos table, E5B9G9R9 / fp16 -> fp32, luminance) into one of two
-//     shared-memory tile buffers, and stage the three centre-only inputs of each output pixel next to it;
-//   * CONSUMER warps filter tile t out of the other buffer: taps are four conflict-free LDS.128 at immediate
-//     offsets, weights go through one lg2 and three ex2, and nothing in their instruction stream waits on HBM
-//     (only the composing iteration reads its four extra centre-only images directly, ~500 instructions ahead of use).
-//
-// Hand-off is two pairs of named barriers (full[b]: producers arrive / consumers sync; empty[b]: the reverse), so the
-// two roles never meet at a CTA-wide __syncthreads.  Tiles are dealt round-robin to the CTAs (tile = blockIdx.x +
-// k * gridDim.x) in row-major order, so the halos of neighbouring tiles are read while still in L2.
+//   k_atrous_t2<.., TH, PAIR, CTAS> .. one tile per CTA, every thread stages then filters.  PAIR: a thread filters a
+//       vertical pair of output pixels, so 12 tile entries serve 16 tap evaluations (2/3 of the LDS bytes) ("t2": 64x16
+//       tiles, 2 CTAs/SM).  !PAIR: one pixel per tap loop at 64 registers ("t3": 64x8 tiles, 4 CTAs/SM).
+//   k_atrous_ws ..................... ONE persistent CTA per SM with split roles:
+//     * PRODUCER warps stream tile t+1 from HBM (full-line row segments of the six tapped images; the packed normals
+//       one tile further ahead, so that the sin/cos table lookups ride in the same memory round trip), unpack every
+//       tile pixel once into one of two shared-memory tile buffers, and stage the three centre-only inputs of each
+//       output pixel next to it;
+//     * CONSUMER warps filter tile t out of the other buffer (pixel pairs): nothing in their instruction stream waits
+//       on HBM (only the composing iteration reads its four extra centre-only images directly, ~500 instructions
+//       ahead of use).
+//     Hand-off is two pairs of named barriers (full[b]: producers arrive / consumers sync; empty[b]: the reverse), so
+//     the two roles never meet at a CTA-wide __syncthreads.  Tiles are dealt round-robin to the CTAs (tile = blockIdx.x
+//     + k * gridDim.x) in row-major order, so the halos of neighbouring tiles are read while still in L2.
 #pragma once
 
 #include "asvgf_atrous_tiled.cuh"
