@@ -21,6 +21,19 @@ def test_oracle_reproduces_golden_fixtures():
         assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
 
 
+def test_oracle_reproduces_post_pass_fixtures():
+    """asvgf_post_64x36.npz (tests/golden/make_golden_post.py): resolve, exposure and scattering accumulation."""
+    import make_golden_post
+    ref = np.load(os.path.join(os.path.dirname(GOLDEN), "asvgf_post_64x36.npz"))
+    got = make_golden_post.run()
+    assert sorted(ref.files) == sorted(got)
+    for k in ref.files:
+        assert ref[k].dtype == got[k].dtype and ref[k].shape == got[k].shape, k
+        assert np.array_equal(ref[k].view(np.uint8), got[k].view(np.uint8)), k
+    assert int(ref["f2_histogram"].sum()) == make_golden_post.W * make_golden_post.H and float(ref["f2_avgLuminance"][0]) > 0.0
+    assert float(ref["f2_ScatteringHistory"].max()) == 3.0      # three frames of history where nothing was disoccluded
+
+
 @pytest.mark.gpu
 def test_cuda_path_matches_golden_fixtures():
     import synth
