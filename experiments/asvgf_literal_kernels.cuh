@@ -11,22 +11,15 @@
 // segment a warp touches is one or two full 128-byte lines; packed storage formats are kept end to end.
 #pragma once
 
-#include "asvgf_device.cuh"
+#include "../raytracedgl1_b200/csrc/asvgf_args.cuh"
 
 namespace asvgf
 {
 
-constexpr int kBlockW = 32;
-constexpr int kBlockH = 8;
 
 // ------------------------------------------------------------------------------------------------------------
 // G: gradient samples
 // ------------------------------------------------------------------------------------------------------------
-struct GradientSamplesArgs
-{
-    Img     gradientPrevPix, disPing, disHistory, motion, gradientInputsPrev, isSky, indirAccumPrev, fwdLum;
-    int32_t gyBegin, gyEnd; // gradient rows to compute
-};
 
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples( const __grid_constant__ GradientSamplesArgs a, const __grid_constant__ Uniform u )
 {
@@ -107,12 +100,6 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples( const 
 // ------------------------------------------------------------------------------------------------------------
 // GA: gradient a-trous (3x3, weights {1,.5,.25}, stride 1<<iteration, re-quantised to unorm8 every iteration)
 // ------------------------------------------------------------------------------------------------------------
-struct GradientAtrousArgs
-{
-    Img     src, dst, history;
-    int32_t iteration;
-    int32_t gyBegin, gyEnd;
-};
 
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_atrous( const __grid_constant__ GradientAtrousArgs a, const __grid_constant__ Uniform u )
 {
@@ -151,14 +138,6 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_atrous( const _
 // ------------------------------------------------------------------------------------------------------------
 // T: temporal accumulation
 // ------------------------------------------------------------------------------------------------------------
-struct TemporalArgs
-{
-    Img unfDirect, unfIndir, unfSpec, viewDir, motion, depth, normal, metRough, surfPos, disPing;
-    Img depthPrev, normalPrev, diffHistory, momentsPrev, histLenPrev, specPrev, indirPrev, surfPosPrev;
-    Img outDiffTemporary, outMoments, outHistLen, outSpecAccum, outIndirAccum, outMask;
-    NormalLut lut;
-    int32_t   writeMask;
-};
 
 ASVGF_DEVICE float specAccumSpeed( float minFrames, float Amax, float roughness, float NoV, float parallax ) // :80-92
 {
@@ -390,11 +369,6 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_temporal( const __grid_c
 // F: anti-firefly.  Clamp each colour component to the [min,max] of its 24 neighbours in 5x5 (centre excluded).
 // Tile + 2-pixel halo of the three E5 images staged in shared memory; zeros outside the image participate.
 // ------------------------------------------------------------------------------------------------------------
-struct AntiFireflyArgs
-{
-    Img src[ 3 ]; // DiffTemporary, SpecAccumColor, IndirAccum
-    Img dst[ 3 ]; // DiffAccumColor, SpecPingColor, IndirPing
-};
 
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_antifirefly( const __grid_constant__ AntiFireflyArgs a, const __grid_constant__ Uniform u )
 {
@@ -446,11 +420,6 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_antifirefly( const __gri
 // ------------------------------------------------------------------------------------------------------------
 // V: variance estimation
 // ------------------------------------------------------------------------------------------------------------
-struct VarianceArgs
-{
-    Img       color, normal, depth, histLen, moments, out;
-    NormalLut lut;
-};
 
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance( const __grid_constant__ VarianceArgs a, const __grid_constant__ Uniform u )
 {
@@ -518,15 +487,6 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance( const __grid_c
 // A: edge-stopping a-trous wavelet filter (3x3 at stride 1<<iteration) over diffuse+variance, specular, indirect.
 // ITER0 additionally computes/stores the 3x3-Gaussian-prefiltered luminance sigma; LAST composes PreFinal.
 // ------------------------------------------------------------------------------------------------------------
-struct AtrousArgs
-{
-    Img       srcDiff, srcSpec, srcIndir, dstDiff, dstSpec, dstIndir;
-    Img       depth, depthGrad, normal, metRough, histLen, filteredVariance;
-    Img       albedo, throughput, isSky, preFinal, histogramInput;
-    NormalLut lut;
-    int32_t   iteration;
-    int32_t   tilesPerCta; // production kernels: consecutive 64-column tiles one CTA walks (software pipeline)
-};
 
 template< bool ITER0, bool LAST >
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_atrous( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )

@@ -54,8 +54,8 @@ typedef enum AsvgfCreateFlagBits
     ASVGF_CREATE_BAND_APRON        = 1u << 3, /* band handles: every pass also computes the rows beyond the band that the
                                                  later passes of the frame will read (asvgfBandApronRows), so one frame
                                                  needs two halo exchanges instead of one before each pass            */
-    ASVGF_CREATE_LITERAL_KERNELS   = 1u << 2  /* run the literal one-thread-per-pixel kernels (precise powf/expf, no
-                                                 tiling): slow, closest to the shader text; for A/B numerics checks  */
+    ASVGF_CREATE_LITERAL_KERNELS   = 1u << 2  /* experiments/ build only (make LITERAL=1): one-thread-per-pixel kernels that follow
+                                                 the shader text; ASVGF_UNSUPPORTED in the release build and on band handles */
 } AsvgfCreateFlagBits;
 
 /* = Denoiser ctor + Framebuffers::PrepareForSize (Source/Denoiser.cpp:24-55, Source/Framebuffers.cpp:216-230) */
@@ -63,7 +63,7 @@ typedef struct AsvgfCreateInfo
 {
     uint32_t renderWidth;      /* full frame, must be even (Source/VulkanDevice.cpp:186-187)                     */
     uint32_t renderHeight;
-    uint32_t atrousIterations; /* 4 = the reference; 1..8 accepted (5 = BASELINE config 3, parity unpinned)      */
+    uint32_t atrousIterations; /* 4 = the reference; 2..8 accepted (5 = BASELINE config 3)                       */
     uint32_t flags;            /* AsvgfCreateFlagBits                                                            */
     int32_t  device;           /* CUDA ordinal, -1 = the calling thread's current device                        */
     /* Horizontal band owned by this handle, for one-process-per-GPU frame splitting.  bandRowEnd == 0 means the
@@ -72,7 +72,8 @@ typedef struct AsvgfCreateInfo
        COMPUTES only the owned rows and READS halo rows, which the host fills (NCCL/P2P) before the pass. */
     uint32_t bandRowBegin;
     uint32_t bandRowEnd;
-    uint32_t bandHaloRows;     /* multiple of 3; >= 8*2^(atrousIterations-4) for the a-trous reach               */
+    uint32_t bandHaloRows;     /* multiple of 3; >= 2^(atrousIterations-1), and with ASVGF_CREATE_BAND_APRON also
+                                  >= max(apron(TEMPORAL), 3*apron(GRADIENT_SAMPLES)) (asvgfBandApronRows); checked     */
 } AsvgfCreateInfo;
 
 /* Passes in the reference's dispatch order (Source/Denoiser.cpp:87-254, Source/PathTracer.cpp:212-218). */
@@ -108,7 +109,8 @@ ASVGF_API AsvgfResult asvgfGetImage( AsvgfDenoiser denoiser, uint32_t imageIndex
                                      uint32_t* pRows );
 
 /* Caller-owned storage for one PHYSICAL image (no swap applied: bind X and X_PREV separately).  pDevice addresses
-   the first stored row (same row range as asvgfGetImage reports).  Vulkan-CUDA interop is the caller's business. */
+   the first stored row (same row range as asvgfGetImage reports); pDevice and pitchBytes must be multiples of 16 bytes
+   (ASVGF_WRONG_ARGUMENT otherwise). */
 ASVGF_API AsvgfResult asvgfBindExternalImage( AsvgfDenoiser denoiser, uint32_t imageIndex, void* pDevice,
                                               size_t pitchBytes );
 

@@ -5,12 +5,12 @@
 // (FrameIndexToFBIndex), :639-700 (image extents), Source/PathTracer.cpp:196-219 (gradient samples dispatch).
 #include "../../include/asvgf.h"
 
-#include "asvgf_kernels.cuh"
 #include "asvgf_fast.cuh"
 #include "asvgf_atrous_tiled.cuh"
-#include "asvgf_atrous_pair.cuh"
-#include "asvgf_atrous_ws.cuh"
 #include "asvgf_post.cuh"
+#ifdef ASVGF_WITH_LITERAL // expression-by-expression kernels for A/B numerics; not part of the release build
+    #include "../../experiments/asvgf_literal_kernels.cuh"
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -172,19 +172,13 @@ struct AsvgfDenoiser_T
     NormalLut lut{};
     bool      haveLut     = false;
     uint64_t  launchCount = 0;
-    bool      atrousPair  = false; // ASVGF_ATROUS=pair selects the packed-f32x2 a-trous kernel (measured slower: the pass is smem-pipe bound)
-    // a-trous kernel: 0 = k_atrous_t2 (vectorised staging + pair filter, one tile per CTA), 1 = k_atrous_ws (same, warp-specialised
-    // persistent), 2 = k_atrous_tiled (scalar staging, one pixel per tap loop; default: 0.20/0.19/0.19/0.23 ms at 4K with
-    // 64 x 8 tiles at four CTAs per SM, against 0.22/0.21/0.21/0.25 for t2), 3 = auto: tiled for the plain iterations, t2
-    // for the composing one; ASVGF_ATROUS=tiled|t2|ws|auto|pair
-    int       atrousMode  = 2;
+    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 2 ] = {}; // cudaFuncSetAttribute done for (iteration, composing)
     int       smCount     = 0;
     int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
     // exposure state (= the reference's tonemapping buffer) and the tables of the histogram pass
     AsvgfTonemapping* tm       = nullptr;
     float*            log2Half = nullptr; // correctly rounded log2 of every fp16 bit pattern
     uint8_t*          binTable = nullptr; // histogram bin of every fp16 bit pattern for the current uniform
-    int       atrousTilesPerCta = 1; // ASVGF_ATROUS_TILES: tiles one CTA walks with the next tile's loads in flight (measured: 1, 2, 4 equal; 8+ slower)
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
     {
@@ -241,7 +235,12 @@ AsvgfResult launchCheck( AsvgfDenoiser_T& d, const char* name )
     return ASVGF_SUCCESS;
 }
 
+#ifdef ASVGF_WITH_LITERAL
 bool literal( const AsvgfDenoiser_T& d ) { return ( d.info.flags & ASVGF_CREATE_LITERAL_KERNELS ) != 0; }
+    #define ASVGF_LITERAL_OR( d, literalLaunch, productionLaunch ) do { if( literal( d ) ) { literalLaunch; } else { productionLaunch; } } while( 0 )
+#else
+    #define ASVGF_LITERAL_OR( d, literalLaunch, productionLaunch ) do { productionLaunch; } while( 0 )
+#endif
 
 AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
 {
@@ -253,8 +252,8 @@ AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi,
     a.gradientInputsPrev = d.get( ASVGF_IMAGE_GRADIENT_INPUTS_PREV, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
     a.indirAccumPrev = d.get( ASVGF_IMAGE_INDIR_ACCUM_PREV, fi ); a.fwdLum = d.get( ASVGF_IMAGE_FWD_LUM, fi );
     a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
-    if( literal( d ) ) k_gradient_samples<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
-    else k_gradient_samples_fast<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LITERAL_OR( d, ( k_gradient_samples<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ),
+                      ( k_gradient_samples_fast<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_gradient_samples" );
 }
 
@@ -267,8 +266,8 @@ AsvgfResult runGradientAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, 
     a.dst = d.get( even ? ASVGF_IMAGE_DIS_PONG_GRADIENT : ASVGF_IMAGE_DIS_PING_GRADIENT, fi );
     a.history = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi );
     a.iteration = ( int32_t )iteration; a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
-    if( literal( d ) ) k_gradient_atrous<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
-    else k_gradient_atrous_fast<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LITERAL_OR( d, ( k_gradient_atrous<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ),
+                      ( k_gradient_atrous_fast<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_gradient_atrous" );
 }
 
@@ -294,8 +293,8 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.outIndirAccum = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi ); a.outMask = d.get( ASVGF_IMAGE_DEBUG_MASK, fi );
     a.lut = d.lut;
     a.writeMask = ( ( d.info.flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) && a.outMask.p ) ? 1 : 0;
-    if( literal( d ) ) k_temporal<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
-    else k_temporal_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LITERAL_OR( d, ( k_temporal<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
+                      ( k_temporal_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_temporal" );
 }
 
@@ -306,12 +305,9 @@ AsvgfResult runAntiFirefly( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, con
     AntiFireflyArgs a;
     a.src[ 0 ] = d.get( ASVGF_IMAGE_DIFF_TEMPORARY, fi ); a.src[ 1 ] = d.get( ASVGF_IMAGE_SPEC_ACCUM_COLOR, fi ); a.src[ 2 ] = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi );
     a.dst[ 0 ] = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SPEC_PING_COLOR, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_INDIR_PING, fi );
-    if( literal( d ) ) k_antifirefly<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
-    else
-    {
-        const dim3 grid( ( unsigned )( ( d.W + kAfTile - 1 ) / kAfTile ), ( unsigned )( ( u.yEnd - u.yBegin + kAfTile - 1 ) / kAfTile ), 3 );
-        k_antifirefly_fast<<< grid, kAfThreads, 0, s >>>( a, u );
-    }
+    const dim3 grid( ( unsigned )( ( d.W + kAfTile - 1 ) / kAfTile ), ( unsigned )( ( u.yEnd - u.yBegin + kAfTile - 1 ) / kAfTile ), 3 );
+    ASVGF_LITERAL_OR( d, ( k_antifirefly<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
+                      ( k_antifirefly_fast<<< grid, kAfThreads, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_antifirefly" );
 }
 
@@ -323,15 +319,15 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.color = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
     a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
     a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
-    if( literal( d ) ) k_variance<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
-    else k_variance_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LITERAL_OR( d, ( k_variance<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
+                      ( k_variance_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_variance" );
 }
 
 AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t iteration )
 {
     if( iteration >= d.iterations ) return fail( ASVGF_WRONG_ARGUMENT, "a-trous iteration beyond atrousIterations" );
-    const bool last = iteration + 1 == d.iterations;
+    const bool last = iteration + 1 == d.iterations && iteration > 0; // CmSVGFAtrous.comp:278: only CmSVGFAtrous.comp composes
     // routing: CmSVGFAtrous_Iter0.comp:312-334, CmSVGFAtrous.comp:237-276; beyond 4 iterations it keeps ping-ponging
     uint32_t sDiff, sSpec, sIndir, dDiff, dSpec, dIndir;
     if( iteration == 0 )
@@ -366,10 +362,9 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
     a.tilesPerCta = 1;
 
-    const int    step = 1 << iteration;
-    const bool   pair = d.atrousPair;
-    const size_t smem = pair ? atrousPairSmemBytes( step ) : atrousTiledSmemBytes( step );
-    if( literal( d ) || step > 32 )
+    const int step = 1 << iteration;
+#ifdef ASVGF_WITH_LITERAL
+    if( literal( d ) )
     {
         const dim3 grid = gridFor( ( int )d.W, u.yEnd - u.yBegin );
         if( iteration == 0 ) k_atrous< true, false ><<< grid, kBlock, 0, s >>>( a, u );
@@ -377,107 +372,43 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         else k_atrous< false, false ><<< grid, kBlock, 0, s >>>( a, u );
         return launchCheck( d, "k_atrous" );
     }
-    const int  rows  = u.yEnd - u.yBegin;
-    // the warp-specialised kernel moves four pixels per load: it needs W % 4 == 0 and 16-byte aligned rows
-    auto vec16 = [ & ]( const Img& im ) { return ( ( uintptr_t )im.p % 16 ) == 0 && ( im.pitch % 16 ) == 0; };
-    const bool wsOk = ( d.W % 4 ) == 0 && step <= 32 && vec16( a.normal ) && vec16( a.depth ) && vec16( a.metRough ) && vec16( a.srcDiff ) && vec16( a.srcSpec ) &&
-                      vec16( a.srcIndir ) && vec16( a.depthGrad ) && vec16( a.filteredVariance ) && vec16( a.histLen );
-    if( ( d.atrousMode == 0 || d.atrousMode == 4 || ( d.atrousMode == 3 && last ) ) && !pair && wsOk )
-    {
-        const bool   t3      = d.atrousMode == 4; // 64 x 8 tiles, single pixels, four CTAs per SM
-        const int    th      = t3 ? kT3TileH : atrousWsTileH( step );
-        const int    rowSets = ( ( rows + th * step - 1 ) / ( th * step ) ) * step;
-        const int    tilesX  = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-        const size_t smemT2  = atrousT2SmemBytes( step, th );
-        const dim3   grid( ( unsigned )tilesX, ( unsigned )rowSets, 1 );
-        auto launchT2 = [ & ]( auto kernel ) -> cudaError_t {
-            cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smemT2 );
-            if( e != cudaSuccess ) return e;
-            kernel<<< grid, kT2Threads, smemT2, s >>>( a, u );
-            return cudaSuccess;
-        };
-        cudaError_t e = cudaErrorInvalidValue;
-#define ASVGF_T2_KERNEL( S, I0, L ) ( t3 ? launchT2( k_atrous_t2< S, I0, L, kT3TileH, false, kT3MinCtas > ) : launchT2( k_atrous_t2< S, I0, L, atrousWsTileH( S ), true, ASVGF_T2_MIN_CTAS > ) )
-#define ASVGF_T2_CASE( S ) \
-    case S: e = last ? ASVGF_T2_KERNEL( S, false, true ) : ASVGF_T2_KERNEL( S, false, false ); break;
-        switch( step )
+#endif
+    // dilated tiles: 64 columns x kAtTileH rows spaced `step` apart; grid.y enumerates (band of kAtTileH*step rows, residue)
+    const int    rows   = u.yEnd - u.yBegin;
+    const int    bands  = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
+    const int    tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
+    const size_t smem   = atrousTiledSmemBytes( step );
+    const dim3   grid( ( unsigned )tilesX, ( unsigned )( bands * step ), 1 );
+    // the opt-in to more than 48 KB of dynamic shared memory is per function and per device: once, not per launch
+    auto launch = [ & ]( auto kernel, bool& optedIn ) -> cudaError_t {
+        if( !optedIn )
         {
-            case 1: e = ASVGF_T2_KERNEL( 1, true, false ); break; // iteration 0 is never the last
-            ASVGF_T2_CASE( 2 )
-            ASVGF_T2_CASE( 4 )
-            ASVGF_T2_CASE( 8 )
-            ASVGF_T2_CASE( 16 )
-            ASVGF_T2_CASE( 32 )
-            default: break;
-        }
-#undef ASVGF_T2_CASE
-#undef ASVGF_T2_KERNEL
-        if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_t2)" );
-        return launchCheck( d, "k_atrous_t2" );
-    }
-    if( d.atrousMode == 1 && !pair && wsOk )
-    {
-        // warp-specialised persistent kernel: one CTA per SM walks the dilated tiles round-robin
-        const int    th      = atrousWsTileH( step );
-        const int    rowSets = ( ( rows + th * step - 1 ) / ( th * step ) ) * step;
-        const int    tilesX  = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-        const size_t smemWs  = atrousWsSmemBytes( step );
-        a.tilesPerCta        = rowSets;
-        const int nTiles     = tilesX * rowSets;
-        const dim3 grid( ( unsigned )( nTiles < d.smCount ? nTiles : d.smCount ), 1, 1 );
-        auto launchWs = [ & ]( auto kernel ) -> cudaError_t {
-            cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smemWs );
+            cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
             if( e != cudaSuccess ) return e;
-            kernel<<< grid, kWsThreads, smemWs, s >>>( a, u );
-            return cudaSuccess;
-        };
-        cudaError_t e = cudaErrorInvalidValue;
-#define ASVGF_WS_CASE( S ) \
-    case S: e = last ? launchWs( k_atrous_ws< S, false, true > ) : launchWs( k_atrous_ws< S, false, false > ); break;
-        switch( step )
-        {
-            case 1: e = launchWs( k_atrous_ws< 1, true, false > ); break; // iteration 0 is never the last
-            ASVGF_WS_CASE( 2 )
-            ASVGF_WS_CASE( 4 )
-            ASVGF_WS_CASE( 8 )
-            ASVGF_WS_CASE( 16 )
-            ASVGF_WS_CASE( 32 )
-            default: break;
+            optedIn = true;
         }
-#undef ASVGF_WS_CASE
-        if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_ws)" );
-        return launchCheck( d, "k_atrous_ws" );
-    }
-    // dilated tiles: 64 columns x 16 rows spaced `step` apart; grid.y enumerates (band of 16*step rows, residue)
-    const int  bands = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
-    const int  tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-    a.tilesPerCta     = ( pair || !kAtMultiTile ) ? 1 : d.atrousTilesPerCta;
-    const dim3 grid( ( unsigned )( ( tilesX + a.tilesPerCta - 1 ) / a.tilesPerCta ), ( unsigned )( bands * step ), 1 );
-    auto launch = [ & ]( auto kernel ) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
-        if( e != cudaSuccess ) return e;
         kernel<<< grid, kAtThreads, smem, s >>>( a, u );
         return cudaSuccess;
     };
     cudaError_t e = cudaErrorInvalidValue;
-#define ASVGF_ATROUS_CASE( S )                                                                                              \
-    case S:                                                                                                                 \
-        if( pair ) e = last ? launch( k_atrous_pair< S, false, true > ) : launch( k_atrous_pair< S, false, false > );       \
-        else e = last ? launch( k_atrous_tiled< S, false, true > ) : launch( k_atrous_tiled< S, false, false > );           \
-        break;
+    bool&       opted = d.atrousOptIn[ iteration ][ last ? 1 : 0 ];
+#define ASVGF_ATROUS_CASE( S ) \
+    case S: e = last ? launch( k_atrous_tiled< S, false, true >, opted ) : launch( k_atrous_tiled< S, false, false >, opted ); break;
     switch( step )
     {
-        case 1: e = pair ? launch( k_atrous_pair< 1, true, false > ) : launch( k_atrous_tiled< 1, true, false > ); break; // iteration 0 is never the last
+        case 1: e = launch( k_atrous_tiled< 1, true, false >, opted ); break; // iteration 0 is never the last (atrousIterations >= 2)
         ASVGF_ATROUS_CASE( 2 )
         ASVGF_ATROUS_CASE( 4 )
         ASVGF_ATROUS_CASE( 8 )
         ASVGF_ATROUS_CASE( 16 )
         ASVGF_ATROUS_CASE( 32 )
+        ASVGF_ATROUS_CASE( 64 )
+        ASVGF_ATROUS_CASE( 128 )
         default: break;
     }
 #undef ASVGF_ATROUS_CASE
-    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous)" );
-    return launchCheck( d, pair ? "k_atrous_pair" : "k_atrous_tiled" );
+    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_tiled)" );
+    return launchCheck( d, "k_atrous_tiled" );
 }
 
 AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
@@ -643,6 +574,22 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     if( pInfo->renderWidth > 32768 || pInfo->renderHeight > 32768 ) return fail( ASVGF_WRONG_ARGUMENT, "render size too large" );
     if( pInfo->atrousIterations < 2 || pInfo->atrousIterations > ASVGF_MAX_ATROUS_ITERATIONS ) return fail( ASVGF_WRONG_ARGUMENT, "atrousIterations must be 2..8" );
 
+#ifndef ASVGF_WITH_LITERAL
+    if( pInfo->flags & ASVGF_CREATE_LITERAL_KERNELS ) return fail( ASVGF_UNSUPPORTED, "the literal kernels are not part of this build (make LITERAL=1)" );
+#endif
+    if( ( pInfo->flags & ASVGF_CREATE_LITERAL_KERNELS ) && pInfo->bandRowEnd != 0 )
+        return fail( ASVGF_UNSUPPORTED, "the literal kernels bounds-check against the frame, not the stored rows: no band handles" );
+    if( pInfo->bandRowEnd != 0 )
+    {
+        // a pass reads up to 2^(N-1) rows beyond the rows it computes (the last a-trous iteration); with the apron schedule the
+        // first pass of the chain computes apron(TEMPORAL) rows beyond the band and the gradient passes 3x their gradient rows
+        uint32_t need = 1u << ( pInfo->atrousIterations - 1 );
+        if( pInfo->flags & ASVGF_CREATE_BAND_APRON )
+            need = std::max( need, ( uint32_t )std::max( apronRows( pInfo->atrousIterations, ASVGF_PASS_TEMPORAL ), 3 * apronRows( pInfo->atrousIterations, ASVGF_PASS_GRADIENT_SAMPLES ) ) );
+        if( pInfo->bandHaloRows < need )
+            return fail( ASVGF_WRONG_ARGUMENT, "bandHaloRows is smaller than the vertical reach of the passes (" + std::to_string( need ) + " rows)" );
+    }
+
     int deviceCount = 0;
     if( cudaGetDeviceCount( &deviceCount ) != cudaSuccess || deviceCount == 0 )
     {
@@ -656,12 +603,6 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     AsvgfDenoiser_T* d = new( std::nothrow ) AsvgfDenoiser_T();
     if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
     d->info = *pInfo; d->device = device;
-    if( const char* e = std::getenv( "ASVGF_ATROUS" ) )
-    {
-        d->atrousPair = std::strcmp( e, "pair" ) == 0;
-        d->atrousMode = std::strcmp( e, "ws" ) == 0 ? 1 : std::strcmp( e, "t2" ) == 0 ? 0 : std::strcmp( e, "auto" ) == 0 ? 3 : std::strcmp( e, "t3" ) == 0 ? 4 : 2;
-    }
-    if( const char* e = std::getenv( "ASVGF_ATROUS_TILES" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 64 ) d->atrousTilesPerCta = n; }
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
@@ -724,7 +665,6 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             return fail( rr, msg );
         }
     }
-    if( const char* e = std::getenv( "ASVGF_WS_CTAS" ) ) { const int n = std::atoi( e ); if( n >= 1 && n <= 4096 ) d->smCount = n; }
 
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
     {
@@ -795,8 +735,8 @@ AsvgfResult asvgfBindExternalImage( AsvgfDenoiser d, uint32_t imageIndex, void* 
     Img& im = d->img[ imageIndex ];
     if( !pDevice || pitchBytes < ( size_t )im.w * desc.bpp || pitchBytes % desc.bpp || pitchBytes > 0xffffffffull )
         return fail( ASVGF_WRONG_ARGUMENT, "bad pointer or pitch" );
-    if( ( ( uintptr_t )pDevice % ( desc.bpp < 16 ? desc.bpp : 16 ) ) || ( pitchBytes % ( desc.bpp < 16 ? desc.bpp : 16 ) ) )
-        return fail( ASVGF_WRONG_ARGUMENT, "pointer/pitch must be texel-aligned" );
+    // the kernels move 8- and 16-byte vectors (two E5 texels, four fp16 channels, TMA boxes): rows must keep that alignment
+    if( ( ( uintptr_t )pDevice % 16 ) || ( pitchBytes % 16 ) ) return fail( ASVGF_WRONG_ARGUMENT, "pointer and pitch must be multiples of 16 bytes" );
     if( d->owned[ imageIndex ] && im.p )
     {
         DeviceGuard guard( d->device );

@@ -1,0 +1,63 @@
+// asvgf_args.cuh -- launch geometry and kernel argument blocks of the A-SVGF pass kernels: one block per reference
+// dispatch (Source/Denoiser.cpp:87-254), holding the views of the images that dispatch binds (descriptor set 0).
+#pragma once
+
+#include "asvgf_device.cuh"
+
+namespace asvgf
+{
+
+constexpr int kBlockW = 32; // one-thread-per-pixel kernels: 32 consecutive x per warp (full 128-byte row segments)
+constexpr int kBlockH = 8;
+
+// G: gradient samples, RtGradients.rgen:44-181 (image-space part; the re-shade is read from FwdLum)
+struct GradientSamplesArgs
+{
+    Img     gradientPrevPix, disPing, disHistory, motion, gradientInputsPrev, isSky, indirAccumPrev, fwdLum;
+    int32_t gyBegin, gyEnd; // gradient rows to compute
+};
+
+// GA: gradient a-trous, CmASVGFGradientAtrous.comp:42-105
+struct GradientAtrousArgs
+{
+    Img     src, dst, history;
+    int32_t iteration;
+    int32_t gyBegin, gyEnd;
+};
+
+// T: temporal accumulation, CmSVGFTemporalAccumulation.comp:58-385
+struct TemporalArgs
+{
+    Img unfDirect, unfIndir, unfSpec, viewDir, motion, depth, normal, metRough, surfPos, disPing;
+    Img depthPrev, normalPrev, diffHistory, momentsPrev, histLenPrev, specPrev, indirPrev, surfPosPrev;
+    Img outDiffTemporary, outMoments, outHistLen, outSpecAccum, outIndirAccum, outMask;
+    NormalLut lut;
+    int32_t   writeMask;
+};
+
+// F: anti-firefly, CmAntiFirefly.comp:47-159
+struct AntiFireflyArgs
+{
+    Img src[ 3 ]; // DiffTemporary, SpecAccumColor, IndirAccum
+    Img dst[ 3 ]; // DiffAccumColor, SpecPingColor, IndirPing
+};
+
+// V: variance estimation, CmSVGFEstimateVariance.comp:74-205
+struct VarianceArgs
+{
+    Img       color, normal, depth, histLen, moments, out;
+    NormalLut lut;
+};
+
+// A: a-trous, CmSVGFAtrous_Iter0.comp:92-335 (iteration 0) and CmSVGFAtrous.comp:65-349 (the last one composes PreFinal)
+struct AtrousArgs
+{
+    Img       srcDiff, srcSpec, srcIndir, dstDiff, dstSpec, dstIndir;
+    Img       depth, depthGrad, normal, metRough, histLen, filteredVariance;
+    Img       albedo, throughput, isSky, preFinal, histogramInput;
+    NormalLut lut;
+    int32_t   iteration;
+    int32_t   tilesPerCta; // production kernels: consecutive 64-column tiles one CTA walks (software pipeline)
+};
+
+} // namespace asvgf

@@ -18,7 +18,7 @@
 //   k_variance_fast ............... CmSVGFEstimateVariance.comp:74-205
 #pragma once
 
-#include "asvgf_kernels.cuh"
+#include "asvgf_args.cuh"
 
 namespace asvgf
 {

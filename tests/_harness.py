@@ -9,7 +9,7 @@ Tolerances (north_star: "fp16-output max abs error <= 1e-3 relative to luminance
     states the tolerance)
   * packed E5B9G9R9 / B10G11R11 / unorm8 images ..................... the same bound on decoded values PLUS one
     quantisation step of the storage format (9-, 6/5- and 8-bit mantissas are coarser than 1e-3, so a 1-ulp fp32
-    difference before the store can legitimately flip one code), and >= MIN_EXACT of the texels bit-identical.
+    difference before the store can legitimately flip one code), and >= MIN_EXACT of the texels bit-identical (PreFinal and the unorm8 gradients: >= 99.9 %).
 """
 import numpy as np
 
@@ -19,7 +19,42 @@ from raytracedgl1_b200 import layout
 
 REL_TOL = 1e-3
 EPS = 1e-3
-MIN_EXACT = 0.99
+# fraction of PACKED texels that must be bit-identical (PreFinal "bit-exact or +-1 code, >= 99.9 % exact")
+MIN_EXACT = 0.995
+MIN_EXACT_BY_IMAGE = {"PreFinal": 0.999, "DISPingGradient": 0.999, "DISPongGradient": 0.999, "DISGradientHistory": 0.999}
+# whole-frame comparisons (a frame from identical frame-start state): an E5 code flipped in an intermediate image is carried
+# by the later passes; at most OUTLIER_FRAC of the texels may exceed the single-pass tolerance, none by more than OUTLIER_FACTOR
+OUTLIER_FACTOR = 3.0
+OUTLIER_FRAC = 2e-4
+
+# worst values seen by this process, per image: written to gpurun_out/parity_achieved.json at exit (the gates above are set
+# from these records)
+ACHIEVED = {}
+
+
+def _record(name, r, size):
+    a = ACHIEVED.setdefault(name, dict(min_exact_frac=1.0, worst_ratio=0.0, max_outlier_frac=0.0, comparisons=0))
+    a["min_exact_frac"] = min(a["min_exact_frac"], r["exact_frac"])
+    a["worst_ratio"] = max(a["worst_ratio"], r["worst"])
+    a["max_outlier_frac"] = max(a["max_outlier_frac"], r["n_outlier"] / max(size, 1))
+    a["comparisons"] += 1
+
+
+def _dump_achieved():
+    import json, os
+    if not ACHIEVED:
+        return
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(root, exist_ok=True)
+        with open(os.path.join(root, "parity_achieved.json"), "w") as f:
+            json.dump(ACHIEVED, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+import atexit  # noqa: E402
+atexit.register(_dump_achieved)
 
 COLOR_AND_VARIANCE = ("DiffColorHistory", "DiffPingColorAndVariance", "DiffPongColorAndVariance")
 
@@ -49,10 +84,15 @@ class Pair:
                 self.cuda.upload(name, fi, arr)
         return synth.uniform(self.W, self.H, frame)
 
-    def sync_state_to_cuda(self):
-        """Make the CUDA side's whole image table bit-identical to the oracle's."""
-        for name in layout.IMAGES:
+    def sync_state_to_cuda(self, names=None):
+        """Make the CUDA side's image table (or just `names`, physical images) bit-identical to the oracle's."""
+        for name in (names or layout.IMAGES):
             self.cuda.upload(name, 0, np.ascontiguousarray(self.oracle.image(name, 0)))
+
+    def sync_images(self, names, fi):
+        """Re-lock the (logical, frame index fi) images `names` of the CUDA side to the oracle's bits."""
+        for name in names:
+            self.cuda.upload(name, fi, np.ascontiguousarray(self.oracle.image(name, fi)))
 
     def run_frame(self, frame, uniform_edit=None, mutate=None):
         fi = frame & 1
@@ -69,7 +109,8 @@ class Pair:
 
     def compare(self, fi, names=None, whole_frame=True):
         """whole_frame=True: outputs of a full frame from identical frame-start state (intermediate E5 code flips may
-        propagate): 99.9% of texels within tolerance, none beyond 6x.  False: a single pass from identical state."""
+        propagate): all but OUTLIER_FRAC of the texels within tolerance, none beyond OUTLIER_FACTOR x.  False: a single
+        pass from identical state, every texel within tolerance."""
         out = {}
         for name in (names or layout.IMAGES):
             ref = self.oracle.image(name, fi)
@@ -80,7 +121,7 @@ class Pair:
                     lum = layout.luminance(np.abs(self.oracle.image("DiffColorHistory", fi)[..., :3].astype(np.float32)))
                     lum = np.where(np.isfinite(lum), lum, 0.0)
             if whole_frame:
-                out[name] = compare_image(name, ref, got, outlier_factor=6.0, outlier_frac=1e-3, lum_scale=lum)
+                out[name] = compare_image(name, ref, got, outlier_factor=OUTLIER_FACTOR, outlier_frac=OUTLIER_FRAC, lum_scale=lum)
             else:
                 out[name] = compare_image(name, ref, got, lum_scale=lum)
         return out
@@ -112,7 +153,9 @@ def compare_image(name, ref, got, rel_tol=REL_TOL, outlier_factor=1.0, outlier_f
     dref, kind = _decode(name, ref)
     if kind == "int":
         nbad = int((ref != got).sum())
-        return dict(kind=kind, exact_frac=exact_frac, n_bad=nbad, n_outlier=nbad, ok=nbad == 0, worst=float(nbad > 0))
+        r = dict(kind=kind, exact_frac=exact_frac, n_bad=nbad, n_outlier=nbad, ok=nbad == 0, worst=float(nbad > 0))
+        _record(name, r, ref.size)
+        return r
     dgot, _ = _decode(name, got)
     with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
         finite = np.isfinite(dref) & np.isfinite(dgot)
@@ -152,8 +195,10 @@ def compare_image(name, ref, got, rel_tol=REL_TOL, outlier_factor=1.0, outlier_f
     nout = int((ratio > 1.0).sum())
     # (small images: a fraction of the texels rounds down to zero allowed outliers; allow three)
     allowed = max(outlier_frac * ratio.size, 3.0) if outlier_frac > 0 else 0.0
-    ok = nbad == 0 and nout <= allowed and (kind == "float" or exact_frac >= MIN_EXACT)
-    return dict(kind=kind, exact_frac=exact_frac, n_bad=nbad, n_outlier=nout, ok=ok, worst=worst)
+    ok = nbad == 0 and nout <= allowed and (kind == "float" or exact_frac >= MIN_EXACT_BY_IMAGE.get(name, MIN_EXACT))
+    r = dict(kind=kind, exact_frac=exact_frac, n_bad=nbad, n_outlier=nout, ok=ok, worst=worst)
+    _record(name, r, ratio.size)
+    return r
 
 
 def finite_or_big(x):

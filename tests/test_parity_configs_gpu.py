@@ -1,0 +1,86 @@
+"""Parity at the sizes BASELINE.json names, on one GPU, through the C ABI:
+
+  config 2   1920x1080, 64-frame sequence with camera motion and disocclusions, every frame compared from identical
+             frame-start state (the CUDA state is re-locked to the oracle's after each frame); integer outputs
+             (GradientPrevPix, the disocclusion/history mask) bit-exact on every frame
+  config 3   3840x2160 (the benchmarked frame: 60 x 270 tile grids, every residue of the dilated rows at stride 8),
+             two frames, every pass compared from identical state
+  config 4   7680x4320, one frame with two frames of history, every pass from identical state
+
+Tolerances: tests/_harness.py.  The oracle takes ~0.6 s (1080p) / 2.4 s (4K) / 10 s (8K) per frame on 16 cores.
+"""
+import numpy as np
+import pytest
+
+from _harness import Pair, assert_all_ok
+from test_parity_gpu import OUTPUTS_PER_PASS, _summary
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_1080p_64_frames_locked():
+    p = Pair(1920, 1080)
+    try:
+        disoccluded = 0
+        for frame in range(64):
+            fi, u = p.run_frame(frame)
+            res = p.compare(fi)
+            assert_all_ok(res, "1080p frame %d %s" % (frame, _summary(res)))
+            assert res["DebugMask"]["n_bad"] == 0 and res["GradientPrevPix"]["n_bad"] == 0
+            disoccluded += int((p.oracle.image("DebugMask", fi) != 63).sum())
+            # re-lock what the frame wrote (every image but the producer's inputs)
+            p.sync_state_to_cuda()
+        assert disoccluded > 64 * 1000          # camera motion and moving objects do disocclude
+    finally:
+        p.close()
+
+
+def _per_pass_from_identical_state(p, frame, passes):
+    fi = frame & 1
+    u = p.feed_inputs(frame, fi)
+    p.sync_state_to_cuda()
+    for ps in passes:
+        p.oracle.run_pass(ps, fi, u)
+        p.cuda.denoise_pass(ps, fi, u)
+        p.cuda.synchronize()
+        res = p.compare(fi, OUTPUTS_PER_PASS[ps], whole_frame=False)
+        assert_all_ok(res, "%dx%d frame %d pass %d %s" % (p.W, p.H, frame, ps, _summary(res)))
+        for name in OUTPUTS_PER_PASS[ps]:
+            if res[name]["kind"] == "int":
+                assert res[name]["n_bad"] == 0
+        p.sync_images(OUTPUTS_PER_PASS[ps], fi)  # both sides enter the next pass with the oracle's bits
+
+
+def test_config3_4k_per_pass_two_frames():
+    p = Pair(3840, 2160)
+    try:
+        for frame in range(2):
+            _per_pass_from_identical_state(p, frame, range(12))
+    finally:
+        p.close()
+
+
+def test_config3_4k_five_iterations_last_frame_only():
+    """BASELINE config 3 names 5 a-trous iterations: stride-16 tiles and the composing kernel at iteration 4."""
+    p = Pair(3840, 2160, iterations=5, with_cuda=True)
+    try:
+        fi, u = p.run_frame(0)
+        res = p.compare(fi)
+        assert_all_ok(res, "4K N=5 frame 0 %s" % _summary(res))
+    finally:
+        p.close()
+
+
+def test_config4_8k_per_pass_with_history():
+    p = Pair(7680, 4320)
+    try:
+        for frame in range(2):                   # history: oracle only
+            fi = frame & 1
+            u = p.feed_inputs(frame, fi)
+            p.oracle.gradient_samples(fi, u)
+            p.oracle.denoise(fi, u)
+        _per_pass_from_identical_state(p, 2, range(12))
+        m = p.oracle.image("DebugMask", 0)
+        assert (m == 63).mean() > 0.5 and (m != 63).sum() > 0
+    finally:
+        p.close()

@@ -52,52 +52,6 @@ def test_per_pass_parity_from_identical_state(size):
         p.close()
 
 
-@pytest.mark.parametrize("variant", ["t3", "t2", "ws", "tiled", "pair"])
-def test_atrous_kernel_variants(variant, monkeypatch):
-    """Every a-trous kernel the library can select (ASVGF_ATROUS, read by asvgfCreate): the default one-tile-per-CTA
-    pair filter (t2), the warp-specialised persistent kernel (ws), the scalar tiled kernel and the packed-f32x2 one.
-    Per-pass parity of the four a-trous iterations plus a 5-iteration handle (stride 16 tile geometry)."""
-    monkeypatch.setenv("ASVGF_ATROUS", variant)
-    for W, H, iters in ((320, 180, 4), (512, 288, 5)):
-        p = Pair(W, H, iterations=iters)
-        try:
-            for frame in range(3):
-                fi = frame & 1
-                u = p.feed_inputs(frame, fi)
-                for ps in range(0, 8 + iters):
-                    p.sync_state_to_cuda()
-                    p.oracle.run_pass(ps, fi, u)
-                    p.cuda.denoise_pass(ps, fi, u)
-                    p.cuda.synchronize()
-                    if ps < 8:
-                        continue
-                    names = ["PreFinal", "HistogramInput"] if ps == 7 + iters else None
-                    res = p.compare(fi, names, whole_frame=False) if names else p.compare(fi, whole_frame=False)
-                    assert_all_ok(res, "%s %dx%d frame %d pass %d %s" % (variant, W, H, frame, ps, _summary(res)))
-        finally:
-            p.close()
-
-
-def test_literal_kernels_parity():
-    """ASVGF_CREATE_LITERAL_KERNELS: the one-thread-per-pixel kernels that restate the shaders expression by
-    expression stay available for A/B numerics checks; they must agree with the oracle too, and the production
-    kernels must agree with them on the integer outputs."""
-    from raytracedgl1_b200 import denoiser as dn
-    p = Pair(320, 180, flags=dn.CREATE_EXPORT_DEBUG_MASK | dn.CREATE_LITERAL_KERNELS)
-    q = Pair(320, 180)
-    try:
-        for frame in range(4):
-            fi, u = p.run_frame(frame)
-            q.run_frame(frame)
-            res = p.compare(fi)
-            assert_all_ok(res, "literal frame %d %s" % (frame, _summary(res)))
-            for name in ("DebugMask", "GradientPrevPix"):
-                assert np.array_equal(p.cuda.download(name, fi), q.cuda.download(name, fi)), name
-            p.sync_state_to_cuda(); q.sync_state_to_cuda()
-    finally:
-        p.close(); q.close()
-
-
 def test_sequence_parity_locked_and_masks_bit_exact():
     """16-frame sequence with camera motion, moving objects and the light switch (frame 24 is covered by the next
     test).  After every frame the CUDA state is re-locked to the oracle's, so each frame is compared from identical
