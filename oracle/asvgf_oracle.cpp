@@ -13,12 +13,17 @@
  *                         Source/Shaders/BRDF.h:27-29,49-64
  *   pass order/routing .. Source/Denoiser.cpp:87-254;  cur/prev swap: Source/Framebuffers.cpp:35-50
  *
- * PARITY UNPINNED by the reference (it has no golden vectors and its SPIR-V cannot run here).  Behaviours that
- * GLSL/Vulkan leave implementation-defined are pinned as follows (the CUDA path pins the same):
+ * PARITY PINNED: the reference ships no golden vectors, but its shaders are plain GLSL, and oracle/_ref executes their
+ * UNMODIFIED text (compiled as C++ over the reference's vendored GLM, oracle/ref_glsl/build_ref.py).  Every dispatch of
+ * Denoiser::Denoise and the post dispatches are bit-identical between this file and those shaders from identical state
+ * (tests/test_ref_pins_oracle.py: sizes 6x7 ... 322x182, the light switch, every debug flag, NaN/Inf garbage inputs), and
+ * the fixtures that executor generated are committed (tests/golden/asvgf_ref_96x54.npz).  Only gradientSamples() -- a
+ * ray-generation shader with no compute form -- is pinned by restatement and known-answer tests alone.
+ * Behaviours that GLSL/Vulkan leave implementation-defined are pinned as follows (oracle/_ref and the CUDA path pin the same):
  *   - out-of-bounds texelFetch/imageLoad returns an all-zero texel; out-of-bounds imageStore is discarded
  *   - f32 -> f16 / unorm8 / uf11 / uf10 on imageStore: round-to-nearest-even; uf1x: NaN and negatives -> 0, overflow -> max finite
  *   - GLSL round() = round-half-even; mix(a,b,t) = a*(1-t) + b*t; dot(a,b) = (ax*bx + ay*by) + az*bz;
- *     mat*vec sums columns left to right; no fused multiply-add anywhere (build with -ffp-contract=off)
+ *     mat*vec = (c0*x + c1*y) + (c2*z + c3*w), GLM's order; no fused multiply-add anywhere (build with -ffp-contract=off)
  *   - sin/cos of decodeNormal: correctly rounded fp32 of the fp32 angle; pow/exp/exp2/log: libm fp32
  *   - floor(log2(x)) of the E5B9G9R9 encoder: the exact exponent of x (what exact arithmetic gives)
  *   - float -> int conversions saturate at +-1e9 (out-of-range is undefined in GLSL)
@@ -83,14 +88,16 @@ inline int f2i( float f ) // saturating float->int (pinned, see header)
 }
 inline float glslPow( float x, float y ) { return powf( x, y ); }
 
-// column-major mat4 * vec4
+// column-major mat4 * vec4.  GLSL does not fix the order of the four-term sums; the pin is the order of the reference's
+// own vendored GLM (Tests/Libs/glm/glm/detail/type_mat4x4.inl, mat * vec: (c0*x + c1*y) + (c2*z + c3*w)), which is what
+// oracle/_ref executes
 inline vec4 mulMat( const float* m, vec4 v )
 {
     vec4 r;
-    r.x = ( ( m[ 0 ] * v.x + m[ 4 ] * v.y ) + m[ 8 ] * v.z ) + m[ 12 ] * v.w;
-    r.y = ( ( m[ 1 ] * v.x + m[ 5 ] * v.y ) + m[ 9 ] * v.z ) + m[ 13 ] * v.w;
-    r.z = ( ( m[ 2 ] * v.x + m[ 6 ] * v.y ) + m[ 10 ] * v.z ) + m[ 14 ] * v.w;
-    r.w = ( ( m[ 3 ] * v.x + m[ 7 ] * v.y ) + m[ 11 ] * v.z ) + m[ 15 ] * v.w;
+    r.x = ( m[ 0 ] * v.x + m[ 4 ] * v.y ) + ( m[ 8 ] * v.z + m[ 12 ] * v.w );
+    r.y = ( m[ 1 ] * v.x + m[ 5 ] * v.y ) + ( m[ 9 ] * v.z + m[ 13 ] * v.w );
+    r.z = ( m[ 2 ] * v.x + m[ 6 ] * v.y ) + ( m[ 10 ] * v.z + m[ 14 ] * v.w );
+    r.w = ( m[ 3 ] * v.x + m[ 7 ] * v.y ) + ( m[ 11 ] * v.z + m[ 15 ] * v.w );
     return r;
 }
 

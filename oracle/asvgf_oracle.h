@@ -6,9 +6,10 @@
  * and bench.py's cpu_baseline / --impl reference legs -- never by the product path (libasvgf.so), which has
  * no CPU fallback.
  *
- * PARITY UNPINNED BY THE REFERENCE: RTGL1 ships no golden vectors, tests or prebuilt SPIR-V for this path and
- * the shaders cannot be executed in the build container (no glslc / Vulkan loader / lavapipe), so the oracle is
- * pinned only by (i) being a line-by-line restatement and (ii) the analytic known-answer tests in tests/.
+ * PARITY PINNED BY THE REFERENCE'S OWN SHADER TEXT: RTGL1 ships no golden vectors and no Vulkan runs here, but
+ * oracle/_ref compiles the unmodified Source/Shaders/Cm*.comp as C++ (oracle/ref_glsl/build_ref.py) and this oracle is
+ * bit-identical to it on every dispatch (tests/test_ref_pins_oracle.py, tests/golden/asvgf_ref_96x54.npz).  The
+ * gradient-sample stage (RtGradients.rgen, ray generation) is pinned by restatement and known-answer tests only.
  */
 #ifndef ASVGF_ORACLE_H_
 #define ASVGF_ORACLE_H_

@@ -95,14 +95,14 @@ ASVGF_DEVICE float3 operator*( float3 a, float s ) { return make_float3( mulr( a
 ASVGF_DEVICE float3 operator*( float3 a, float3 b ) { return make_float3( mulr( a.x, b.x ), mulr( a.y, b.y ), mulr( a.z, b.z ) ); }
 ASVGF_DEVICE float3 normalize3r( float3 v ) { float inv = divr( 1.0f, __fsqrt_rn( dot3r( v, v ) ) ); return v * inv; }
 
-// column-major mat4 * vec4, columns summed left to right
+// column-major mat4 * vec4 in the pinned order (GLM's, as the oracle): (c0*x + c1*y) + (c2*z + c3*w)
 ASVGF_DEVICE float4 mulMat( const float* m, float4 v )
 {
     float4 r;
-    r.x = addr( addr( addr( mulr( m[ 0 ], v.x ), mulr( m[ 4 ], v.y ) ), mulr( m[ 8 ], v.z ) ), mulr( m[ 12 ], v.w ) );
-    r.y = addr( addr( addr( mulr( m[ 1 ], v.x ), mulr( m[ 5 ], v.y ) ), mulr( m[ 9 ], v.z ) ), mulr( m[ 13 ], v.w ) );
-    r.z = addr( addr( addr( mulr( m[ 2 ], v.x ), mulr( m[ 6 ], v.y ) ), mulr( m[ 10 ], v.z ) ), mulr( m[ 14 ], v.w ) );
-    r.w = addr( addr( addr( mulr( m[ 3 ], v.x ), mulr( m[ 7 ], v.y ) ), mulr( m[ 11 ], v.z ) ), mulr( m[ 15 ], v.w ) );
+    r.x = addr( addr( mulr( m[ 0 ], v.x ), mulr( m[ 4 ], v.y ) ), addr( mulr( m[ 8 ], v.z ), mulr( m[ 12 ], v.w ) ) );
+    r.y = addr( addr( mulr( m[ 1 ], v.x ), mulr( m[ 5 ], v.y ) ), addr( mulr( m[ 9 ], v.z ), mulr( m[ 13 ], v.w ) ) );
+    r.z = addr( addr( mulr( m[ 2 ], v.x ), mulr( m[ 6 ], v.y ) ), addr( mulr( m[ 10 ], v.z ), mulr( m[ 14 ], v.w ) ) );
+    r.w = addr( addr( mulr( m[ 3 ], v.x ), mulr( m[ 7 ], v.y ) ), addr( mulr( m[ 11 ], v.z ), mulr( m[ 15 ], v.w ) ) );
     return r;
 }
 
