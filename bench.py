@@ -110,10 +110,51 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+REFERENCE_KIND = ("the reference's own compute shaders (unmodified GLSL text of Source/Shaders/Cm*.comp compiled as C++ over its "
+                  "vendored GLM: oracle/_ref) on the host cores; Vulkan/lavapipe does not exist in this image")
+
+
+class _RefSide:
+    """The reference arm's implementation: oracle/_ref (kind 'reference') when its prebuilt library travelled with the
+    repo, else the hand-written oracle port.  The gradient-sample stage (a ray-generation shader) has no compute form:
+    with _ref it is run by the oracle on a copy of the state (a few percent of the step)."""
+
+    def __init__(self, W, rows, N):
+        import oracle
+        from oracle import ref
+        from raytracedgl1_b200 import layout
+        self.layout = layout
+        self.o = oracle.Oracle(W, rows, N)
+        self.kind = "port"
+        self.r = None
+        if N == 4 and ref.available():          # CmSVGFAtrous.comp is written for exactly four iterations (its #error guard)
+            self.r = ref.RefDenoiser(W, rows)
+            self.kind = "reference"
+
+    def image(self, name, fi):
+        return (self.r or self.o).image(name, fi)
+
+    def frame(self, fi, u):
+        if self.r is None:
+            self.o.gradient_samples(fi, u)
+            self.o.denoise(fi, u)
+            return
+        for n in ("Motion", "GradientInputs_Prev", "IsSky", "IndirAccum_Prev", "FwdLum", "DISGradientHistory", "GradientPrevPix"):
+            self.o.image(n, fi)[...] = self.r.image(n, fi)
+        self.o.gradient_samples(fi, u)
+        for n in ("DISPingGradient", "GradientPrevPix"):
+            self.r.image(n, fi)[...] = self.o.image(n, fi)
+        self.r.denoise(fi, u)
+
+    def close(self):
+        self.o.close()
+
+
 def run_reference(args, rank, world):
-    """The reference arm for this tier: the reference's CPU-side stand-in (the oracle, kind 'port' -- the GLSL
-    reference cannot be compiled or run here) on all host threads, each step a bounded band of the
-    same workload."""
+    """The reference arm for this tier: the reference's own CPU-executable form of the path -- oracle/_ref, i.e. the
+    unmodified shader text compiled for the host (kind 'reference'); the oracle port when that library is absent -- on all
+    host threads, each step a bounded band of the same workload.  The line also carries the (faster) oracle port's rate,
+    so that the ratio the driver computes can be read against both."""
     if rank != 0:
         return
     import oracle
@@ -121,33 +162,36 @@ def run_reference(args, rank, world):
     W, H, N, desc = WORKLOADS[args.workload]
     oracle.set_threads(0)
     cores = oracle.get_threads()
-    # calibrate on a small frame, then size the per-step band so that (steps+warmup) steps take about 100 s
-    cal_w, cal_h = 640, 360
-    o = oracle.Oracle(cal_w, cal_h, N)
-    g = synth.generate(cal_w, cal_h, 1)
-    for k, v in g.items():
-        o.image(k, 1)[...] = v
-    u = synth.uniform(cal_w, cal_h, 1)
-    o.gradient_samples(1, u); o.denoise(1, u)
-    t0 = time.perf_counter()
-    o.gradient_samples(1, u); o.denoise(1, u)
-    rate = cal_w * cal_h / (time.perf_counter() - t0)           # pixels per second
-    o.close()
-    budget_s = 100.0
+
+    def rate_of(side_factory, cal_w=640, cal_h=180):
+        side = side_factory(cal_w, cal_h, N)
+        g = synth.generate(cal_w, cal_h, 1)
+        for k, v in g.items():
+            side.image(k, 1)[...] = v
+        u = synth.uniform(cal_w, cal_h, 1)
+        side.frame(1, u)
+        t0 = time.perf_counter()
+        side.frame(1, u)
+        r = cal_w * cal_h / (time.perf_counter() - t0)          # pixels per second
+        kind = side.kind
+        side.close()
+        return r, kind
+
+    rate, kind = rate_of(_RefSide)
+    budget_s = 100.0                                            # (steps + warmup) steps take about this long
     rows = int(rate * budget_s / (args.steps + args.warmup) / W)
     rows = max(36, min(H, rows - rows % 3))
-    o = oracle.Oracle(W, rows, N)
+    side = _RefSide(W, rows, N)
     frames = []
-    for f in (0, 1):                                            # the top `rows` rows of two consecutive 4K-wide frames
+    for f in (0, 1):                                            # the top `rows` rows of two consecutive full-width frames
         frames.append((synth.generate(W, rows, f), synth.uniform(W, rows, f)))
 
     def step(i):
         fi = i & 1
         g, u = frames[fi]
         for k, v in g.items():
-            o.image(k, fi)[...] = v
-        o.gradient_samples(fi, u)
-        o.denoise(fi, u)
+            side.image(k, fi)[...] = v
+        side.frame(fi, u)
 
     for i in range(args.warmup):
         step(i)
@@ -155,19 +199,37 @@ def run_reference(args, rank, world):
     for i in range(args.steps):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
+    side.close()
     value = W * rows * args.steps / dt / 1e6
     sample = "%dx%d band (top rows of the %dx%d frame) per step, %d steps" % (W, rows, W, H, args.steps)
+    port = None
+    if kind == "reference":                                     # the hand-written port, for context (about 10 s)
+        class _Port(_RefSide):
+            def __init__(self, W, rows, N):
+                import oracle as om
+                self.o, self.r, self.kind = om.Oracle(W, rows, N), None, "port"
+        prate, _ = rate_of(_Port, 1280, 360)
+        port = {"value": prate / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "sample": "one 1280x360 frame with history"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "atrous_iterations": N, "reference_kind": "CPU oracle port of the GLSL shaders; "
-                   "the SPIR-V/lavapipe reference is unavailable in this image (no glslc, no Vulkan ICD)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": run_config(args.workload, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "what": REFERENCE_KIND if kind == "reference" else "CPU oracle port of the GLSL shaders (oracle/_ref not present)"},
+        "cpu_port": port,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_config(workload, n_frames):
+    """The `config` object both arms print (the driver compares them key by key)."""
+    W, H, N, desc = WORKLOADS[workload]
+    return {"workload": desc, "width": W, "height": H, "atrous_iterations": N, "streams_per_gpu": 1,
+            "parallelism": "independent view streams, 1 per GPU, no collective",
+            "l2": "no flush: per-stream images total %.2f GB, each pass streams > 126 MB L2" % (201 * W * H / 1e9)}
 
 
 def cpu_baseline(W, H, N, frames):
@@ -225,7 +287,12 @@ def run_ours(args, rank, world, local_rank):
     W, H, N, desc = WORKLOADS[args.workload]
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
-    d = dn.Denoiser(W, H, N, device=local_rank)
+    # the latency-bound gradient chain (gradient samples + 4 gradient a-trous dispatches) is enqueued on its own stream:
+    # the library orders it against the temporal passes itself (asvgf.h, ASVGF_CREATE_EAGER_GRADIENT_ATROUS), so the chain
+    # of frame t+1 overlaps the a-trous iterations of frame t
+    gstream = torch.cuda.Stream()
+    gh = gstream.cuda_stream
+    d = dn.Denoiser(W, H, N, device=local_rank, flags=dn.CREATE_EAGER_GRADIENT_ATROUS)
 
     # A cycled sequence of consecutive synthetic frames (camera motion, moving objects, disocclusions, fireflies;
     # independent stream per rank: its own seed).  Host copies live in pinned memory (the e2e leg uploads them),
@@ -293,13 +360,15 @@ def run_ours(args, rank, world, local_rank):
 
     # the launches of one frame in dispatch order: gradient samples, gradient a-trous x4, temporal, anti-firefly,
     # variance, N a-trous iterations
-    passes = list(range(0, layout.PASS_ATROUS_0 + N))
+    # (the per-pass leg runs them one by one on one stream; pass 0 then carries the whole gradient chain, the four
+    # gradient a-trous ids are no-ops, and the guide plane gets its own slot)
+    passes = list(range(0, layout.PASS_ATROUS_0)) + [layout.PASS_GUIDE] + list(range(layout.PASS_ATROUS_0, layout.PASS_ATROUS_0 + N))
 
     def step_production(i):
         f, fi = i % n_frames, i & 1
         u = uniforms[f]
         bind(fi, resident[f])
-        d.gradient_samples(fi, u, stream=sh)      # = PathTracer::CalculateGradientsSamples (image-space part)
+        d.gradient_samples(fi, u, stream=gh)      # = PathTracer::CalculateGradientsSamples (image-space part) + gradient a-trous
         d.denoise(fi, u, stream=sh)               # = Denoiser::Denoise
 
     def step_per_pass(i, events):
@@ -329,6 +398,7 @@ def run_ours(args, rank, world, local_rank):
     e_begin.record(stream)
     for i in range(args.steps):
         step_production(args.warmup + i)
+    stream.wait_stream(gstream)               # (the last frame's gradient chain is already behind its temporal pass)
     e_end.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -388,8 +458,9 @@ def run_ours(args, rank, world, local_rank):
     def run_step(i, read_back):
         f, fi = i % n_host, i & 1
         stream.wait_event(up_done[i])
+        gstream.wait_event(up_done[i])
         bind(fi, staging[i % 3], staging[(i - 1) % 3])
-        d.gradient_samples(fi, uniforms[f], stream=sh)
+        d.gradient_samples(fi, uniforms[f], stream=gh)
         d.denoise(fi, uniforms[f], stream=sh)
         comp_done[i].record(stream)
         enqueue_upload(i + 1)                        # next frame's copy starts while this frame is being denoised
@@ -443,11 +514,9 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": W, "height": H, "atrous_iterations": N,
-                       "streams_per_gpu": 1, "parallelism": "independent view streams, 1 per GPU, no collective",
-                       "sequence": "%d consecutive synthetic frames (camera motion, moving objects, disocclusions), cycled" % n_frames,
-                       "l2": "no flush: per-stream images total %.2f GB, each pass streams > 126 MB L2" % (201 * W * H / 1e9),
-                       "algorithmic_bytes_per_px": chain_bpp},
+            "config": run_config(args.workload, n_frames),
+            "sequence": "%d consecutive synthetic frames (camera motion, moving objects, disocclusions), cycled" % n_frames,
+            "algorithmic_bytes_per_px": chain_bpp,
             "clocks": clocks,
             "e2e": {"value": world * W * H * e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,

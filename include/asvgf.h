@@ -54,6 +54,12 @@ typedef enum AsvgfCreateFlagBits
     ASVGF_CREATE_BAND_APRON        = 1u << 3, /* band handles: every pass also computes the rows beyond the band that the
                                                  later passes of the frame will read (asvgfBandApronRows), so one frame
                                                  needs two halo exchanges instead of one before each pass            */
+    ASVGF_CREATE_EAGER_GRADIENT_ATROUS = 1u << 4, /* asvgfGradientSamples also enqueues, on ITS stream, the four gradient a-trous
+                                                 dispatches that open the following asvgfDenoise (Denoiser.cpp:87-120), which
+                                                 then skips them: a caller that gives the two calls different streams gets the
+                                                 latency-bound gradient chain of frame t+1 overlapped with the a-trous
+                                                 iterations of frame t.  The library orders the two streams itself (events);
+                                                 results are identical.  Ignored on band handles.                     */
     ASVGF_CREATE_LITERAL_KERNELS   = 1u << 2  /* experiments/ build only (make LITERAL=1): one-thread-per-pixel kernels that follow
                                                  the shader text; ASVGF_UNSUPPORTED in the release build and on band handles */
 } AsvgfCreateFlagBits;
@@ -90,7 +96,10 @@ typedef enum AsvgfPass
     ASVGF_PASS_ATROUS_0          = 8,  /* CmSVGFAtrous_Iter0.comp; ASVGF_PASS_ATROUS_0+i = CmSVGFAtrous.comp, i  */
     ASVGF_PASS_COUNT             = 8 + ASVGF_MAX_ATROUS_ITERATIONS,
     /* the four gradient a-trous dispatches in one call, as asvgfDenoise issues them (Denoiser.cpp:87-120) */
-    ASVGF_PASS_GRADIENT_ATROUS_ALL = 100
+    ASVGF_PASS_GRADIENT_ATROUS_ALL = 100,
+    /* not a reference dispatch: decodes the frame's normal / depth / roughness once into the plane the a-trous iterations
+       read (asvgfDenoise issues it first; asvgfDenoisePass issues it on demand before an a-trous pass) */
+    ASVGF_PASS_GUIDE = 101
 } AsvgfPass;
 
 ASVGF_API AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser );
@@ -124,7 +133,8 @@ ASVGF_API AsvgfResult asvgfDownloadImage( AsvgfDenoiser denoiser, AsvgfStream st
 ASVGF_API AsvgfResult asvgfResetHistory( AsvgfDenoiser denoiser, AsvgfStream stream );
 
 /* = PathTracer::CalculateGradientsSamples, image-space part (RtGradients.rgen:44-105,139-181); the ray-traced
-   re-shade is read from ASVGF_IMAGE_FWD_LUM.  Enqueues only. */
+   re-shade is read from ASVGF_IMAGE_FWD_LUM.  Enqueues only.  `stream` may differ from the stream asvgfDenoise is given:
+   the library makes this pass wait for the previous frame's temporal pass and the next temporal pass wait for it. */
 ASVGF_API AsvgfResult asvgfGradientSamples( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                             const AsvgfGlobalUniform* pUniform );
 /* = Denoiser::Denoise.  Enqueues the whole chain (gradient a-trous x4, temporal, anti-firefly, variance,

@@ -171,6 +171,14 @@ struct AsvgfDenoiser_T
     bool      owned[ ASVGF_IMAGE_COUNT ]{};
     NormalLut lut{};
     bool      haveLut     = false;
+    // internal per-frame scratch: the decoded geometry of the current frame (asvgf_atrous_tiled.cuh, k_guide)
+    Img       guide{};
+    // cross-stream ordering of the gradient chain (asvgfGradientSamples may be given another stream than asvgfDenoise):
+    // the gradient-sample pass of frame t+1 waits for the temporal pass of frame t, the temporal pass waits for the gradient chain
+    cudaEvent_t evTemporalDone = nullptr, evGradientsDone = nullptr;
+    bool        temporalRecorded = false, gradientsRecorded = false;
+    bool        gradientAtrousDone = false; // ASVGF_CREATE_EAGER_GRADIENT_ATROUS: the chain already ran behind the gradient samples
+    bool        guideValid = false;         // the guide plane matches the geometry images of the frame being denoised
     uint64_t  launchCount = 0;
     bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 2 ] = {}; // cudaFuncSetAttribute done for (iteration, composing)
     int       smCount     = 0;
@@ -324,6 +332,19 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     return launchCheck( d, "k_variance" );
 }
 
+// decoded geometry of the frame (normal, depth, roughness) for the a-trous iterations, over every stored row
+AsvgfResult runGuide( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi )
+{
+    NEED( ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_DEPTH_WORLD, ASVGF_IMAGE_METALLIC_ROUGHNESS );
+    GuideArgs a;
+    a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi ); a.metRough = d.get( ASVGF_IMAGE_METALLIC_ROUGHNESS, fi );
+    a.guide = d.guide; a.lut = d.lut;
+    a.yBegin = d.row0; a.yEnd = d.row0 + d.rows;
+    const dim3 grid( ( unsigned )( ( d.W + 255 ) / 256 ), ( unsigned )( ( d.rows + 3 ) / 4 ), 1 );
+    k_guide<<< grid, 256, 0, s >>>( a );
+    return launchCheck( d, "k_guide" );
+}
+
 AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t iteration )
 {
     if( iteration >= d.iterations ) return fail( ASVGF_WRONG_ARGUMENT, "a-trous iteration beyond atrousIterations" );
@@ -360,7 +381,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.albedo = d.get( ASVGF_IMAGE_ALBEDO, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
     a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.histogramInput = d.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
-    a.tilesPerCta = 1;
+    a.guide = d.guide;
 
     const int step = 1 << iteration;
 #ifdef ASVGF_WITH_LITERAL
@@ -696,6 +717,25 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             return fail( rr, msg );
         }
     }
+    {
+        Img& g = d->guide;
+        g.w = ( int32_t )d->W; g.h = ( int32_t )d->H; g.row0 = d->row0; g.rows = d->rows;
+        const uint32_t pitch = ( d->W * 16u + 255u ) & ~255u;
+        uint8_t*       mem   = nullptr;
+        cudaError_t    e     = cudaMalloc( ( void** )&mem, ( size_t )pitch * ( size_t )g.rows );
+        if( e == cudaSuccess ) e = cudaMemset( mem, 0, ( size_t )pitch * ( size_t )g.rows );
+        if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &d->evTemporalDone, cudaEventDisableTiming );
+        if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &d->evGradientsDone, cudaEventDisableTiming );
+        if( e != cudaSuccess )
+        {
+            if( mem ) cudaFree( mem );
+            AsvgfResult rr = cudaFail( e, "cudaMalloc(guide plane)" );
+            std::string msg = g_lastError;
+            asvgfDestroy( d );
+            return fail( rr, msg );
+        }
+        setImgStorage( g, mem, pitch, 16 );
+    }
     *pDenoiser = d;
     return ASVGF_SUCCESS;
 }
@@ -707,6 +747,9 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
         if( d->owned[ i ] && d->img[ i ].p ) cudaFree( d->img[ i ].p );
     if( d->haveLut ) releaseLut( d->device );
+    if( d->guide.p ) cudaFree( d->guide.p );
+    if( d->evTemporalDone ) cudaEventDestroy( d->evTemporalDone );
+    if( d->evGradientsDone ) cudaEventDestroy( d->evGradientsDone );
     if( d->log2Half ) cudaFree( d->log2Half );
     if( d->binTable ) cudaFree( d->binTable );
     if( d->tm ) cudaFree( d->tm );
@@ -744,6 +787,7 @@ AsvgfResult asvgfBindExternalImage( AsvgfDenoiser d, uint32_t imageIndex, void* 
         d->owned[ imageIndex ] = false;
     }
     setImgStorage( im, ( uint8_t* )pDevice, ( uint32_t )pitchBytes, desc.bpp );
+    d->guideValid = false;
     return ASVGF_SUCCESS;
 }
 
@@ -757,6 +801,7 @@ static AsvgfResult copyImage( AsvgfDenoiser d, AsvgfStream stream, uint32_t imag
     if( hostPitch == 0 ) hostPitch = rowBytes;
     if( hostPitch < rowBytes ) return fail( ASVGF_WRONG_ARGUMENT, "host pitch smaller than a row" );
     DeviceGuard guard( d->device );
+    if( upload ) d->guideValid = false;
     if( upload ) CUDA_TRY( cudaMemcpy2DAsync( im.p, im.pitch, pHost, hostPitch, rowBytes, ( size_t )im.rows, cudaMemcpyHostToDevice, ( cudaStream_t )stream ) );
     else CUDA_TRY( cudaMemcpy2DAsync( pHost, hostPitch, im.p, im.pitch, rowBytes, ( size_t )im.rows, cudaMemcpyDeviceToHost, ( cudaStream_t )stream ) );
     return ASVGF_SUCCESS;
@@ -776,6 +821,7 @@ AsvgfResult asvgfResetHistory( AsvgfDenoiser d, AsvgfStream stream )
     DeviceGuard guard( d->device );
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
         if( d->owned[ i ] && d->img[ i ].p ) CUDA_TRY( cudaMemsetAsync( d->img[ i ].p, 0, ( size_t )d->img[ i ].pitch * d->img[ i ].rows, ( cudaStream_t )stream ) );
+    d->guideValid = false;
     return ASVGF_SUCCESS;
 }
 
@@ -783,22 +829,53 @@ AsvgfResult asvgfGradientSamples( AsvgfDenoiser d, AsvgfStream stream, uint32_t 
 {
     AsvgfResult r = checkCall( d, frameIndex, pUniform );
     if( r != ASVGF_SUCCESS ) return r;
-    DeviceGuard guard( d->device );
-    return runPass( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), ASVGF_PASS_GRADIENT_SAMPLES );
+    DeviceGuard        guard( d->device );
+    const cudaStream_t s = ( cudaStream_t )stream;
+    const Uniform      u = makeUniform( *d, *pUniform );
+    // this pass reads what the previous frame's temporal pass wrote (IndirAccum_Prev) and overwrites what it read
+    // (DISPingGradient): when the two are enqueued on different streams the order must be made explicit
+    if( d->temporalRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evTemporalDone, 0 ) );
+    d->guideValid = false; // a new frame starts
+    r = runPass( *d, s, frameIndex, u, ASVGF_PASS_GRADIENT_SAMPLES );
+    if( r != ASVGF_SUCCESS ) return r;
+    d->gradientAtrousDone = false;
+    if( ( d->info.flags & ASVGF_CREATE_EAGER_GRADIENT_ATROUS ) && d->info.bandRowEnd == 0 )
+    {
+        r = runPass( *d, s, frameIndex, u, ASVGF_PASS_GRADIENT_ATROUS_ALL ); // Denoiser.cpp:87-120, issued early
+        if( r != ASVGF_SUCCESS ) return r;
+        d->gradientAtrousDone = true;
+    }
+    CUDA_TRY( cudaEventRecord( d->evGradientsDone, s ) );
+    d->gradientsRecorded = true;
+    return ASVGF_SUCCESS;
 }
 
 AsvgfResult asvgfDenoise( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
 {
     AsvgfResult r = checkCall( d, frameIndex, pUniform );
     if( r != ASVGF_SUCCESS ) return r;
-    DeviceGuard   guard( d->device );
-    const Uniform u = makeUniform( *d, *pUniform );
-    r = runPass( *d, ( cudaStream_t )stream, frameIndex, u, ASVGF_PASS_GRADIENT_ATROUS_ALL ); // Denoiser.cpp:87-120
+    DeviceGuard        guard( d->device );
+    const cudaStream_t s = ( cudaStream_t )stream;
+    const Uniform      u = makeUniform( *d, *pUniform );
+    r = runGuide( *d, s, frameIndex ); // independent of the gradient chain: overlaps it when that runs on another stream
     if( r != ASVGF_SUCCESS ) return r;
-    for( uint32_t pass = ASVGF_PASS_TEMPORAL; pass < ASVGF_PASS_ATROUS_0 + d->iterations; pass++ ) // Denoiser.cpp:87-254
+    d->guideValid = true;
+    if( d->gradientsRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evGradientsDone, 0 ) );
+    if( !d->gradientAtrousDone )
     {
-        r = runPass( *d, ( cudaStream_t )stream, frameIndex, u, pass );
+        r = runPass( *d, s, frameIndex, u, ASVGF_PASS_GRADIENT_ATROUS_ALL ); // Denoiser.cpp:87-120
         if( r != ASVGF_SUCCESS ) return r;
+    }
+    d->gradientAtrousDone = false;
+    for( uint32_t pass = ASVGF_PASS_TEMPORAL; pass < ASVGF_PASS_ATROUS_0 + d->iterations; pass++ ) // Denoiser.cpp:123-254
+    {
+        r = runPass( *d, s, frameIndex, u, pass );
+        if( r != ASVGF_SUCCESS ) return r;
+        if( pass == ASVGF_PASS_TEMPORAL )
+        {
+            CUDA_TRY( cudaEventRecord( d->evTemporalDone, s ) );
+            d->temporalRecorded = true;
+        }
     }
     return ASVGF_SUCCESS;
 }
@@ -808,7 +885,41 @@ AsvgfResult asvgfDenoisePass( AsvgfDenoiser d, AsvgfStream stream, uint32_t fram
     AsvgfResult r = checkCall( d, frameIndex, pUniform );
     if( r != ASVGF_SUCCESS ) return r;
     DeviceGuard guard( d->device );
-    return runPass( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), pass );
+    const cudaStream_t s = ( cudaStream_t )stream;
+    if( pass == ASVGF_PASS_GUIDE )
+    {
+        r = runGuide( *d, s, frameIndex );
+        d->guideValid = r == ASVGF_SUCCESS;
+        return r;
+    }
+    const bool gradAtrous = ( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) || pass == ASVGF_PASS_GRADIENT_ATROUS_ALL;
+    if( gradAtrous && d->gradientAtrousDone ) return ASVGF_SUCCESS; // ASVGF_CREATE_EAGER_GRADIENT_ATROUS: already ran behind the gradient samples
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_ATROUS_0 + d->iterations )
+    {
+        // the guide plane is refreshed by the first a-trous dispatch after anything that may have changed the geometry images
+        if( !d->guideValid )
+        {
+            r = runGuide( *d, s, frameIndex );
+            if( r != ASVGF_SUCCESS ) return r;
+            d->guideValid = true;
+        }
+    }
+    else
+    {
+        d->guideValid = false;
+        if( pass == ASVGF_PASS_TEMPORAL )
+        {
+            d->gradientAtrousDone = false;
+            if( d->gradientsRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evGradientsDone, 0 ) );
+        }
+    }
+    r = runPass( *d, s, frameIndex, makeUniform( *d, *pUniform ), pass );
+    if( r == ASVGF_SUCCESS && pass == ASVGF_PASS_TEMPORAL )
+    {
+        CUDA_TRY( cudaEventRecord( d->evTemporalDone, s ) );
+        d->temporalRecorded = true;
+    }
+    return r;
 }
 
 AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
@@ -887,6 +998,7 @@ const char* asvgfPassName( uint32_t pass )
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return "k_gradient_samples";
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return "k_gradient_atrous";
     if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL ) return "k_gradient_atrous";
+    if( pass == ASVGF_PASS_GUIDE ) return "k_guide";
     if( pass == ASVGF_PASS_TEMPORAL ) return "k_temporal";
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return "k_antifirefly";
     if( pass == ASVGF_PASS_VARIANCE ) return "k_variance";
@@ -908,6 +1020,7 @@ double asvgfPassBytesPerPixel( uint32_t pass, uint32_t atrousIterations )
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return 12.8;
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return 1.0;
     if( pass == ASVGF_PASS_GRADIENT_ATROUS_ALL ) return 4.0; // the reference's four dispatches (36 B per gradient pixel)
+    if( pass == ASVGF_PASS_GUIDE ) return 0.0; // not a reference dispatch: its 24 B/px are extra traffic this design adds, not algorithmic bytes
     if( pass == ASVGF_PASS_TEMPORAL ) return 126.4;
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return 24.0;
     if( pass == ASVGF_PASS_VARIANCE ) return 30.0;

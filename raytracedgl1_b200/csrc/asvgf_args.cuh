@@ -55,9 +55,9 @@ struct AtrousArgs
     Img       srcDiff, srcSpec, srcIndir, dstDiff, dstSpec, dstIndir;
     Img       depth, depthGrad, normal, metRough, histLen, filteredVariance;
     Img       albedo, throughput, isSky, preFinal, histogramInput;
+    Img       guide;       // (n.xyz, depth | roughness byte) of the current frame, written by k_guide
     NormalLut lut;
     int32_t   iteration;
-    int32_t   tilesPerCta; // production kernels: consecutive 64-column tiles one CTA walks (software pipeline)
 };
 
 } // namespace asvgf

@@ -1,64 +1,42 @@
-// asvgf_atrous_tiled.cuh -- the production a-trous kernel (all iterations), sm_100a.
+// asvgf_atrous_tiled.cuh -- the a-trous kernel (CmSVGFAtrous.comp iterations >= 1, and CmSVGFAtrous_Iter0.comp when the fused
+// F+V+A0 kernel is not used), sm_100a, plus the per-frame guide plane it reads.
 //
-// Same arithmetic as CmSVGFAtrous_Iter0.comp:158-335 / CmSVGFAtrous.comp:65-349 (see k_atrous in asvgf_kernels.cuh for
-// the literal form), restructured for the B200 SM, where the pass is instruction-issue bound (ncu: the literal form
-// runs 2200 instructions per pixel with DRAM at 6 %; profiles/r01_v1_*, r01_v2_*):
+// Arithmetic: CmSVGFAtrous_Iter0.comp:158-335 / CmSVGFAtrous.comp:65-349.  Structure (round 2; ncu of the round-1 kernel:
+// 578 instructions per pixel, issue 73 %, shared-memory pipe 60 %, ALU pipe 41 % -- instruction- and LDS-bound, DRAM 30 %):
 //
-//  * DILATED TILE.  For stride s a pixel only ever touches rows y, y+-s.  A CTA therefore owns 64 contiguous columns of
-//    8 rows spaced s apart (rows y0+r, y0+r+s, ...; the s residues r go to s different CTAs).  Its halo is one dilated
-//    row above/below and s columns left/right, so the read amplification is (10/8)*((64+2s)/64) = 1.29..1.56 for
-//    every stride instead of the (1+2s/T)^2 of a square tile, and every global access is still a full-line row segment.
-//    (64 x 8 keeps a tile at 41-51 KB of shared memory and 64 registers per thread: four CTAs = 32 warps per SM.)
-//  * DECODE ONCE.  Each tile pixel is unpacked once on the way into shared memory -- normal through the exact sin/cos
-//    table, E5B9G9R9 and fp16 to fp32, luminance -- into four float4 planes, so a tap costs four conflict-free
-//    LDS.128 and no conversions.  The stride is a template parameter: every tap address is an immediate offset.
-//  * WEIGHTS THROUGH ONE LOG.  w_n = (n.n')^128 and the specular lobe (n.n')^P share L = lg2(n.n'), and the wavelet
-//    kernel weight / inside-the-render-area test is folded into the exponent (lk = log2 k, or -inf outside):
+//  * GUIDE PLANE.  Normal, depth and roughness do not change between the iterations of a frame, yet every iteration used to
+//    re-decode them per staged texel (two dependent sin/cos-table gathers per normal).  k_guide decodes them ONCE per frame
+//    into a float4 plane (n.xyz, depth); roughness rides in the low byte of the depth word (an fp16 depth leaves the low 13
+//    mantissa bits of its fp32 form zero) and is split off while staging.  A tile's geometry costs one 16-byte load per texel.
+//  * DILATED TILE.  For stride s a pixel only touches rows y, y+-s: a CTA owns 64 columns of 8 rows spaced s apart (the s
+//    residues go to s different CTAs); halo = one dilated row above/below, max(s,4) columns left/right.  Read amplification
+//    1.4-1.56 at every stride, every global access a full-line row segment.
+//  * VECTOR STAGING.  A thread stages four consecutive texels: 4+2+1+1 16-byte loads, one address computation per image,
+//    decode, 16 STS.128.  No per-texel index arithmetic, no table gathers.
+//  * WEIGHTS THROUGH ONE LOG.  w_n = (n.n')^128 and the specular lobe (n.n')^P share L = lg2(n.n'); the wavelet weight and the
+//    render-area test are folded into the exponent (lk = log2 k, or -inf outside):
 //      wBase = ex2(128 L + lk - wz^2 log2e),  wDiff = ex2(128 L + lk - (wz^2 + wl) log2e),  wSpec = r * ex2(. + P L)
-//    i.e. 1 lg2 + 3 ex2 on the MUFU pipe and ~40 FMA-pipe instructions per tap instead of two powf and two expf.
-//    Relative weight error <= ~3e-4 (|P|<=1152 times the 2^-22 absolute error of lg2.approx), inside the 1e-3 output
-//    tolerance because the weights are normalised; integer/boolean outputs do not depend on this kernel.
+//    1 lg2 + 3 ex2 and ~30 FMA-pipe instructions per tap.  Tiles whose taps all stay inside the render area (all but the
+//    frame / checkerboard-separator borders) take a loop with immediate lk; the choice is per CTA, not per pixel.
+//  * 64 registers, 41-51 KB of shared memory: four CTAs = 32 warps per SM.
 #pragma once
 
 #include "asvgf_fast.cuh"
 
-#include <type_traits>
-
 namespace asvgf
 {
 
-// Tile height / CTAs per SM.  Measured at 4K (ms per iteration, plain / composing), one tile per CTA:
-//   16 rows, 2 CTAs/SM (128 regs, 16 warps/SM): 0.22 / 0.25      8 rows, 3 CTAs/SM (80 regs): 0.21 / 0.23
-//    8 rows, 4 CTAs/SM ( 64 regs, 32 warps/SM): 0.19 / 0.23     16 rows, 2 x 512 threads (64 regs): 0.20 / 0.23
-// The pass is bound by issue latency (a long dependent chain per tap), so the warps per SM matter more than the 11 %
-// of extra halo rows the shorter tile stages.
-#ifndef ASVGF_AT_TILE_H
-    #define ASVGF_AT_TILE_H 8
-#endif
-#ifndef ASVGF_AT_THREADS
-    #define ASVGF_AT_THREADS 256
-#endif
+constexpr int kAtTileW   = 64;  // columns per CTA
+constexpr int kAtTileH   = 8;   // dilated rows per CTA
+constexpr int kAtThreads = 256; // 2 pixels per thread
 #ifndef ASVGF_AT_MIN_CTAS
     #define ASVGF_AT_MIN_CTAS 4
 #endif
-#ifndef ASVGF_AT_MULTI_TILE
-    #define ASVGF_AT_MULTI_TILE 0 // 1: a CTA walks a.tilesPerCta tiles with the next tile's loads in flight (measured equal to one tile per CTA)
-#endif
-constexpr bool kAtMultiTile = ASVGF_AT_MULTI_TILE != 0;
-constexpr int kAtTileW   = 64;               // columns per CTA
-constexpr int kAtTileH   = ASVGF_AT_TILE_H;  // dilated rows per CTA
-constexpr int kAtThreads = ASVGF_AT_THREADS; // 4 pixels per thread
-constexpr int kAtBytesPerTilePixel = 64;
+
+constexpr int    atrousHalo( int step ) { return step < 4 ? 4 : step; } // halo columns: multiples of 4 keep 16-byte row segments
+constexpr size_t atrousTiledSmemBytes( int step ) { return ( size_t )( kAtTileW + 2 * atrousHalo( step ) ) * ( kAtTileH + 2 ) * 64; }
 
 ASVGF_DEVICE float ex2Approx( float x ) { return fex2( x ); }
-// exp2 that keeps denormal results (MUFU.EX2 flushes them): a vanishing weight must stay non-zero exactly as long as
-// the shader's exp() does, because an infinite fp16 variance times a zero weight is NaN but times a denormal weight is inf
-ASVGF_DEVICE float ex2ApproxDenorm( float x )
-{
-    const bool  tiny = x < -126.0f;
-    const float r    = fex2( tiny ? x * 0.5f : x );
-    return tiny ? r * r : r;
-}
 
 // B10G11R11_UFLOAT <-> fp32 through the fp16 bit layout (a uf11 is the top 11 bits of a positive half, a uf10 the top 10)
 ASVGF_DEVICE float3 unpackUfloat111110Fast( uint32_t p )
@@ -77,116 +55,149 @@ template< uint32_t MBITS > ASVGF_DEVICE uint32_t floatToUfloatFast( float f ) //
 }
 ASVGF_DEVICE uint32_t packUfloat111110Fast( float3 c ) { return floatToUfloatFast< 6 >( c.x ) | ( floatToUfloatFast< 6 >( c.y ) << 11 ) | ( floatToUfloatFast< 5 >( c.z ) << 22 ); }
 
-// raw (still packed) texels of one tile pixel and of one output pixel's centre-only inputs: what a thread keeps in
-// registers while the loads of the NEXT tile are in flight behind the arithmetic of the current one
-// (no arithmetic may touch a loaded value before the tile is committed: a use would stall the thread on the load)
-struct AtrousRaw { uint32_t n, s, i; uint2 d; uint16_t depth, mr; };
-template< bool ITER0, bool LAST > struct AtrousCentre { uint2 histLen, tp; uint32_t albedo; uint16_t gradDepth, sigma, metRough; uint8_t sky; };
+// ------------------------------------------------------------------------------------------------------------
+// guide plane: (n.x, n.y, n.z, depth | roughness byte) of every stored pixel of the current frame
+// ------------------------------------------------------------------------------------------------------------
+struct GuideArgs
+{
+    Img       normal, depth, metRough, guide;
+    NormalLut lut;
+    int32_t   yBegin, yEnd; // stored rows
+};
 
+ASVGF_DEVICE float4 guideTexel( const NormalLut& lut, uint32_t encNormal, uint16_t depthHalf, uint16_t metRough )
+{
+    const float3   n = decodeNormal( lut, encNormal );
+    const uint32_t w = __float_as_uint( h2f( depthHalf ) ) | ( ( uint32_t )metRough >> 8 ); // fp16 -> fp32 leaves the low 13 bits zero
+    return make_float4( n.x, n.y, n.z, __uint_as_float( w ) );
+}
+ASVGF_DEVICE float guideDepth( float w ) { return __uint_as_float( __float_as_uint( w ) & 0xffffff00u ); }
+ASVGF_DEVICE float guideRoughByte( float w ) { return ( float )( __float_as_uint( w ) & 0xffu ); } // 0..255
+
+__global__ void __launch_bounds__( 256 ) k_guide( const __grid_constant__ GuideArgs a )
+{
+    // one thread = four consecutive pixels of a row (W is even; a partial group at the right edge is handled per pair)
+    const int x0 = ( blockIdx.x * 64 + ( threadIdx.x & 63 ) ) * 4;
+    const int y  = a.yBegin + blockIdx.y * 4 + ( threadIdx.x >> 6 );
+    if( x0 >= a.guide.w || y >= a.yEnd ) return;
+    const bool full = x0 + 3 < a.guide.w;
+    uint32_t   n[ 4 ];
+    uint16_t   d[ 4 ], mr[ 4 ];
+    if( full )
+    {
+        const uint4 nn = __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.normal, x0, y ) ) );
+        const uint2 dd = __ldg( reinterpret_cast< const uint2* >( at< uint16_t >( a.depth, x0, y ) ) );
+        const uint2 rr = __ldg( reinterpret_cast< const uint2* >( at< uint16_t >( a.metRough, x0, y ) ) );
+        n[ 0 ] = nn.x; n[ 1 ] = nn.y; n[ 2 ] = nn.z; n[ 3 ] = nn.w;
+        d[ 0 ] = ( uint16_t )dd.x; d[ 1 ] = ( uint16_t )( dd.x >> 16 ); d[ 2 ] = ( uint16_t )dd.y; d[ 3 ] = ( uint16_t )( dd.y >> 16 );
+        mr[ 0 ] = ( uint16_t )rr.x; mr[ 1 ] = ( uint16_t )( rr.x >> 16 ); mr[ 2 ] = ( uint16_t )rr.y; mr[ 3 ] = ( uint16_t )( rr.y >> 16 );
+    }
+    else
+    {
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            const bool ok = x0 + k < a.guide.w;
+            n[ k ]  = ldIf< uint32_t >( a.normal, x0 + k, y, ok, 0u );
+            d[ k ]  = ldIf< uint16_t >( a.depth, x0 + k, y, ok, ( uint16_t )0 );
+            mr[ k ] = ldIf< uint16_t >( a.metRough, x0 + k, y, ok, ( uint16_t )0 );
+        }
+    }
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+        if( x0 + k < a.guide.w ) *atW< float4 >( a.guide, x0 + k, y ) = guideTexel( a.lut, n[ k ], d[ k ], mr[ k ] );
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the filter
+// ------------------------------------------------------------------------------------------------------------
 template< int STEP, bool ITER0, bool LAST >
 __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
-    extern __shared__ __align__( 16 ) uint8_t smemRaw[];
-    constexpr int TW    = kAtTileW + 2 * STEP; // tile width incl. halo columns
-    constexpr int TROWS = kAtTileH + 2;
-    constexpr int NPX   = TW * TROWS;
-    constexpr int NIT   = ( NPX + kAtThreads - 1 ) / kAtThreads;
-    constexpr int PIX   = ( kAtTileW * kAtTileH ) / kAtThreads;
+    extern __shared__ __align__( 128 ) uint8_t smemRaw[];
+    constexpr int HALO   = atrousHalo( STEP );
+    constexpr int TW     = kAtTileW + 2 * HALO; // staged columns
+    constexpr int TROWS  = kAtTileH + 2;
+    constexpr int NPX    = TW * TROWS;
+    constexpr int GROUPS = TW / 4;              // 4-texel groups per staged row
+    constexpr int NGRP   = GROUPS * TROWS;
+    constexpr int PIX    = ( kAtTileW * kAtTileH ) / kAtThreads;
     float4* sA = reinterpret_cast< float4* >( smemRaw ); // normal.xyz, depth
     float4* sB = sA + NPX;                               // diffuse rgb, variance
     float4* sC = sB + NPX;                               // specular rgb, luminance of the diffuse rgb
-    float4* sD = sC + NPX;                               // indirect rgb, roughness
+    float4* sD = sC + NPX;                               // indirect rgb, roughness byte (0..255 as float)
 
-    // dilated rows: blockIdx.y enumerates (band, residue); row(j) = yBase + j*STEP, j = -1 .. kAtTileH.
-    // A CTA walks a.tilesPerCta consecutive 64-column tiles of that row set; while it filters tile t from shared
-    // memory, the global loads of tile t+1 are already in flight into registers (software pipeline), so only the first
-    // tile's HBM latency is exposed.
+    // dilated rows: blockIdx.y enumerates (band, residue); row(j) = yBase + j*STEP, j = -1 .. kAtTileH
     const int band  = blockIdx.y / STEP, res = blockIdx.y - band * STEP;
     const int yBase = u.yBegin + band * ( kAtTileH * STEP ) + res;
-    const int nTilesCta = kAtMultiTile ? a.tilesPerCta : 1;
-    const int xFirst = blockIdx.x * nTilesCta * kAtTileW;
+    const int xBase = blockIdx.x * kAtTileW;
     const Rows rows = rowsOf( a.depth );
 
-    AtrousRaw raw[ NIT ];
-    AtrousCentre< ITER0, LAST > cen[ PIX ], cenNext[ kAtMultiTile ? PIX : 1 ];
-
-    auto issue = [ & ]( int xBase, AtrousCentre< ITER0, LAST >( &cc )[ PIX ] )
+    // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----
+    uint16_t cGrad[ PIX ], cSigma[ PIX ], cSpecLen[ PIX ];
+#pragma unroll
+    for( int k = 0; k < PIX; k++ )
     {
-#pragma unroll
-        for( int k = 0; k < PIX; k++ )
-        {
-            const int  p  = threadIdx.x + k * kAtThreads;
-            const int  j  = p / kAtTileW, c = p - j * kAtTileW;
-            const int  px = xBase + c, py = yBase + j * STEP;
-            const bool ok = px < u.W && py < u.yEnd;
-            cc[ k ].gradDepth = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
-            cc[ k ].histLen   = ldIf< uint2 >( a.histLen, px, py, ok, make_uint2( 0u, 0u ) );
-            if( !ITER0 ) cc[ k ].sigma = ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
-            if( LAST )
-            {
-                const int sepx = u.W / 2, isOdd = px >= sepx ? 1 : 0;
-                const int regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
-                cc[ k ].albedo   = ldIf< uint32_t >( a.albedo, regX, py, ok, 0u );
-                cc[ k ].tp       = ldIf< uint2 >( a.throughput, px, py, ok, make_uint2( 0u, 0u ) );
-                cc[ k ].sky      = ldIf< uint8_t >( a.isSky, px, py, ok, ( uint8_t )0 );
-                cc[ k ].metRough = ldIf< uint16_t >( a.metRough, px, py, ok, ( uint16_t )0 );
-            }
-        }
-#pragma unroll
-        for( int it = 0; it < NIT; it++ )
-        {
-            const int  e = threadIdx.x + it * kAtThreads;
-            const int  r = e / TW, c = e - r * TW;
-            const int  gx = xBase - STEP + c, gy = yBase + ( r - 1 ) * STEP;
-            const bool ok = e < NPX && rows.in( gx, gy );
-            raw[ it ].n  = ldIf< uint32_t >( a.normal, gx, gy, ok, 0u );
-            raw[ it ].depth = ldIf< uint16_t >( a.depth, gx, gy, ok, ( uint16_t )0 );
-            raw[ it ].mr    = ldIf< uint16_t >( a.metRough, gx, gy, ok, ( uint16_t )0 );
-            raw[ it ].d  = ldIf< uint2 >( a.srcDiff, gx, gy, ok, make_uint2( 0u, 0u ) );
-            raw[ it ].s  = ldIf< uint32_t >( a.srcSpec, gx, gy, ok, 0u );
-            raw[ it ].i  = ldIf< uint32_t >( a.srcIndir, gx, gy, ok, 0u );
-        }
-    };
-    // unpack every tile pixel once into the four float4 planes
-    auto commit = [ & ]()
-    {
-#pragma unroll
-        for( int it = 0; it < NIT; it++ )
-        {
-            const int e = threadIdx.x + it * kAtThreads;
-            if( e >= NPX ) break;
-            const float3 n  = decodeNormal( a.lut, raw[ it ].n );
-            const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &raw[ it ].d.x ) );
-            const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &raw[ it ].d.y ) );
-            const float3 sp = decodeE5( raw[ it ].s ), in = decodeE5( raw[ it ].i );
-            sA[ e ] = make_float4( n.x, n.y, n.z, h2f( raw[ it ].depth ) );
-            sB[ e ] = make_float4( rg.x, rg.y, bv.x, bv.y );
-            sC[ e ] = make_float4( sp.x, sp.y, sp.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
-            sD[ e ] = make_float4( in.x, in.y, in.z, unorm8ToFloatFast( ( uint32_t )raw[ it ].mr >> 8 ) );
-        }
-    };
-
-    issue( xFirst, cen );
-  for( int t = 0; t < nTilesCta; t++ )
-  {
-    const int xBase = xFirst + t * kAtTileW;
-    if( xBase >= u.W ) break;
-    if( kAtMultiTile && t > 0 )
-    {
-        __syncthreads(); // every warp is done reading the previous tile
-#pragma unroll
-        for( int k = 0; k < PIX; k++ ) cen[ k ] = cenNext[ kAtMultiTile ? k : 0 ];
+        const int  p  = threadIdx.x + k * kAtThreads;
+        const int  j  = p / kAtTileW, c = p - j * kAtTileW;
+        const int  px = xBase + c, py = yBase + j * STEP;
+        const bool ok = px < u.W && py < u.yEnd;
+        cGrad[ k ]    = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
+        cSpecLen[ k ] = ok ? __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.histLen, px, py ) ) + 2 ) : ( uint16_t )0; // .b of rgba16f
+        cSigma[ k ]   = ITER0 ? ( uint16_t )0 : ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
     }
-    commit();
+
+    // ---- stage the tile: four consecutive texels per thread ----
+#pragma unroll
+    for( int g0 = 0; g0 < NGRP; g0 += kAtThreads )
+    {
+        const int g = g0 + threadIdx.x;
+        if( NGRP % kAtThreads != 0 && g >= NGRP ) break;
+        const int  r = g / GROUPS, cg = g - r * GROUPS;
+        const int  gx = xBase - HALO + 4 * cg, gy = yBase + ( r - 1 ) * STEP;
+        const bool rowOk = gy >= rows.y0 && gy < rows.y1;
+        const bool ok01 = rowOk && gx >= 0 && gx < u.W, ok23 = rowOk && gx >= 0 && gx + 2 < u.W; // gx is a multiple of 4, W is even
+        float4 ga[ 4 ];
+        uint4  d01, d23, sp, in;
+        {
+            const float4* pg = at< float4 >( a.guide, gx, gy );
+            const float4  z4 = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+            ga[ 0 ] = ok01 ? __ldg( pg ) : z4;
+            ga[ 1 ] = ok01 ? __ldg( pg + 1 ) : z4;
+            ga[ 2 ] = ok23 ? __ldg( pg + 2 ) : z4;
+            ga[ 3 ] = ok23 ? __ldg( pg + 3 ) : z4;
+            const uint4 z = make_uint4( 0u, 0u, 0u, 0u );
+            const uint4* pd = reinterpret_cast< const uint4* >( at< uint2 >( a.srcDiff, gx, gy ) );
+            d01 = ok01 ? __ldg( pd ) : z;
+            d23 = ok23 ? __ldg( pd + 1 ) : z;
+            sp  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcSpec, gx, gy ) ) ) : z;
+            in  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcIndir, gx, gy ) ) ) : z;
+        }
+        const int      e0 = r * TW + 4 * cg;
+        const uint32_t dd[ 8 ] = { d01.x, d01.y, d01.z, d01.w, d23.x, d23.y, d23.z, d23.w };
+        const uint32_t ss[ 4 ] = { sp.x, sp.y, sp.z, sp.w }, ii[ 4 ] = { in.x, in.y, in.z, in.w };
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k ] ) );
+            const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k + 1 ] ) );
+            const float3 s3 = decodeE5( ss[ k ] ), i3 = decodeE5( ii[ k ] );
+            sA[ e0 + k ] = make_float4( ga[ k ].x, ga[ k ].y, ga[ k ].z, guideDepth( ga[ k ].w ) );
+            sB[ e0 + k ] = make_float4( rg.x, rg.y, bv.x, bv.y );
+            sC[ e0 + k ] = make_float4( s3.x, s3.y, s3.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
+            sD[ e0 + k ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ k ].w ) );
+        }
+    }
     __syncthreads();
-    if constexpr( kAtMultiTile )
-    {
-        if( t + 1 < nTilesCta && xBase + kAtTileW < u.W ) issue( xBase + kAtTileW, cenNext ); // in flight during the arithmetic below
-    }
 
     const int       sep   = u.W / 2;
     constexpr float LOG2E = 1.4426950408889634f;
     const float     NINF  = __uint_as_float( 0xff800000u );
+    const float     TINY  = __uint_as_float( 0x00800000u ); // 2^-126: lg2 = -126, so P * L stays finite when P = 0
+
+    // every tap of every pixel of this tile inside its render area (ShaderCommonGLSLFunc.h:345-366)?  Uniform per CTA.
+    const bool tileInterior = ( xBase >= sep ? xBase - STEP >= sep : xBase + kAtTileW + STEP <= sep ) && xBase - STEP >= 0 && xBase + kAtTileW + STEP <= u.W &&
+                              yBase - STEP >= 0 && yBase + kAtTileH * STEP < u.H;
 
 #pragma unroll
     for( int k = 0; k < PIX; k++ )
@@ -196,13 +207,14 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         const int px = xBase + c, py = yBase + j * STEP;
         if( px >= u.W || py >= u.yEnd ) continue;
 
-        const int    ce = ( j + 1 ) * TW + ( c + STEP );
+        const int    ce = ( j + 1 ) * TW + ( c + HALO );
         const float4 cA = sA[ ce ], cB = sB[ ce ], cC = sC[ ce ], cD = sD[ ce ];
         float3 outDiff = make_float3( cB.x, cB.y, cB.z ), outSpec = make_float3( cC.x, cC.y, cC.z ), outIndir = make_float3( cD.x, cD.y, cD.z );
         float  outVariance = cB.w;
 
         const float depth     = cA.w;
-        const float roughness = cD.w;
+        const float roughByte = cD.w;
+        const float roughness = roughByte * ( 1.0f / 255.0f );
         const bool  invalid   = depth < 0.0f || depth > 10000.0f;
 
         if( invalid )
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         }
         else
         {
-            const float gradDepth = h2f( cen[ k ].gradDepth );
+            const float gradDepth = h2f( cGrad[ k ] );
             const float l         = cC.w;
 
             float sigmaL;
@@ -233,13 +245,14 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             }
             else
             {
-                sigmaL = h2f( cen[ k ].sigma );
+                sigmaL = h2f( cSigma[ k ] );
             }
             const float kLum = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
 
+            // w_r = max(0, 1 - 10 |dr|) * wRough with r = byte / 255: the byte difference times wRough * 10/255
             const float wRoughMultiplier  = saturatef( fmaf( roughness, 30.0f, -( float )a.iteration ) );
-            const float wR10              = wRoughMultiplier * 10.0f;
-            const float historyLengthSpec = __low2float( *reinterpret_cast< const __half2* >( &cen[ k ].histLen.y ) );
+            const float wR10              = wRoughMultiplier * ( 10.0f / 255.0f );
+            const float historyLengthSpec = h2f( cSpecLen[ k ] );
             const float alpha             = roughness * roughness;
             float       P                 = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
             P                             = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
@@ -249,66 +262,60 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             const float rgd   = frcp( gradDepth );
             const float invK1 = SQRT_LOG2E * fminf( rgd, 100.0f ), invK2 = SQRT_LOG2E * fminf( 0.5f * rgd, 100.0f );
 
-            // taps outside the checkerboarded render area (ShaderCommonGLSLFunc.h:345-366: they never cross x = W/2 or
-            // leave the frame) get exponent -inf; interior pixels take the loop whose wavelet weights are immediates
-            const int  ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
-            const bool okL = px - STEP >= ax0, okR = px + STEP < ax1, okT = py - STEP >= 0, okB = py + STEP < u.H;
-            const float PINF = __uint_as_float( 0x7f800000u );
-
             float weightSum = 1.0f, weightSumSpec = 1.0f, weightSumIndir = 1.0f;
 
-            auto taps = [ & ]( auto interiorTag )
+            auto tap = [ & ]( const int qe, const float invK, const float lk )
             {
-                constexpr bool INTERIOR = decltype( interiorTag )::value;
+                const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
+                const float  nN = fmaxf( TINY, fmaf( cA.z, qA.z, fmaf( cA.y, qA.y, cA.x * qA.x ) ) );
+                const float  L  = flg2( nN );
+                const float  wZ = fabsf( depth - qA.w ) * invK;
+                const float  eN    = fmaf( 128.0f, L, lk );
+                const float  eBase = fmaf( -wZ, wZ, eN );
+                const float  eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
+                const float  wBase = fex2( eBase );
+                const float  wDiff = fex2( eDiff );
+                float        rfac; // max(0, 1 - 10|dr|) * wRough, both factors in [0,1]
+                asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( roughByte - qD.w ) ), "f"( -wR10 ), "f"( wRoughMultiplier ) );
+                const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
+
+                outDiff.x = fmaf( qB.x, wDiff, outDiff.x ); outDiff.y = fmaf( qB.y, wDiff, outDiff.y ); outDiff.z = fmaf( qB.z, wDiff, outDiff.z );
+                outSpec.x = fmaf( qC.x, wSpec, outSpec.x ); outSpec.y = fmaf( qC.y, wSpec, outSpec.y ); outSpec.z = fmaf( qC.z, wSpec, outSpec.z );
+                outIndir.x = fmaf( qD.x, wBase, outIndir.x ); outIndir.y = fmaf( qD.y, wBase, outIndir.y ); outIndir.z = fmaf( qD.z, wBase, outIndir.z );
+                weightSum += wDiff; weightSumSpec += wSpec; weightSumIndir += wBase;
+                // (var*w)*w.  A vanishing weight next to an infinite fp16 variance gives inf*0 = NaN here where the shader's exp() may
+                // still hold a denormal (inf): non-finite either way, and GLSL leaves the underflow of exp() to the implementation.
+                outVariance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, outVariance );
+            };
+
+            if( tileInterior )
+            {
 #pragma unroll
                 for( int yy = -1; yy <= 1; yy++ )
-                {
 #pragma unroll
                     for( int xx = -1; xx <= 1; xx++ )
                     {
                         if( xx == 0 && yy == 0 ) continue;
-                        const int    qe = ce + yy * TW + xx * STEP;
-                        const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
-
-                        const float nN = fmaxf( 0.0f, fmaf( cA.z, qA.z, fmaf( cA.y, qA.y, cA.x * qA.x ) ) );
-                        const float L  = fmaxf( flg2( nN ), -126.0f );
-                        const float wZ = fabsf( depth - qA.w ) * ( ( xx != 0 && yy != 0 ) ? invK2 : invK1 );
-                        float       lk = ( xx != 0 && yy != 0 ) ? -2.0f : -1.0f; // log2 of the wavelet weight
-                        if( !INTERIOR )
-                        {
-                            const bool in = ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true );
-                            lk            = in ? lk : NINF;
-                        }
-                        const float e0    = fmaf( 128.0f, L, lk );
-                        const float eBase = fmaf( -wZ, wZ, e0 );
-                        const float eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
-                        const float wBase = fex2( eBase );
-                        const float wDiff = fex2( eDiff );
-                        float       rfac; // max(0, 1 - 10|dr|) * wRough, both factors in [0,1]
-                        asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( roughness - qD.w ) ), "f"( -wR10 ), "f"( wRoughMultiplier ) );
-                        const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
-
-                        outDiff.x = fmaf( qB.x, wDiff, outDiff.x ); outDiff.y = fmaf( qB.y, wDiff, outDiff.y ); outDiff.z = fmaf( qB.z, wDiff, outDiff.z );
-                        outSpec.x = fmaf( qC.x, wSpec, outSpec.x ); outSpec.y = fmaf( qC.y, wSpec, outSpec.y ); outSpec.z = fmaf( qC.z, wSpec, outSpec.z );
-                        outIndir.x = fmaf( qD.x, wBase, outIndir.x ); outIndir.y = fmaf( qD.y, wBase, outIndir.y ); outIndir.z = fmaf( qD.z, wBase, outIndir.z );
-                        weightSum += wDiff; weightSumSpec += wSpec; weightSumIndir += wBase;
-                        // (var*w)*w: MUFU.EX2 flushes a denormal weight to zero where the shader's exp() keeps it, which only
-                        // shows when the tap's fp16 variance is +inf (inf*denormal = inf, inf*0 = NaN): only that case pays
-                        // for the denormal-preserving exponential
-                        if( qB.w == PINF )
-                        {
-                            const float wd = ex2ApproxDenorm( eDiff );
-                            outVariance    = fmaf( __fmul_rn( qB.w, wd ), wd, outVariance );
-                        }
-                        else
-                        {
-                            outVariance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, outVariance );
-                        }
+                        const bool diag = xx != 0 && yy != 0;
+                        tap( ce + yy * TW + xx * STEP, diag ? invK2 : invK1, diag ? -2.0f : -1.0f );
                     }
-                }
-            };
-            if( okL && okR && okT && okB ) taps( std::true_type{} );
-            else taps( std::false_type{} );
+            }
+            else
+            {
+                // taps outside the checkerboarded render area (they never cross x = W/2 or leave the frame) get exponent -inf
+                const int  ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+                const bool okL = px - STEP >= ax0, okR = px + STEP < ax1, okT = py - STEP >= 0, okB = py + STEP < u.H;
+#pragma unroll
+                for( int yy = -1; yy <= 1; yy++ )
+#pragma unroll
+                    for( int xx = -1; xx <= 1; xx++ )
+                    {
+                        if( xx == 0 && yy == 0 ) continue;
+                        const bool diag = xx != 0 && yy != 0;
+                        const bool in   = ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true );
+                        tap( ce + yy * TW + xx * STEP, diag ? invK2 : invK1, in ? ( diag ? -2.0f : -1.0f ) : NINF );
+                    }
+            }
             const float inv = frcp( weightSum ), invSpec = frcp( weightSumSpec ), invIndir = frcp( weightSumIndir );
             outDiff     = make_float3( outDiff.x * inv, outDiff.y * inv, outDiff.z * inv );
             outVariance = outVariance * ( inv * inv );
@@ -325,21 +332,25 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             continue;
         }
 
-        // composition, CmSVGFAtrous.comp:278-348
-        const int     isOdd = px >= sep ? 1 : 0;
-        const int     regX  = ( px - isOdd * sep ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
-        float3        albedo = unpackUfloat111110Fast( cen[ k ].albedo );
-        const uint2   tp     = cen[ k ].tp;
+        // composition, CmSVGFAtrous.comp:278-348 (the extra centre-only inputs are loaded here: one pixel at a time keeps the
+        // registers of the tap loop free)
+        const int      isOdd = px >= sep ? 1 : 0;
+        const int      regX  = ( px - isOdd * sep ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
+        const uint32_t albedoBits = __ldg( at< uint32_t >( a.albedo, regX, py ) );
+        const uint2    tp     = __ldg( at< uint2 >( a.throughput, px, py ) );
+        const uint32_t sky    = __ldg( at< uint8_t >( a.isSky, px, py ) );
+        const uint32_t metBits = __ldg( at< uint16_t >( a.metRough, px, py ) );
+        float3        albedo = unpackUfloat111110Fast( albedoBits );
         const float2  tp01   = __half22float2( *reinterpret_cast< const __half2* >( &tp.x ) );
         const float3  throughput = make_float3( tp01.x, tp01.y, __low2float( *reinterpret_cast< const __half2* >( &tp.y ) ) );
-        const uint32_t sky   = cen[ k ].sky;
         if( ( u.debugShowFlags & ( 1u << 9 ) ) != 0 ) albedo = make_float3( 1.0f, 1.0f, 1.0f );
 
         float3 illuminated;
         if( sky == 0u )
         {
-            const float metallic = unorm8ToFloatFast( ( uint32_t )cen[ k ].metRough & 0xffu );
-            const float t  = saturatef( ( roughness - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
+            const float metallic = unorm8ToFloatFast( metBits & 0xffu );
+            const float rough    = unorm8ToFloatFast( metBits >> 8 );
+            const float t  = saturatef( ( rough - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
             const float sm = t * t * ( 3.0f - 2.0f * t );
             const float3 specular = fmix3( outSpec, outIndir, sm );
             const float3 roS = fmix3( make_float3( 0.04f, 0.04f, 0.04f ), albedo, metallic ); // BRDF.h:49-53
@@ -363,9 +374,6 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         *atW< uint32_t >( a.preFinal, regX, py ) =
             packUfloat111110Fast( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) );
     }
-  } // tiles of this CTA
 }
-
-constexpr size_t atrousTiledSmemBytes( int step ) { return ( size_t )( kAtTileW + 2 * step ) * ( kAtTileH + 2 ) * kAtBytesPerTilePixel; }
 
 } // namespace asvgf

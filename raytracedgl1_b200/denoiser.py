@@ -21,6 +21,7 @@ SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND = ran
 CREATE_EXPORT_DEBUG_MASK = 1 << 0
 CREATE_EXTERNAL_IMAGES = 1 << 1
 CREATE_LITERAL_KERNELS = 1 << 2
+CREATE_EAGER_GRADIENT_ATROUS = 1 << 4
 CREATE_BAND_APRON = 1 << 3
 
 EXPORTED_SYMBOLS = [

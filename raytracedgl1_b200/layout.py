@@ -92,6 +92,7 @@ PASS_ANTIFIREFLY = 6
 PASS_VARIANCE = 7
 PASS_ATROUS_0 = 8
 PASS_GRADIENT_ATROUS_ALL = 100  # the four gradient a-trous dispatches in one call
+PASS_GUIDE = 101                # decoded geometry plane of the frame (not a reference dispatch)
 
 
 def image_extent(name_or_index, width, height):
