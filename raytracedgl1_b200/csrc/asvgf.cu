@@ -6,6 +6,7 @@
 #include "../../include/asvgf.h"
 
 #include "asvgf_fast.cuh"
+#include "asvgf_temporal.cuh"
 #include "asvgf_atrous_tiled.cuh"
 #include "asvgf_post.cuh"
 #ifdef ASVGF_WITH_LITERAL // expression-by-expression kernels for A/B numerics; not part of the release build
@@ -216,6 +217,9 @@ Uniform makeUniform( const AsvgfDenoiser_T& d, const AsvgfGlobalUniform& g )
         u.specMinFrames = std::fmin( std::fmax( 0.2f * rcp, 0.0f ), 128.0f );
     }
     for( int i = 0; i < 3; i++ ) u.cameraDelta[ i ] = g.cameraPositionPrev[ i ] - g.cameraPosition[ i ];
+    u.projSparse = 1;
+    for( int i : { 1, 2, 3, 4, 6, 7, 12, 13, 15 } )
+        if( g.projection[ i ] != 0.0f || g.projectionPrev[ i ] != 0.0f ) u.projSparse = 0;
     return u;
 }
 
@@ -301,8 +305,15 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.outIndirAccum = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi ); a.outMask = d.get( ASVGF_IMAGE_DEBUG_MASK, fi );
     a.lut = d.lut;
     a.writeMask = ( ( d.info.flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) && a.outMask.p ) ? 1 : 0;
-    ASVGF_LITERAL_OR( d, ( k_temporal<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_temporal_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
+    // one texel offset serves every image when they all hold the same number of texels per row (the library's own allocation)
+    bool uniformPitch = true;
+    for( const Img* im : { &a.unfDirect, &a.unfIndir, &a.unfSpec, &a.viewDir, &a.motion, &a.depth, &a.normal, &a.metRough, &a.surfPos, &a.depthPrev, &a.normalPrev,
+                           &a.diffHistory, &a.momentsPrev, &a.histLenPrev, &a.specPrev, &a.indirPrev, &a.surfPosPrev, &a.outDiffTemporary, &a.outMoments, &a.outHistLen,
+                           &a.outSpecAccum, &a.outIndirAccum } )
+        uniformPitch = uniformPitch && im->pitchT == a.depth.pitchT;
+    const dim3 grid = gridFor( ( int )d.W, u.yEnd - u.yBegin );
+    ASVGF_LITERAL_OR( d, ( k_temporal<<< grid, kBlock, 0, s >>>( a, u ) ),
+                      ( uniformPitch ? k_temporal_fast< true ><<< grid, kBlock, 0, s >>>( a, u ) : k_temporal_fast< false ><<< grid, kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_temporal" );
 }
 
@@ -697,7 +708,9 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
         im.w = ( int32_t )w; im.h = ( int32_t )h;
         im.row0 = desc.thirdRes ? d->grow0 : d->row0;
         im.rows = desc.thirdRes ? d->grows : d->rows;
-        setImgStorage( im, nullptr, ( w * desc.bpp + 255u ) & ~255u, desc.bpp );
+        // every image of one resolution holds the same number of texels per row, align256(width): the pitch is a multiple of 256 B for
+        // every texel size, and kernels that touch many images at one pixel compute a single texel offset (asvgf_temporal.cuh)
+        setImgStorage( im, nullptr, ( ( w + 255u ) & ~255u ) * desc.bpp, desc.bpp );
         if( pInfo->flags & ASVGF_CREATE_EXTERNAL_IMAGES ) continue;
         if( i == ASVGF_IMAGE_DEBUG_MASK && !( pInfo->flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) ) continue;
         const size_t bytes = ( size_t )im.pitch * ( size_t )im.rows;
@@ -720,7 +733,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     {
         Img& g = d->guide;
         g.w = ( int32_t )d->W; g.h = ( int32_t )d->H; g.row0 = d->row0; g.rows = d->rows;
-        const uint32_t pitch = ( d->W * 16u + 255u ) & ~255u;
+        const uint32_t pitch = ( ( d->W + 255u ) & ~255u ) * 16u;
         uint8_t*       mem   = nullptr;
         cudaError_t    e     = cudaMalloc( ( void** )&mem, ( size_t )pitch * ( size_t )g.rows );
         if( e == cudaSuccess ) e = cudaMemset( mem, 0, ( size_t )pitch * ( size_t )g.rows );

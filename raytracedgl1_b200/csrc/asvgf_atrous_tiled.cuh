@@ -12,7 +12,8 @@
 //    residues go to s different CTAs); halo = one dilated row above/below, max(s,4) columns left/right.  Read amplification
 //    1.4-1.56 at every stride, every global access a full-line row segment.
 //  * VECTOR STAGING.  A thread stages four consecutive texels: 4+2+1+1 16-byte loads, one address computation per image,
-//    decode, 16 STS.128.  No per-texel index arithmetic, no table gathers.
+//    decode, 16 STS.128 into quarter-row slots (conflict-free for the staging stores and for the tap loads, see below).
+//    No per-texel index arithmetic, no table gathers.
 //  * WEIGHTS THROUGH ONE LOG.  w_n = (n.n')^128 and the specular lobe (n.n')^P share L = lg2(n.n'); the wavelet weight and the
 //    render-area test are folded into the exponent (lk = log2 k, or -inf outside):
 //      wBase = ex2(128 L + lk - wz^2 log2e),  wDiff = ex2(128 L + lk - (wz^2 + wl) log2e),  wSpec = r * ex2(. + P L)
@@ -34,7 +35,14 @@ constexpr int kAtThreads = 256; // 2 pixels per thread
 #endif
 
 constexpr int    atrousHalo( int step ) { return step < 4 ? 4 : step; } // halo columns: multiples of 4 keep 16-byte row segments
-constexpr size_t atrousTiledSmemBytes( int step ) { return ( size_t )( kAtTileW + 2 * atrousHalo( step ) ) * ( kAtTileH + 2 ) * 64; }
+// Shared-memory layout of one staged row: QUARTER-ROW SLOTS.  Column c lives in slot (c & 3) * GP + (c >> 2).  The staging thread
+// that holds columns 4g..4g+3 stores them to slots g, GP + g, 2 GP + g, 3 GP + g: consecutive lanes hit consecutive slots, and
+// a quarter warp of the tap loop (eight consecutive columns) hits slots {0, GP, 2GP, 3GP, 1, GP+1, ...} + const, which are
+// distinct modulo 8 (= distinct 16-byte bank groups) when GP = 2 or 6 (mod 8).  Both sides of the tile are conflict-free.
+// (Storing four consecutive texels per lane into a plain row layout was measured: 4-way conflicts on every STS.128, 18 M
+// conflict cycles per launch, the kernel 25 % slower in spite of 23 % fewer instructions.)
+constexpr int    atrousGroupPitch( int step ) { int g = ( kAtTileW + 2 * atrousHalo( step ) ) / 4; while( g % 8 != 2 && g % 8 != 6 ) g++; return g; }
+constexpr size_t atrousTiledSmemBytes( int step ) { return ( size_t )( 4 * atrousGroupPitch( step ) ) * ( kAtTileH + 2 ) * 64; }
 
 ASVGF_DEVICE float ex2Approx( float x ) { return fex2( x ); }
 
@@ -118,9 +126,11 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
     constexpr int HALO   = atrousHalo( STEP );
     constexpr int TW     = kAtTileW + 2 * HALO; // staged columns
     constexpr int TROWS  = kAtTileH + 2;
-    constexpr int NPX    = TW * TROWS;
     constexpr int GROUPS = TW / 4;              // 4-texel groups per staged row
     constexpr int NGRP   = GROUPS * TROWS;
+    constexpr int GP     = atrousGroupPitch( STEP ); // slots per quarter row
+    constexpr int RP     = 4 * GP;                   // slots per staged row
+    constexpr int NPX    = RP * TROWS;
     constexpr int PIX    = ( kAtTileW * kAtTileH ) / kAtThreads;
     float4* sA = reinterpret_cast< float4* >( smemRaw ); // normal.xyz, depth
     float4* sB = sA + NPX;                               // diffuse rgb, variance
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             sp  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcSpec, gx, gy ) ) ) : z;
             in  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcIndir, gx, gy ) ) ) : z;
         }
-        const int      e0 = r * TW + 4 * cg;
+        const int      e0 = r * RP + cg; // texel k of the group -> quarter row k
         const uint32_t dd[ 8 ] = { d01.x, d01.y, d01.z, d01.w, d23.x, d23.y, d23.z, d23.w };
         const uint32_t ss[ 4 ] = { sp.x, sp.y, sp.z, sp.w }, ii[ 4 ] = { in.x, in.y, in.z, in.w };
 #pragma unroll
@@ -182,10 +192,10 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
             const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k ] ) );
             const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k + 1 ] ) );
             const float3 s3 = decodeE5( ss[ k ] ), i3 = decodeE5( ii[ k ] );
-            sA[ e0 + k ] = make_float4( ga[ k ].x, ga[ k ].y, ga[ k ].z, guideDepth( ga[ k ].w ) );
-            sB[ e0 + k ] = make_float4( rg.x, rg.y, bv.x, bv.y );
-            sC[ e0 + k ] = make_float4( s3.x, s3.y, s3.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
-            sD[ e0 + k ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ k ].w ) );
+            sA[ e0 + k * GP ] = make_float4( ga[ k ].x, ga[ k ].y, ga[ k ].z, guideDepth( ga[ k ].w ) );
+            sB[ e0 + k * GP ] = make_float4( rg.x, rg.y, bv.x, bv.y );
+            sC[ e0 + k * GP ] = make_float4( s3.x, s3.y, s3.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
+            sD[ e0 + k * GP ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ k ].w ) );
         }
     }
     __syncthreads();
@@ -207,7 +217,10 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
         const int px = xBase + c, py = yBase + j * STEP;
         if( px >= u.W || py >= u.yEnd ) continue;
 
-        const int    ce = ( j + 1 ) * TW + ( c + HALO );
+        // slots of the three tap columns c - STEP, c, c + STEP of staged row j + 1 (for STEP >= 4 they differ by STEP / 4)
+        auto slotOf = [ & ]( int col ) { return ( j + 1 ) * RP + ( col & 3 ) * GP + ( col >> 2 ); };
+        const int    ce = slotOf( c + HALO );
+        const int    dL = STEP >= 4 ? -( STEP / 4 ) : slotOf( c + HALO - STEP ) - ce, dR = STEP >= 4 ? STEP / 4 : slotOf( c + HALO + STEP ) - ce;
         const float4 cA = sA[ ce ], cB = sB[ ce ], cC = sC[ ce ], cD = sD[ ce ];
         float3 outDiff = make_float3( cB.x, cB.y, cB.z ), outSpec = make_float3( cC.x, cC.y, cC.z ), outIndir = make_float3( cD.x, cD.y, cD.z );
         float  outVariance = cB.w;
@@ -238,7 +251,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
                 for( int yy = -1; yy <= 1; yy++ )
 #pragma unroll
                     for( int xx = -1; xx <= 1; xx++ )
-                        r = fmaf( sB[ ce + yy * TW + xx ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+                        r = fmaf( sB[ ce + yy * RP + ( xx < 0 ? dL : xx > 0 ? dR : 0 ) ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
                 r      = __fsqrt_rn( fmaxf( r, 0.0f ) );
                 *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( r );
                 sigmaL = r;
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
                     {
                         if( xx == 0 && yy == 0 ) continue;
                         const bool diag = xx != 0 && yy != 0;
-                        tap( ce + yy * TW + xx * STEP, diag ? invK2 : invK1, diag ? -2.0f : -1.0f );
+                        tap( ce + yy * RP + ( xx < 0 ? dL : xx > 0 ? dR : 0 ), diag ? invK2 : invK1, diag ? -2.0f : -1.0f );
                     }
             }
             else
@@ -313,7 +326,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
                         if( xx == 0 && yy == 0 ) continue;
                         const bool diag = xx != 0 && yy != 0;
                         const bool in   = ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true );
-                        tap( ce + yy * TW + xx * STEP, diag ? invK2 : invK1, in ? ( diag ? -2.0f : -1.0f ) : NINF );
+                        tap( ce + yy * RP + ( xx < 0 ? dL : xx > 0 ? dR : 0 ), diag ? invK2 : invK1, in ? ( diag ? -2.0f : -1.0f ) : NINF );
                     }
             }
             const float inv = frcp( weightSum ), invSpec = frcp( weightSumSpec ), invIndir = frcp( weightSumIndir );

@@ -56,6 +56,7 @@ struct Uniform // the members of ShGlobalUniform the path reads (ShaderCommonC.h
     float    halfW, invHalfW, invH; // renderWidth/2, 1/(renderWidth/2), 1/renderHeight  (ShaderCommonGLSLFunc.h:271-277)
     float    specMinFrames;         // clamp(0.2/timeDelta, 0, 128)                       (CmSVGFTemporalAccumulation.comp:70-74)
     float    cameraDelta[ 3 ];      // cameraPositionPrev - cameraPosition                 (:60)
+    int32_t  projSparse;            // projection and projectionPrev are zero outside m0, m5, m8..m11, m14 (Matrix.cpp:380-395)
 };
 
 struct NormalLut // (sin, cos) of phi_j = j*pi/65535 and theta_k = k*2*pi/65536, correctly rounded fp32

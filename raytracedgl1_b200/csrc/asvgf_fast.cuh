@@ -13,7 +13,7 @@
 //
 //   k_gradient_samples_fast ....... RtGradients.rgen:44-181 (image-space part)
 //   k_gradient_atrous_fast ........ CmASVGFGradientAtrous.comp:42-105
-//   k_temporal_fast ............... CmSVGFTemporalAccumulation.comp:58-385
+//   k_temporal_fast ............... CmSVGFTemporalAccumulation.comp:58-385   (asvgf_temporal.cuh)
 //   k_antifirefly_fast ............ CmAntiFirefly.comp:47-159
 //   k_variance_fast ............... CmSVGFEstimateVariance.comp:74-205
 #pragma once
@@ -253,62 +253,8 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_atrous_fast( co
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// T: temporal accumulation
+// T: temporal accumulation -- the kernel lives in asvgf_temporal.cuh; shared colour helper:
 // ------------------------------------------------------------------------------------------------------------
-ASVGF_DEVICE float3 decodeNormalExact( const NormalLut& lut, uint32_t p ) { return decodeNormal( lut, p ); }
-
-struct TapTest
-{
-    bool  ok[ 4 ];
-};
-
-// the 2x2 consistency gather of CmSVGFTemporalAccumulation.comp:149-162 / :258-270 (exact)
-// encN = the centre pixel's packed normal: a tap whose packed normal has the same bits decodes to the same vector, and
-// dot(n, n) of a decoded (unit) normal is 1 up to rounding, i.e. > 0.95 -- so when all four taps match (flat surfaces,
-// most pixels) the eight sin/cos table gathers and the dot products are skipped; the result is identical by construction.
-ASVGF_DEVICE uint32_t consistencyBits( const TemporalArgs& a, const Rows& rows, int bx, int by, int ax0, int ax1, int H, float depth, float motionZ, float3 normal,
-                                       uint32_t encN )
-{
-    uint32_t dz[ 4 ], en[ 4 ];
-    bool     in[ 4 ];
-#pragma unroll
-    for( int t = 0; t < 4; t++ )
-    {
-        const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
-        in[ t ] = y >= 0 && y < H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
-        dz[ t ] = ldIf< uint16_t >( a.depthPrev, x, y, in[ t ], ( uint16_t )0 );
-        en[ t ] = ldIf< uint32_t >( a.normalPrev, x, y, in[ t ], encN ); // taps outside never count: let them match
-    }
-    uint32_t    nOk = 15u;
-    if( ( en[ 0 ] != encN ) | ( en[ 1 ] != encN ) | ( en[ 2 ] != encN ) | ( en[ 3 ] != encN ) )
-    {
-        float2 sp[ 4 ], st[ 4 ];
-#pragma unroll
-        for( int t = 0; t < 4; t++ )
-        {
-            sp[ t ] = __ldg( a.lut.phi + ( en[ t ] >> 16 ) );
-            st[ t ] = __ldg( a.lut.theta + ( en[ t ] & 0xffffu ) );
-        }
-        nOk = 0u;
-#pragma unroll
-        for( int t = 0; t < 4; t++ )
-        {
-            const float3 nPrev = make_float3( mulr( sp[ t ].x, st[ t ].y ), mulr( sp[ t ].x, st[ t ].x ), sp[ t ].y );
-            nOk |= dot3r( normal, nPrev ) > 0.95f ? ( 1u << t ) : 0u;
-        }
-    }
-    uint32_t bits = 0;
-    const float az = fabsf( depth );
-#pragma unroll
-    for( int t = 0; t < 4; t++ )
-    {
-        const float num = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
-        const bool  ok  = in[ t ] && ( ( nOk >> t ) & 1u ) && quotientBelowTenth( num, az );
-        bits |= ok ? ( 1u << t ) : 0u;
-    }
-    return bits;
-}
-
 ASVGF_DEVICE float specAccumSpeedFast( float minFrames, float Amax, float roughness, float powA, float parallax ) // :80-92, powA = pow(sat(1-NoV), 0.66)
 {
     const float b                   = fmaf( roughness, roughness, 1.1f );
@@ -317,261 +263,6 @@ ASVGF_DEVICE float specAccumSpeedFast( float minFrames, float Amax, float roughn
     float       f                   = 1.0f - fex2( -200.0f * roughness * roughness );
     f *= fpow( saturatef( roughness ), 0.5f * powerScale );
     return clampf( 256.0f * f, minFrames, Amax );
-}
-
-#ifndef ASVGF_T_EAGER_HISTORY
-    #define ASVGF_T_EAGER_HISTORY 0
-#endif
-#ifndef ASVGF_T_MIN_CTAS
-    #define ASVGF_T_MIN_CTAS 4 // 64 registers (100 B of spills): measured 0.485 ms vs 0.523 (3 CTAs, 80 regs) vs 0.602 (2 CTAs)
-#endif
-__global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_temporal_fast( const __grid_constant__ TemporalArgs a, const __grid_constant__ Uniform u )
-{
-    const int px = blockIdx.x * kBlockW + threadIdx.x;
-    const int py = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
-    if( px >= u.W || py >= u.yEnd ) return;
-    const Rows rows = rowsOf( a.depth );
-
-    // ---- current pixel: all loads up front ----
-    const uint32_t eD = __ldg( at< uint32_t >( a.unfDirect, px, py ) );
-    const uint32_t eI = __ldg( at< uint32_t >( a.unfIndir, px, py ) );
-    const uint32_t eS = __ldg( at< uint32_t >( a.unfSpec, px, py ) );
-    const uint2    rv = __ldg( at< uint2 >( a.viewDir, px, py ) );
-    const uint2    mv = __ldg( at< uint2 >( a.motion, px, py ) );
-    const uint16_t dv = __ldg( at< uint16_t >( a.depth, px, py ) );
-    const uint32_t nv32 = __ldg( at< uint32_t >( a.normal, px, py ) );
-    const uint16_t mr = __ldg( at< uint16_t >( a.metRough, px, py ) );
-    const float4   sp4 = __ldg( at< float4 >( a.surfPos, px, py ) );
-    const uint32_t gr = __ldg( at< uint32_t >( a.disPing, px / 3, py / 3 ) );
-
-    const float3 unfilteredDiff = decodeE5( eD ), unfilteredIndir = decodeE5( eI ), unfilteredSpec = decodeE5( eS );
-    const float2 ray01 = __half22float2( *reinterpret_cast< const __half2* >( &rv.x ) );
-    const float2 ray23 = __half22float2( *reinterpret_cast< const __half2* >( &rv.y ) );
-    const float3 rayDir = make_float3( ray01.x, ray01.y, ray23.x );
-    const float  rayHit = ray23.y;
-    const float2 mot01 = __half22float2( *reinterpret_cast< const __half2* >( &mv.x ) );
-    const float  motionZ = __low2float( *reinterpret_cast< const __half2* >( &mv.y ) );
-    const float  depth = h2f( dv );
-    const float3 normal = decodeNormal( a.lut, nv32 );
-    const float  roughness = unorm8ToFloatFast( ( uint32_t )mr >> 8 );
-
-    const int sep = u.W / 2, ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
-
-    const float l  = luminance( unfilteredDiff );
-    const float l2 = mulr( l, l );
-
-    // ---- reprojection (exact) ----
-    int   pixPrevX, pixPrevY;
-    float subX, subY;
-    {
-        const float ppx = mulr( addr( mulr( addr( ( float )px, 0.5f ), u.invHalfW ), mot01.x ), u.halfW );
-        const float ppy = mulr( addr( mulr( addr( ( float )py, 0.5f ), u.invH ), mot01.y ), u.renderHeight );
-        const float qx = subr( ppx, 0.5f ), qy = subr( ppy, 0.5f );
-        const float fx = floorf( qx ), fy = floorf( qy );
-        pixPrevX = f2i( fx ); pixPrevY = f2i( fy );
-        subX = subr( qx, fx ); subY = subr( qy, fy );
-    }
-    const float bw[ 4 ] = { mulr( subr( 1.0f, subX ), subr( 1.0f, subY ) ), mulr( subX, subr( 1.0f, subY ) ),
-                            mulr( subr( 1.0f, subX ), subY ), mulr( subX, subY ) };
-
-    // ---- history fetches ----
-    uint2    hDiff[ 4 ], hLen[ 4 ];
-    uint32_t hMom[ 4 ], hSpec[ 4 ], hInd[ 4 ];
-#if ASVGF_T_EAGER_HISTORY
-    // issued for every tap inside the render area BEFORE the consistency tests: one serial memory round trip less
-    // (the tests need depth/normal of the same texels, then the sin/cos table); inconsistent taps are loaded in vain
-#pragma unroll
-    for( int t = 0; t < 4; t++ )
-    {
-        const int  x = pixPrevX + ( t & 1 ), y = pixPrevY + ( t >> 1 );
-        const bool ok = y >= 0 && y < u.H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
-        hDiff[ t ] = ldIf< uint2 >( a.diffHistory, x, y, ok, make_uint2( 0u, 0u ) );
-        hMom[ t ]  = ldIf< uint32_t >( a.momentsPrev, x, y, ok, 0u );
-        hLen[ t ]  = ldIf< uint2 >( a.histLenPrev, x, y, ok, make_uint2( 0u, 0u ) );
-        hSpec[ t ] = ldIf< uint32_t >( a.specPrev, x, y, ok, 0u );
-        hInd[ t ]  = ldIf< uint32_t >( a.indirPrev, x, y, ok, 0u );
-    }
-    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal, nv32 );
-#else
-    uint32_t mask = consistencyBits( a, rows, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal, nv32 );
-    // of the consistent taps only (all in flight together)
-#pragma unroll
-    for( int t = 0; t < 4; t++ )
-    {
-        const int  x = pixPrevX + ( t & 1 ), y = pixPrevY + ( t >> 1 );
-        const bool ok = ( mask >> t ) & 1u;
-        hDiff[ t ] = ldIf< uint2 >( a.diffHistory, x, y, ok, make_uint2( 0u, 0u ) );
-        hMom[ t ]  = ldIf< uint32_t >( a.momentsPrev, x, y, ok, 0u );
-        hLen[ t ]  = ldIf< uint2 >( a.histLenPrev, x, y, ok, make_uint2( 0u, 0u ) );
-        hSpec[ t ] = ldIf< uint32_t >( a.specPrev, x, y, ok, 0u );
-        hInd[ t ]  = ldIf< uint32_t >( a.indirPrev, x, y, ok, 0u );
-    }
-#endif
-    const bool   sppOk = rows.in( pixPrevX, pixPrevY );
-    const float4 spp4  = ldIf< float4 >( a.surfPosPrev, pixPrevX, pixPrevY, sppOk, make_float4( 0.0f, 0.0f, 0.0f, 0.0f ) );
-
-    float4 historyLengthDIS = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-    float3 diffPrev = make_float3( 0.0f, 0.0f, 0.0f ), specPrevOnSurf = diffPrev, indirPrev = diffPrev;
-    float2 momentsPrev = make_float2( 0.0f, 0.0f );
-    float  weightSum   = 0.0f;
-#pragma unroll
-    for( int t = 0; t < 4; t++ )
-    {
-        if( !( ( mask >> t ) & 1u ) ) continue;
-        const float  w  = bw[ t ];
-        const float2 d01 = __half22float2( *reinterpret_cast< const __half2* >( &hDiff[ t ].x ) );
-        const float  d2  = __low2float( *reinterpret_cast< const __half2* >( &hDiff[ t ].y ) );
-        diffPrev.x = fmaf( d01.x, w, diffPrev.x ); diffPrev.y = fmaf( d01.y, w, diffPrev.y ); diffPrev.z = fmaf( d2, w, diffPrev.z );
-        const float2 mp = __half22float2( *reinterpret_cast< const __half2* >( &hMom[ t ] ) );
-        momentsPrev.x = fmaf( mp.x, w, momentsPrev.x ); momentsPrev.y = fmaf( mp.y, w, momentsPrev.y );
-        const float2 h01 = __half22float2( *reinterpret_cast< const __half2* >( &hLen[ t ].x ) );
-        const float2 h23 = __half22float2( *reinterpret_cast< const __half2* >( &hLen[ t ].y ) );
-        historyLengthDIS.x = fmaf( h01.x, w, historyLengthDIS.x ); historyLengthDIS.y = fmaf( h01.y, w, historyLengthDIS.y );
-        historyLengthDIS.z = fmaf( h23.x, w, historyLengthDIS.z ); historyLengthDIS.w = fmaf( h23.y, w, historyLengthDIS.w );
-        const float3 sc = decodeE5( hSpec[ t ] ), ic = decodeE5( hInd[ t ] );
-        specPrevOnSurf.x = fmaf( sc.x, w, specPrevOnSurf.x ); specPrevOnSurf.y = fmaf( sc.y, w, specPrevOnSurf.y ); specPrevOnSurf.z = fmaf( sc.z, w, specPrevOnSurf.z );
-        indirPrev.x = fmaf( ic.x, w, indirPrev.x ); indirPrev.y = fmaf( ic.y, w, indirPrev.y ); indirPrev.z = fmaf( ic.z, w, indirPrev.z );
-        weightSum = addr( weightSum, w ); // exact order: decides the weightSum > 1e-4 bit
-    }
-
-    const float antilagAlphaDiff  = unorm8ToFloatFast( gr & 0xffu );
-    const float antilagAlphaIndir = unorm8ToFloatFast( ( gr >> 8 ) & 0xffu );
-    const float antilagAlphaSpec  = unorm8ToFloatFast( ( gr >> 16 ) & 0xffu );
-
-    float3 specColorAccum, diffColorAccum, indirAccum;
-    float2 diffMomentsAccum;
-    float  specHistoryLengthAccum, specHitDistanceAccum, diffHistoryLengthAccum, indirHistoryLengthAccum;
-
-    if( weightSum > 0.0001f )
-    {
-        mask |= 1u << 4;
-        const float inv = frcp( weightSum );
-        specPrevOnSurf = make_float3( specPrevOnSurf.x * inv, specPrevOnSurf.y * inv, specPrevOnSurf.z * inv );
-        const float specHistoryLength   = historyLengthDIS.z * inv;
-        const float specHitDistancePrev = historyLengthDIS.w * inv;
-
-        const float3 surfPos = make_float3( sp4.x, sp4.y, sp4.z ), surfPosPrev = make_float3( spp4.x, spp4.y, spp4.z );
-        const float  nv = fmaxf( 0.0f, -( normal.x * rayDir.x + normal.y * rayDir.y + normal.z * rayDir.z ) );
-
-        const float minFrames = u.specMinFrames;
-        const float oneMinusS = 1.0f - antilagAlphaSpec;
-        const float om2 = oneMinusS * oneMinusS;
-        const float A = clampf( fmaf( specHistoryLength, om2 * om2 * oneMinusS, 1.0f ), minFrames, 256.0f ); // pow(x,5)
-
-        float parallax; // :58-69
-        {
-            const float3 q     = make_float3( surfPosPrev.x - u.cameraDelta[ 0 ], surfPosPrev.y - u.cameraDelta[ 1 ], surfPosPrev.z - u.cameraDelta[ 2 ] );
-            const float  i1    = frsqrt( surfPos.x * surfPos.x + surfPos.y * surfPos.y + surfPos.z * surfPos.z );
-            const float  i2    = frsqrt( q.x * q.x + q.y * q.y + q.z * q.z );
-            const float  cosa  = saturatef( ( surfPos.x * q.x + surfPos.y * q.y + surfPos.z * q.z ) * ( i1 * i2 ) );
-            parallax           = fsqrt( fmaxf( 0.0f, 1.0f - cosa * cosa ) ) * frcp( fmaxf( cosa, 1e-6f ) ) * 60.0f;
-        }
-        const float powA    = fpow( saturatef( 1.0f - nv ), 0.66f );
-        const float AOnSurf = specAccumSpeedFast( minFrames, A, roughness, powA, parallax );
-
-        const float  aOnSurf       = frcp( 1.0f + AOnSurf );
-        const float3 specOnSurf    = fmix3( specPrevOnSurf, unfilteredSpec, aOnSurf );
-        const float  hitDistOnSurf = fmix( specHitDistancePrev, rayHit, aOnSurf );
-
-        specColorAccum         = specOnSurf;
-        specHistoryLengthAccum = AOnSurf;
-        specHitDistanceAccum   = hitDistOnSurf;
-
-        float domFactor; // :93-99
-        {
-            const float da = 0.298475f * 0.69314718056f * flg2( 39.4115f - 39.0029f * roughness );
-            domFactor      = saturatef( fmaf( fpow( saturatef( 1.0f - nv ), 10.8649f ), 1.0f - da, da ) );
-        }
-        const float  vs         = hitDistOnSurf * domFactor;
-        const float3 virtualPos = make_float3( fmaf( rayDir.x, vs, surfPos.x ), fmaf( rayDir.y, vs, surfPos.y ), fmaf( rayDir.z, vs, surfPos.z ) );
-
-        // virtual-point reprojection (exact operation order from here to the tap positions, :232-249)
-        int   pixPrevSpecX, pixPrevSpecY;
-        float subSX, subSY;
-        {
-            const float4 vp       = make_float4( virtualPos.x, virtualPos.y, virtualPos.z, 1.0f );
-            const float4 viewCur  = mulMat( u.view, vp );
-            const float4 viewPrev = mulMat( u.viewPrev, vp );
-            const float4 clipCur  = mulMat( u.projection, viewCur );
-            const float4 clipPrev = mulMat( u.projectionPrev, viewPrev );
-            const float  scx = addr( mulr( divr( clipCur.x, clipCur.w ), 0.5f ), 0.5f ), scy = addr( mulr( divr( clipCur.y, clipCur.w ), 0.5f ), 0.5f );
-            const float  spx = addr( mulr( divr( clipPrev.x, clipPrev.w ), 0.5f ), 0.5f ), spy = addr( mulr( divr( clipPrev.y, clipPrev.w ), 0.5f ), 0.5f );
-            const float  ppx = mulr( addr( mulr( addr( ( float )px, 0.5f ), u.invHalfW ), subr( spx, scx ) ), u.halfW );
-            const float  ppy = mulr( addr( mulr( addr( ( float )py, 0.5f ), u.invH ), subr( spy, scy ) ), u.renderHeight );
-            const float  qx = subr( ppx, 0.5f ), qy = subr( ppy, 0.5f );
-            const float  fx = floorf( qx ), fy = floorf( qy );
-            pixPrevSpecX = f2i( fx ); pixPrevSpecY = f2i( fy );
-            subSX = subr( qx, fx ); subSY = subr( qy, fy );
-        }
-        const float bws[ 4 ] = { mulr( subr( 1.0f, subSX ), subr( 1.0f, subSY ) ), mulr( subSX, subr( 1.0f, subSY ) ),
-                                 mulr( subr( 1.0f, subSX ), subSY ), mulr( subSX, subSY ) };
-        // the same four texels as the first gather give the same test results (same centre depth/normal/motion)
-        const uint32_t vbits = ( pixPrevSpecX == pixPrevX && pixPrevSpecY == pixPrevY )
-                                   ? ( mask & 15u )
-                                   : consistencyBits( a, rows, pixPrevSpecX, pixPrevSpecY, ax0, ax1, u.H, depth, motionZ, normal, nv32 );
-        float weightSumVirtual = 0.0f;
-#pragma unroll
-        for( int t = 0; t < 4; t++ )
-            if( ( vbits >> t ) & 1u ) weightSumVirtual = addr( weightSumVirtual, bws[ t ] );
-
-        if( weightSumVirtual > 0.0001f ) // :282-307
-        {
-            mask |= 1u << 5;
-            float       Avirt    = specAccumSpeedFast( minFrames, A, roughness, powA, 0.0f );
-            // mix(1/(1+Amin), 1/(1+Avirt), 1.0) = 0*(1/(1+Amin)) + 1/(1+Avirt): Avirt is unchanged unless 1/(1+Amin) is not finite
-            const float Ahitdist = fminf( Avirt, 16.0f );
-            const float aVirt    = frcp( 1.0f + Avirt );
-            const float3 specVirt = fmix3( specPrevOnSurf, unfilteredSpec, aVirt );
-            const float  amount   = domFactor;
-            const float  al       = fmix( aOnSurf, aVirt, amount );
-            specColorAccum         = fmix3( specOnSurf, specVirt, amount );
-            specHistoryLengthAccum = frcp( al ) - 1.0f;
-            specHitDistanceAccum   = fmix( specHitDistancePrev, rayHit, frcp( 1.0f + Ahitdist ) );
-        }
-
-        // direct diffuse and indirect (:326-367)
-        diffPrev    = make_float3( diffPrev.x * inv, diffPrev.y * inv, diffPrev.z * inv );
-        momentsPrev = make_float2( momentsPrev.x * inv, momentsPrev.y * inv );
-        indirPrev   = make_float3( indirPrev.x * inv, indirPrev.y * inv, indirPrev.z * inv );
-        {
-            const float om = 1.0f - antilagAlphaDiff, o2 = om * om, o4 = o2 * o2;
-            float       len = historyLengthDIS.x * inv * ( o4 * o4 * o2 ); // pow(x,10)
-            len             = clampf( len + 1.0f, 1.0f, 256.0f );
-            float alpha     = fmaxf( 0.01f, frcp( len ) );
-            alpha           = fmix( alpha, 1.0f, antilagAlphaDiff );
-            diffColorAccum   = fmix3( diffPrev, unfilteredDiff, alpha );
-            diffMomentsAccum = make_float2( fmix( momentsPrev.x, l, alpha ), fmix( momentsPrev.y, l2, alpha ) );
-            diffHistoryLengthAccum = len;
-        }
-        {
-            const float om = 1.0f - antilagAlphaIndir, o2 = om * om, o4 = o2 * o2;
-            float       len = historyLengthDIS.y * inv * ( o4 * o4 * o2 );
-            len             = clampf( len + 1.0f, 1.0f, 256.0f );
-            float alpha     = fmaxf( 0.01f, frcp( len ) );
-            alpha           = fmix( alpha, 1.0f, antilagAlphaIndir );
-            indirAccum      = fmix3( indirPrev, unfilteredIndir, alpha );
-            indirHistoryLengthAccum = len;
-        }
-    }
-    else // :310-315, :368-376
-    {
-        specColorAccum = unfilteredSpec; specHistoryLengthAccum = 1.0f; specHitDistanceAccum = rayHit;
-        diffColorAccum = unfilteredDiff; diffMomentsAccum = make_float2( l, l2 ); diffHistoryLengthAccum = 1.0f;
-        indirAccum = unfilteredIndir; indirHistoryLengthAccum = 1.0f;
-    }
-
-    *atW< uint32_t >( a.outDiffTemporary, px, py ) = encodeE5Fast( diffColorAccum );
-    {
-        const __half2 m = __floats2half2_rn( diffMomentsAccum.x, diffMomentsAccum.y );
-        *atW< uint32_t >( a.outMoments, px, py ) = *reinterpret_cast< const uint32_t* >( &m );
-    }
-    {
-        const __half2 h0 = __floats2half2_rn( diffHistoryLengthAccum, indirHistoryLengthAccum ), h1 = __floats2half2_rn( specHistoryLengthAccum, specHitDistanceAccum );
-        *atW< uint2 >( a.outHistLen, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &h0 ), *reinterpret_cast< const uint32_t* >( &h1 ) );
-    }
-    *atW< uint32_t >( a.outSpecAccum, px, py ) = encodeE5Fast( specColorAccum );
-    *atW< uint32_t >( a.outIndirAccum, px, py ) = encodeE5Fast( indirAccum );
-    if( a.writeMask ) *atW< uint8_t >( a.outMask, px, py ) = ( uint8_t )mask;
 }
 
 // ------------------------------------------------------------------------------------------------------------
