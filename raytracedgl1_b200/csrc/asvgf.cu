@@ -181,7 +181,8 @@ struct AsvgfDenoiser_T
     bool        gradientAtrousDone = false; // ASVGF_CREATE_EAGER_GRADIENT_ATROUS: the chain already ran behind the gradient samples
     bool        guideValid = false;         // the guide plane matches the geometry images of the frame being denoised
     uint64_t  launchCount = 0;
-    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 2 ] = {}; // cudaFuncSetAttribute done for (iteration, composing)
+    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 4 ] = {}; // cudaFuncSetAttribute done for (iteration, composing + 2 * pair)
+    bool      atrousPair = true; // a thread filters two vertically adjacent pixels together (ASVGF_ATROUS_PAIR=0: one after the other)
     int       smCount     = 0;
     int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
     // exposure state (= the reference's tonemapping buffer) and the tables of the histogram pass
@@ -409,8 +410,10 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     const int    rows   = u.yEnd - u.yBegin;
     const int    bands  = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
     const int    tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-    const size_t smem   = atrousTiledSmemBytes( step );
+    const size_t smem   = atrousSmemBytes( step );
     const dim3   grid( ( unsigned )tilesX, ( unsigned )( bands * step ), 1 );
+    a.uniformPitch = a.guide.pitchT == a.srcDiff.pitchT && a.guide.pitchT == a.srcSpec.pitchT && a.guide.pitchT == a.srcIndir.pitchT;
+    const bool pair = d.atrousPair;
     // the opt-in to more than 48 KB of dynamic shared memory is per function and per device: once, not per launch
     auto launch = [ & ]( auto kernel, bool& optedIn ) -> cudaError_t {
         if( !optedIn )
@@ -423,12 +426,13 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         return cudaSuccess;
     };
     cudaError_t e = cudaErrorInvalidValue;
-    bool&       opted = d.atrousOptIn[ iteration ][ last ? 1 : 0 ];
+    bool&       opted = d.atrousOptIn[ iteration ][ ( last ? 1 : 0 ) + ( pair ? 2 : 0 ) ];
+#define ASVGF_ATROUS_LAUNCH( S, I0, L ) ( pair ? launch( k_atrous_tiled< S, I0, L, true >, opted ) : launch( k_atrous_tiled< S, I0, L, false >, opted ) )
 #define ASVGF_ATROUS_CASE( S ) \
-    case S: e = last ? launch( k_atrous_tiled< S, false, true >, opted ) : launch( k_atrous_tiled< S, false, false >, opted ); break;
+    case S: e = last ? ASVGF_ATROUS_LAUNCH( S, false, true ) : ASVGF_ATROUS_LAUNCH( S, false, false ); break;
     switch( step )
     {
-        case 1: e = launch( k_atrous_tiled< 1, true, false >, opted ); break; // iteration 0 is never the last (atrousIterations >= 2)
+        case 1: e = ASVGF_ATROUS_LAUNCH( 1, true, false ); break; // iteration 0 is never the last (atrousIterations >= 2)
         ASVGF_ATROUS_CASE( 2 )
         ASVGF_ATROUS_CASE( 4 )
         ASVGF_ATROUS_CASE( 8 )
@@ -439,6 +443,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         default: break;
     }
 #undef ASVGF_ATROUS_CASE
+#undef ASVGF_ATROUS_LAUNCH
     if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_tiled)" );
     return launchCheck( d, "k_atrous_tiled" );
 }
@@ -636,6 +641,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
     d->info = *pInfo; d->device = device;
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
+    if( const char* e = std::getenv( "ASVGF_ATROUS_PAIR" ) ) d->atrousPair = std::atoi( e ) != 0;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
     if( pInfo->bandRowEnd == 0 )

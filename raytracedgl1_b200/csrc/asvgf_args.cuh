@@ -58,6 +58,7 @@ struct AtrousArgs
     Img       guide;       // (n.xyz, depth | roughness byte) of the current frame, written by k_guide
     NormalLut lut;
     int32_t   iteration;
+    int32_t   uniformPitch; // guide and the three source images hold the same number of texels per row
 };
 
 } // namespace asvgf

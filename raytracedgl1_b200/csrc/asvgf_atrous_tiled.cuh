@@ -119,19 +119,247 @@ __global__ void __launch_bounds__( 256 ) k_guide( const __grid_constant__ GuideA
 // ------------------------------------------------------------------------------------------------------------
 // the filter
 // ------------------------------------------------------------------------------------------------------------
-template< int STEP, bool ITER0, bool LAST >
-__global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
+// Geometry of the staged tile.  STEP >= 4: four-texel vector staging into quarter-row slots (above).  STEP < 4: the side taps
+// sit at columns c +- 1 / c +- 2, whose eight-lane groups are not 4-aligned -- the slot layout would serve them with 2-way
+// conflicts (measured: 19 M conflict cycles) -- so those strides stage one texel per lane into a plain row layout, which is
+// conflict-free for stores and for loads at any alignment.
+template< int STEP > struct AtrousGeom
+{
+    static constexpr bool VEC    = STEP >= 4;
+    static constexpr int  HALO   = VEC ? atrousHalo( STEP ) : STEP;
+    static constexpr int  TW     = kAtTileW + 2 * HALO; // staged columns
+    static constexpr int  TROWS  = kAtTileH + 2;
+    static constexpr int  GROUPS = TW / 4;
+    static constexpr int  GP     = VEC ? atrousGroupPitch( STEP ) : 0;
+    static constexpr int  RP     = VEC ? 4 * GP : TW;   // slots per staged row
+    static constexpr int  NPX    = RP * TROWS;
+    // slot of staged column `col` (0 .. TW-1) of staged row `row`
+    static __device__ __forceinline__ int slot( int row, int col ) { return VEC ? row * RP + ( col & 3 ) * GP + ( col >> 2 ) : row * RP + col; }
+    static constexpr int dCol = VEC ? STEP / 4 : STEP;  // slot distance of the tap columns c +- STEP
+};
+constexpr size_t atrousSmemBytes( int step )
+{
+    return step >= 4 ? atrousTiledSmemBytes( step ) : ( size_t )( kAtTileW + 2 * step ) * ( kAtTileH + 2 ) * 64;
+}
+
+template< int STEP >
+ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, float4* sB, float4* sC, float4* sD )
+{
+    using G = AtrousGeom< STEP >;
+    if constexpr( G::VEC )
+    {
+        constexpr int NGRP = G::GROUPS * G::TROWS;
+#pragma unroll
+        for( int g0 = 0; g0 < NGRP; g0 += kAtThreads )
+        {
+            const int g = g0 + threadIdx.x;
+            if( NGRP % kAtThreads != 0 && g >= NGRP ) break;
+            const int  r = g / G::GROUPS, cg = g - r * G::GROUPS;
+            const int  gx = xBase - G::HALO + 4 * cg, gy = yBase + ( r - 1 ) * STEP;
+            const bool rowOk = gy >= rows.y0 && gy < rows.y1;
+            const bool ok01 = rowOk && gx >= 0 && gx < u.W, ok23 = rowOk && gx >= 0 && gx + 2 < u.W; // gx is a multiple of 4, W is even
+            float4 ga[ 4 ];
+            uint4  d01, d23, sp, in;
+            {
+                const float4* pg = at< float4 >( a.guide, gx, gy );
+                const float4  z4 = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+                ga[ 0 ] = ok01 ? __ldg( pg ) : z4;
+                ga[ 1 ] = ok01 ? __ldg( pg + 1 ) : z4;
+                ga[ 2 ] = ok23 ? __ldg( pg + 2 ) : z4;
+                ga[ 3 ] = ok23 ? __ldg( pg + 3 ) : z4;
+                const uint4 z = make_uint4( 0u, 0u, 0u, 0u );
+                const uint4* pd = reinterpret_cast< const uint4* >( at< uint2 >( a.srcDiff, gx, gy ) );
+                d01 = ok01 ? __ldg( pd ) : z;
+                d23 = ok23 ? __ldg( pd + 1 ) : z;
+                sp  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcSpec, gx, gy ) ) ) : z;
+                in  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcIndir, gx, gy ) ) ) : z;
+            }
+            const int      e0 = r * G::RP + cg; // texel k of the group -> quarter row k
+            const uint32_t dd[ 8 ] = { d01.x, d01.y, d01.z, d01.w, d23.x, d23.y, d23.z, d23.w };
+            const uint32_t ss[ 4 ] = { sp.x, sp.y, sp.z, sp.w }, ii[ 4 ] = { in.x, in.y, in.z, in.w };
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k ] ) );
+                const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k + 1 ] ) );
+                const float3 s3 = decodeE5( ss[ k ] ), i3 = decodeE5( ii[ k ] );
+                sA[ e0 + k * G::GP ] = make_float4( ga[ k ].x, ga[ k ].y, ga[ k ].z, guideDepth( ga[ k ].w ) );
+                sB[ e0 + k * G::GP ] = make_float4( rg.x, rg.y, bv.x, bv.y );
+                sC[ e0 + k * G::GP ] = make_float4( s3.x, s3.y, s3.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
+                sD[ e0 + k * G::GP ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ k ].w ) );
+            }
+        }
+    }
+    else
+    {
+        constexpr int NIT = ( G::NPX + kAtThreads - 1 ) / kAtThreads;
+        float4   ga[ NIT ];
+        uint2    dd[ NIT ];
+        uint32_t ss[ NIT ], ii[ NIT ];
+#pragma unroll
+        for( int it = 0; it < NIT; it++ ) // all loads first: one memory round trip for the tile
+        {
+            const int  e = threadIdx.x + it * kAtThreads;
+            const int  r = e / G::TW, c = e - r * G::TW;
+            const int  gx = xBase - G::HALO + c, gy = yBase + ( r - 1 ) * STEP;
+            const bool ok = e < G::NPX && rows.in( gx, gy );
+            const uint32_t o = ( uint32_t )( gy * ( int )a.guide.pitchT + gx ); // the four images share the pitch in texels when uniformPitch
+            ga[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const float4* >( a.guide.p0 ) + o : at< float4 >( a.guide, gx, gy ) ) : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+            dd[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const uint2* >( a.srcDiff.p0 ) + o : at< uint2 >( a.srcDiff, gx, gy ) ) : make_uint2( 0u, 0u );
+            ss[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const uint32_t* >( a.srcSpec.p0 ) + o : at< uint32_t >( a.srcSpec, gx, gy ) ) : 0u;
+            ii[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const uint32_t* >( a.srcIndir.p0 ) + o : at< uint32_t >( a.srcIndir, gx, gy ) ) : 0u;
+        }
+#pragma unroll
+        for( int it = 0; it < NIT; it++ )
+        {
+            const int e = threadIdx.x + it * kAtThreads;
+            if( e >= G::NPX ) break;
+            const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd[ it ].x ) );
+            const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd[ it ].y ) );
+            const float3 s3 = decodeE5( ss[ it ] ), i3 = decodeE5( ii[ it ] );
+            sA[ e ] = make_float4( ga[ it ].x, ga[ it ].y, ga[ it ].z, guideDepth( ga[ it ].w ) );
+            sB[ e ] = make_float4( rg.x, rg.y, bv.x, bv.y );
+            sC[ e ] = make_float4( s3.x, s3.y, s3.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
+            sD[ e ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ it ].w ) );
+        }
+    }
+}
+
+// state of one output pixel while its taps are evaluated
+struct AtrousPix
+{
+    float3 n;
+    float  depth, l, roughByte;
+    float  kLum, wRough, wR10, P, invK1, invK2;
+    float3 diff, spec, indir;
+    float  variance, wSum, wSumSpec, wSumIndir;
+    bool   invalid;
+
+    // centre texel planes + the centre-only inputs (CmSVGFAtrous.comp:86-118, CmSVGFAtrous_Iter0.comp:201-234)
+    ASVGF_DEVICE void init( const float4 cA, const float4 cB, const float4 cC, const float4 cD, float gradDepth, float sigmaL, float historyLengthSpec, int iteration )
+    {
+        constexpr float LOG2E = 1.4426950408889634f;
+        n = make_float3( cA.x, cA.y, cA.z ); depth = cA.w; l = cC.w; roughByte = cD.w;
+        diff = make_float3( cB.x, cB.y, cB.z ); spec = make_float3( cC.x, cC.y, cC.z ); indir = make_float3( cD.x, cD.y, cD.z );
+        variance = cB.w; wSum = wSumSpec = wSumIndir = 1.0f;
+        invalid  = depth < 0.0f || depth > 10000.0f;
+        const float roughness = roughByte * ( 1.0f / 255.0f );
+        kLum   = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
+        // w_r = max(0, 1 - 10 |dr|) * wRough with r = byte / 255: the byte difference times wRough * 10/255
+        wRough = saturatef( fmaf( roughness, 30.0f, -( float )iteration ) );
+        wR10   = wRough * ( 10.0f / 255.0f );
+        const float alpha = roughness * roughness;
+        P = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
+        P = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
+        // 1/max(g,.01) = min(1/g,100) and 1/max(2g,.01) = min(.5/g,100) from one MUFU (g >= 0; 1/0 = inf), pre-scaled by
+        // sqrt(log2 e) so that -wZ*wZ is already the base-2 exponent
+        constexpr float SQRT_LOG2E = 1.2011224087864498f;
+        const float rgd = frcp( gradDepth );
+        invK1 = SQRT_LOG2E * fminf( rgd, 100.0f ); invK2 = SQRT_LOG2E * fminf( 0.5f * rgd, 100.0f );
+    }
+    // one tap: lk = log2 of the wavelet weight, or -inf outside the render area
+    ASVGF_DEVICE void tap( const float4 qA, const float4 qB, const float4 qC, const float4 qD, const bool diag, const float lk )
+    {
+        const float TINY = __uint_as_float( 0x00800000u ); // 2^-126: lg2 = -126, so P * L stays finite when P = 0
+        const float nN    = fmaxf( TINY, fmaf( n.z, qA.z, fmaf( n.y, qA.y, n.x * qA.x ) ) );
+        const float L     = flg2( nN );
+        const float wZ    = fabsf( depth - qA.w ) * ( diag ? invK2 : invK1 );
+        const float eN    = fmaf( 128.0f, L, lk );
+        const float eBase = fmaf( -wZ, wZ, eN );
+        const float eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
+        const float wBase = fex2( eBase );
+        const float wDiff = fex2( eDiff );
+        float       rfac; // max(0, 1 - 10|dr|) * wRough, both factors in [0,1]
+        asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( roughByte - qD.w ) ), "f"( -wR10 ), "f"( wRough ) );
+        const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
+        diff.x = fmaf( qB.x, wDiff, diff.x ); diff.y = fmaf( qB.y, wDiff, diff.y ); diff.z = fmaf( qB.z, wDiff, diff.z );
+        spec.x = fmaf( qC.x, wSpec, spec.x ); spec.y = fmaf( qC.y, wSpec, spec.y ); spec.z = fmaf( qC.z, wSpec, spec.z );
+        indir.x = fmaf( qD.x, wBase, indir.x ); indir.y = fmaf( qD.y, wBase, indir.y ); indir.z = fmaf( qD.z, wBase, indir.z );
+        wSum += wDiff; wSumSpec += wSpec; wSumIndir += wBase;
+        // (var*w)*w.  A vanishing weight next to an infinite fp16 variance gives inf*0 = NaN here where the shader's exp() may
+        // still hold a denormal (inf): non-finite either way, and GLSL leaves the underflow of exp() to the implementation.
+        variance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, variance );
+    }
+    ASVGF_DEVICE void normalise()
+    {
+        const float inv = frcp( wSum ), invSpec = frcp( wSumSpec ), invIndir = frcp( wSumIndir );
+        diff     = make_float3( diff.x * inv, diff.y * inv, diff.z * inv );
+        variance = variance * ( inv * inv );
+        spec     = make_float3( spec.x * invSpec, spec.y * invSpec, spec.z * invSpec );
+        indir    = make_float3( indir.x * invIndir, indir.y * invIndir, indir.z * invIndir );
+    }
+};
+
+// stores of one pixel: the three colour images, or (LAST) the composition of CmSVGFAtrous.comp:278-348
+template< bool LAST >
+ASVGF_DEVICE void atrousStore( const AtrousArgs& a, const Uniform& u, int px, int py, const float3 outDiff, const float outVariance, const float3 outSpec, const float3 outIndir )
+{
+    if( !LAST )
+    {
+        const __half2 o0 = __floats2half2_rn( outDiff.x, outDiff.y ), o1 = __floats2half2_rn( outDiff.z, outVariance );
+        *atW< uint2 >( a.dstDiff, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
+        *atW< uint32_t >( a.dstSpec, px, py )  = encodeE5MagicClamped( outSpec );
+        *atW< uint32_t >( a.dstIndir, px, py ) = encodeE5MagicClamped( outIndir );
+        return;
+    }
+    // (the extra centre-only inputs are loaded here, one pixel at a time: the registers of the tap loop stay free)
+    const int      sep   = u.W / 2;
+    const int      isOdd = px >= sep ? 1 : 0;
+    const int      regX  = ( px - isOdd * sep ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
+    const uint32_t albedoBits = __ldg( at< uint32_t >( a.albedo, regX, py ) );
+    const uint2    tp     = __ldg( at< uint2 >( a.throughput, px, py ) );
+    const uint32_t sky    = __ldg( at< uint8_t >( a.isSky, px, py ) );
+    const uint32_t metBits = __ldg( at< uint16_t >( a.metRough, px, py ) );
+    float3        albedo = unpackUfloat111110Fast( albedoBits );
+    const float2  tp01   = __half22float2( *reinterpret_cast< const __half2* >( &tp.x ) );
+    const float3  throughput = make_float3( tp01.x, tp01.y, __low2float( *reinterpret_cast< const __half2* >( &tp.y ) ) );
+    if( ( u.debugShowFlags & ( 1u << 9 ) ) != 0 ) albedo = make_float3( 1.0f, 1.0f, 1.0f );
+
+    float3 illuminated;
+    if( sky == 0u )
+    {
+        const float metallic = unorm8ToFloatFast( metBits & 0xffu );
+        const float rough    = unorm8ToFloatFast( metBits >> 8 );
+        const float t  = saturatef( ( rough - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
+        const float sm = t * t * ( 3.0f - 2.0f * t );
+        const float3 specular = fmix3( outSpec, outIndir, sm );
+        const float3 roS = fmix3( make_float3( 0.04f, 0.04f, 0.04f ), albedo, metallic ); // BRDF.h:49-53
+        const float  om  = 1.0f - metallic;
+        illuminated = make_float3( fmaf( ( outDiff.x + outIndir.x ) * albedo.x, om, specular.x * roS.x ), fmaf( ( outDiff.y + outIndir.y ) * albedo.y, om, specular.y * roS.y ),
+                                   fmaf( ( outDiff.z + outIndir.z ) * albedo.z, om, specular.z * roS.z ) );
+        if( ( u.debugShowFlags & ( 1u << 5 ) ) != 0 ) illuminated = make_float3( outDiff.x * albedo.x, outDiff.y * albedo.y, outDiff.z * albedo.z );
+        else if( ( u.debugShowFlags & ( 1u << 6 ) ) != 0 ) illuminated = make_float3( specular.x * roS.x, specular.y * roS.y, specular.z * roS.z );
+        else if( ( u.debugShowFlags & ( 1u << 7 ) ) != 0 ) illuminated = outIndir;
+        const float la = flum( albedo ); // BRDF.h:57-64
+        float       ambient = 1.0f;
+        if( !( la > 0.02f ) ) { const float q = ( la - 0.02f ) * 50.0f; ambient = 1.0f - q * q; }
+        illuminated = make_float3( illuminated.x * throughput.x * ambient, illuminated.y * throughput.y * ambient, illuminated.z * throughput.z * ambient );
+    }
+    else
+    {
+        illuminated = make_float3( albedo.x * throughput.x, albedo.y * throughput.y, albedo.z * throughput.z );
+    }
+    *atW< uint16_t >( a.histogramInput, regX, py ) = f2h( fmaxf( 0.0f, flum( illuminated ) ) );
+    if( ( float )regX < mulr( u.lightmapScreenCoverage, u.renderWidth ) ) illuminated = make_float3( albedo.x * throughput.x, albedo.y * throughput.y, albedo.z * throughput.z ); // classicShading
+    *atW< uint32_t >( a.preFinal, regX, py ) =
+        packUfloat111110Fast( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) );
+}
+
+// PAIR = false: a thread filters its two pixels one after the other (9 tile texels each).
+// PAIR = true:  a thread filters two vertically adjacent (dilated) pixels TOGETHER: their 3x3 neighbourhoods share two of
+//               four rows, so 12 tile texels serve 16 tap evaluations -- 2/3 of the shared-memory traffic, which is what
+//               bounds the single-pixel form (ncu: LDS pipe 65 %, short-scoreboard + MIO stalls 41 %, issue 55 %).
+#ifndef ASVGF_AT_PAIR_MIN_CTAS
+    #define ASVGF_AT_PAIR_MIN_CTAS 3
+#endif
+template< int STEP, bool ITER0, bool LAST, bool PAIR >
+__global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
     extern __shared__ __align__( 128 ) uint8_t smemRaw[];
-    constexpr int HALO   = atrousHalo( STEP );
-    constexpr int TW     = kAtTileW + 2 * HALO; // staged columns
-    constexpr int TROWS  = kAtTileH + 2;
-    constexpr int GROUPS = TW / 4;              // 4-texel groups per staged row
-    constexpr int NGRP   = GROUPS * TROWS;
-    constexpr int GP     = atrousGroupPitch( STEP ); // slots per quarter row
-    constexpr int RP     = 4 * GP;                   // slots per staged row
-    constexpr int NPX    = RP * TROWS;
-    constexpr int PIX    = ( kAtTileW * kAtTileH ) / kAtThreads;
+    using G = AtrousGeom< STEP >;
+    constexpr int RP = G::RP, NPX = G::NPX, HALO = G::HALO;
+    constexpr int PIX = ( kAtTileW * kAtTileH ) / kAtThreads; // 2
+    static_assert( PIX == 2, "two pixels per thread" );
     float4* sA = reinterpret_cast< float4* >( smemRaw ); // normal.xyz, depth
     float4* sB = sA + NPX;                               // diffuse rgb, variance
     float4* sC = sB + NPX;                               // specular rgb, luminance of the diffuse rgb
@@ -143,249 +371,131 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_tile
     const int xBase = blockIdx.x * kAtTileW;
     const Rows rows = rowsOf( a.depth );
 
+    // this thread's two pixels: column c, tile rows jOf(0), jOf(1).  PAIR: adjacent rows 2m, 2m+1; else rows w, w+4
+    const int c  = threadIdx.x & ( kAtTileW - 1 ), m = threadIdx.x / kAtTileW; // m = 0..3
+    auto      jOf = [ & ]( int k ) { return PAIR ? 2 * m + k : m + 4 * k; };
+    const int px = xBase + c;
+
     // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----
     uint16_t cGrad[ PIX ], cSigma[ PIX ], cSpecLen[ PIX ];
 #pragma unroll
     for( int k = 0; k < PIX; k++ )
     {
-        const int  p  = threadIdx.x + k * kAtThreads;
-        const int  j  = p / kAtTileW, c = p - j * kAtTileW;
-        const int  px = xBase + c, py = yBase + j * STEP;
+        const int  py = yBase + jOf( k ) * STEP;
         const bool ok = px < u.W && py < u.yEnd;
         cGrad[ k ]    = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
         cSpecLen[ k ] = ok ? __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.histLen, px, py ) ) + 2 ) : ( uint16_t )0; // .b of rgba16f
         cSigma[ k ]   = ITER0 ? ( uint16_t )0 : ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
     }
 
-    // ---- stage the tile: four consecutive texels per thread ----
-#pragma unroll
-    for( int g0 = 0; g0 < NGRP; g0 += kAtThreads )
-    {
-        const int g = g0 + threadIdx.x;
-        if( NGRP % kAtThreads != 0 && g >= NGRP ) break;
-        const int  r = g / GROUPS, cg = g - r * GROUPS;
-        const int  gx = xBase - HALO + 4 * cg, gy = yBase + ( r - 1 ) * STEP;
-        const bool rowOk = gy >= rows.y0 && gy < rows.y1;
-        const bool ok01 = rowOk && gx >= 0 && gx < u.W, ok23 = rowOk && gx >= 0 && gx + 2 < u.W; // gx is a multiple of 4, W is even
-        float4 ga[ 4 ];
-        uint4  d01, d23, sp, in;
-        {
-            const float4* pg = at< float4 >( a.guide, gx, gy );
-            const float4  z4 = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-            ga[ 0 ] = ok01 ? __ldg( pg ) : z4;
-            ga[ 1 ] = ok01 ? __ldg( pg + 1 ) : z4;
-            ga[ 2 ] = ok23 ? __ldg( pg + 2 ) : z4;
-            ga[ 3 ] = ok23 ? __ldg( pg + 3 ) : z4;
-            const uint4 z = make_uint4( 0u, 0u, 0u, 0u );
-            const uint4* pd = reinterpret_cast< const uint4* >( at< uint2 >( a.srcDiff, gx, gy ) );
-            d01 = ok01 ? __ldg( pd ) : z;
-            d23 = ok23 ? __ldg( pd + 1 ) : z;
-            sp  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcSpec, gx, gy ) ) ) : z;
-            in  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcIndir, gx, gy ) ) ) : z;
-        }
-        const int      e0 = r * RP + cg; // texel k of the group -> quarter row k
-        const uint32_t dd[ 8 ] = { d01.x, d01.y, d01.z, d01.w, d23.x, d23.y, d23.z, d23.w };
-        const uint32_t ss[ 4 ] = { sp.x, sp.y, sp.z, sp.w }, ii[ 4 ] = { in.x, in.y, in.z, in.w };
-#pragma unroll
-        for( int k = 0; k < 4; k++ )
-        {
-            const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k ] ) );
-            const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd[ 2 * k + 1 ] ) );
-            const float3 s3 = decodeE5( ss[ k ] ), i3 = decodeE5( ii[ k ] );
-            sA[ e0 + k * GP ] = make_float4( ga[ k ].x, ga[ k ].y, ga[ k ].z, guideDepth( ga[ k ].w ) );
-            sB[ e0 + k * GP ] = make_float4( rg.x, rg.y, bv.x, bv.y );
-            sC[ e0 + k * GP ] = make_float4( s3.x, s3.y, s3.z, luminance( make_float3( rg.x, rg.y, bv.x ) ) );
-            sD[ e0 + k * GP ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ k ].w ) );
-        }
-    }
+    atrousStage< STEP >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
     __syncthreads();
 
-    const int       sep   = u.W / 2;
-    constexpr float LOG2E = 1.4426950408889634f;
-    const float     NINF  = __uint_as_float( 0xff800000u );
-    const float     TINY  = __uint_as_float( 0x00800000u ); // 2^-126: lg2 = -126, so P * L stays finite when P = 0
-
+    const int   sep  = u.W / 2;
+    const float NINF = __uint_as_float( 0xff800000u );
     // every tap of every pixel of this tile inside its render area (ShaderCommonGLSLFunc.h:345-366)?  Uniform per CTA.
     const bool tileInterior = ( xBase >= sep ? xBase - STEP >= sep : xBase + kAtTileW + STEP <= sep ) && xBase - STEP >= 0 && xBase + kAtTileW + STEP <= u.W &&
                               yBase - STEP >= 0 && yBase + kAtTileH * STEP < u.H;
+    const int  ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
+    const bool okL = px - STEP >= ax0, okR = px + STEP < ax1;
+    constexpr int dC = G::dCol;
 
+    // Iter0.comp:158-187: 3x3 Gaussian {1/4,1/8,1/16} of the variance (products by powers of two are exact)
+    auto sigmaOf = [ & ]( int ce, int k ) {
+        if( !ITER0 ) return h2f( cSigma[ k ] );
+        float r = 0.0f;
 #pragma unroll
-    for( int k = 0; k < PIX; k++ )
+        for( int yy = -1; yy <= 1; yy++ )
+#pragma unroll
+            for( int xx = -1; xx <= 1; xx++ )
+                r = fmaf( sB[ ce + yy * RP + xx * dC ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+        return __fsqrt_rn( fmaxf( r, 0.0f ) );
+    };
+    auto finish = [ & ]( AtrousPix& s, int py ) {
+        if( s.invalid )
+        {
+            if( ITER0 ) { s.variance = 0.0f; s.diff = s.spec = s.indir = make_float3( 0.0f, 0.0f, 0.0f ); } // else pass-through of the centre
+        }
+        else s.normalise();
+        atrousStore< LAST >( a, u, px, py, s.diff, s.variance, s.spec, s.indir );
+    };
+
+    if constexpr( !PAIR )
     {
-        const int p  = threadIdx.x + k * kAtThreads;
-        const int j  = p / kAtTileW, c = p - j * kAtTileW;
-        const int px = xBase + c, py = yBase + j * STEP;
-        if( px >= u.W || py >= u.yEnd ) continue;
-
-        // slots of the three tap columns c - STEP, c, c + STEP of staged row j + 1 (for STEP >= 4 they differ by STEP / 4)
-        auto slotOf = [ & ]( int col ) { return ( j + 1 ) * RP + ( col & 3 ) * GP + ( col >> 2 ); };
-        const int    ce = slotOf( c + HALO );
-        const int    dL = STEP >= 4 ? -( STEP / 4 ) : slotOf( c + HALO - STEP ) - ce, dR = STEP >= 4 ? STEP / 4 : slotOf( c + HALO + STEP ) - ce;
-        const float4 cA = sA[ ce ], cB = sB[ ce ], cC = sC[ ce ], cD = sD[ ce ];
-        float3 outDiff = make_float3( cB.x, cB.y, cB.z ), outSpec = make_float3( cC.x, cC.y, cC.z ), outIndir = make_float3( cD.x, cD.y, cD.z );
-        float  outVariance = cB.w;
-
-        const float depth     = cA.w;
-        const float roughByte = cD.w;
-        const float roughness = roughByte * ( 1.0f / 255.0f );
-        const bool  invalid   = depth < 0.0f || depth > 10000.0f;
-
-        if( invalid )
-        {
-            if( ITER0 )
-            {
-                outVariance = 0.0f;
-                outDiff = outSpec = outIndir = make_float3( 0.0f, 0.0f, 0.0f );
-            }
-        }
-        else
-        {
-            const float gradDepth = h2f( cGrad[ k ] );
-            const float l         = cC.w;
-
-            float sigmaL;
-            if( ITER0 ) // Iter0.comp:158-187: 3x3 Gaussian {1/4,1/8,1/16} of the variance (products by powers of two are exact)
-            {
-                float r = 0.0f;
 #pragma unroll
-                for( int yy = -1; yy <= 1; yy++ )
-#pragma unroll
-                    for( int xx = -1; xx <= 1; xx++ )
-                        r = fmaf( sB[ ce + yy * RP + ( xx < 0 ? dL : xx > 0 ? dR : 0 ) ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
-                r      = __fsqrt_rn( fmaxf( r, 0.0f ) );
-                *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( r );
-                sigmaL = r;
+        for( int k = 0; k < PIX; k++ )
+        {
+            const int j = jOf( k ), py = yBase + j * STEP;
+            if( px >= u.W || py >= u.yEnd ) continue;
+            const int ce = G::slot( j + 1, c + HALO );
+            AtrousPix s;
+            {
+                const float sigmaL = sigmaOf( ce, k );
+                s.init( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], h2f( cGrad[ k ] ), sigmaL, h2f( cSpecLen[ k ] ), a.iteration );
+                if( ITER0 && !s.invalid ) *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( sigmaL );
             }
-            else
+            if( !s.invalid )
             {
-                sigmaL = h2f( cSigma[ k ] );
-            }
-            const float kLum = LOG2E * frcp( fmaf( 4.0f, sigmaL, 0.00001f ) );
-
-            // w_r = max(0, 1 - 10 |dr|) * wRough with r = byte / 255: the byte difference times wRough * 10/255
-            const float wRoughMultiplier  = saturatef( fmaf( roughness, 30.0f, -( float )a.iteration ) );
-            const float wR10              = wRoughMultiplier * ( 10.0f / 255.0f );
-            const float historyLengthSpec = h2f( cSpecLen[ k ] );
-            const float alpha             = roughness * roughness;
-            float       P                 = fmaxf( 0.01f, fmaf( 2.0f, frcp( fmaf( alpha, alpha, 1e-4f ) ), -2.0f ) ); // BRDF.h:27-29
-            P                             = clampf( P, 8.0f, 1024.0f ) * saturatef( historyLengthSpec * 0.125f );
-            // 1/max(g,.01) = min(1/g,100) and 1/max(2g,.01) = min(.5/g,100) from one MUFU (g >= 0; 1/0 = inf), pre-scaled by
-            // sqrt(log2 e) so that -wZ*wZ is already the base-2 exponent
-            constexpr float SQRT_LOG2E = 1.2011224087864498f;
-            const float rgd   = frcp( gradDepth );
-            const float invK1 = SQRT_LOG2E * fminf( rgd, 100.0f ), invK2 = SQRT_LOG2E * fminf( 0.5f * rgd, 100.0f );
-
-            float weightSum = 1.0f, weightSumSpec = 1.0f, weightSumIndir = 1.0f;
-
-            auto tap = [ & ]( const int qe, const float invK, const float lk )
-            {
-                const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
-                const float  nN = fmaxf( TINY, fmaf( cA.z, qA.z, fmaf( cA.y, qA.y, cA.x * qA.x ) ) );
-                const float  L  = flg2( nN );
-                const float  wZ = fabsf( depth - qA.w ) * invK;
-                const float  eN    = fmaf( 128.0f, L, lk );
-                const float  eBase = fmaf( -wZ, wZ, eN );
-                const float  eDiff = fmaf( fabsf( l - qC.w ), -kLum, eBase );
-                const float  wBase = fex2( eBase );
-                const float  wDiff = fex2( eDiff );
-                float        rfac; // max(0, 1 - 10|dr|) * wRough, both factors in [0,1]
-                asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( roughByte - qD.w ) ), "f"( -wR10 ), "f"( wRoughMultiplier ) );
-                const float wSpec = rfac * fex2( fmaf( P, L, eBase ) );
-
-                outDiff.x = fmaf( qB.x, wDiff, outDiff.x ); outDiff.y = fmaf( qB.y, wDiff, outDiff.y ); outDiff.z = fmaf( qB.z, wDiff, outDiff.z );
-                outSpec.x = fmaf( qC.x, wSpec, outSpec.x ); outSpec.y = fmaf( qC.y, wSpec, outSpec.y ); outSpec.z = fmaf( qC.z, wSpec, outSpec.z );
-                outIndir.x = fmaf( qD.x, wBase, outIndir.x ); outIndir.y = fmaf( qD.y, wBase, outIndir.y ); outIndir.z = fmaf( qD.z, wBase, outIndir.z );
-                weightSum += wDiff; weightSumSpec += wSpec; weightSumIndir += wBase;
-                // (var*w)*w.  A vanishing weight next to an infinite fp16 variance gives inf*0 = NaN here where the shader's exp() may
-                // still hold a denormal (inf): non-finite either way, and GLSL leaves the underflow of exp() to the implementation.
-                outVariance = fmaf( __fmul_rn( qB.w, wDiff ), wDiff, outVariance );
-            };
-
-            if( tileInterior )
-            {
+                const bool okT = py - STEP >= 0, okB = py + STEP < u.H;
 #pragma unroll
                 for( int yy = -1; yy <= 1; yy++ )
 #pragma unroll
                     for( int xx = -1; xx <= 1; xx++ )
                     {
                         if( xx == 0 && yy == 0 ) continue;
-                        const bool diag = xx != 0 && yy != 0;
-                        tap( ce + yy * RP + ( xx < 0 ? dL : xx > 0 ? dR : 0 ), diag ? invK2 : invK1, diag ? -2.0f : -1.0f );
+                        const bool  diag = xx != 0 && yy != 0;
+                        const int   qe   = ce + yy * RP + xx * dC;
+                        const bool  in   = tileInterior || ( ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true ) );
+                        s.tap( sA[ qe ], sB[ qe ], sC[ qe ], sD[ qe ], diag, in ? ( diag ? -2.0f : -1.0f ) : NINF );
                     }
             }
-            else
-            {
-                // taps outside the checkerboarded render area (they never cross x = W/2 or leave the frame) get exponent -inf
-                const int  ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
-                const bool okL = px - STEP >= ax0, okR = px + STEP < ax1, okT = py - STEP >= 0, okB = py + STEP < u.H;
+            finish( s, py );
+        }
+    }
+    else
+    {
+        const int j0 = jOf( 0 ), py0 = yBase + j0 * STEP, py1 = py0 + STEP;
+        if( px >= u.W || py0 >= u.yEnd ) return;
+        const bool have1 = py1 < u.yEnd;
+        const int  ce0 = G::slot( j0 + 1, c + HALO ), ce1 = ce0 + RP;
+        AtrousPix  s0, s1;
+        {
+            const float sg0 = sigmaOf( ce0, 0 ), sg1 = sigmaOf( ce1, 1 );
+            s0.init( sA[ ce0 ], sB[ ce0 ], sC[ ce0 ], sD[ ce0 ], h2f( cGrad[ 0 ] ), sg0, h2f( cSpecLen[ 0 ] ), a.iteration );
+            s1.init( sA[ ce1 ], sB[ ce1 ], sC[ ce1 ], sD[ ce1 ], h2f( cGrad[ 1 ] ), sg1, h2f( cSpecLen[ 1 ] ), a.iteration );
+            if( ITER0 && !s0.invalid ) *atW< uint16_t >( a.filteredVariance, px, py0 ) = f2h( sg0 );
+            if( ITER0 && !s1.invalid && have1 ) *atW< uint16_t >( a.filteredVariance, px, py1 ) = f2h( sg1 );
+        }
+        if( !( s0.invalid && s1.invalid ) )
+        {
+            // staged rows j0 .. j0+3 (= tile rows j0-1 .. j0+2): row t feeds pixel 0 as dy = t-1 and pixel 1 as dy = t-2
+            const bool okT0 = py0 - STEP >= 0, okB0 = py0 + STEP < u.H, okT1 = py1 - STEP >= 0, okB1 = py1 + STEP < u.H;
 #pragma unroll
-                for( int yy = -1; yy <= 1; yy++ )
+            for( int t = 0; t < 4; t++ )
 #pragma unroll
-                    for( int xx = -1; xx <= 1; xx++ )
+                for( int xx = -1; xx <= 1; xx++ )
+                {
+                    const int    qe = ce0 + ( t - 1 ) * RP + xx * dC;
+                    const float4 qA = sA[ qe ], qB = sB[ qe ], qC = sC[ qe ], qD = sD[ qe ];
+                    const bool   okX = xx < 0 ? okL : xx > 0 ? okR : true;
+                    if( t <= 2 && !( t == 1 && xx == 0 ) ) // pixel 0: dy = t - 1
                     {
-                        if( xx == 0 && yy == 0 ) continue;
+                        const int  yy = t - 1;
                         const bool diag = xx != 0 && yy != 0;
-                        const bool in   = ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true );
-                        tap( ce + yy * RP + ( xx < 0 ? dL : xx > 0 ? dR : 0 ), diag ? invK2 : invK1, in ? ( diag ? -2.0f : -1.0f ) : NINF );
+                        const bool in = tileInterior || ( okX && ( yy < 0 ? okT0 : yy > 0 ? okB0 : true ) );
+                        s0.tap( qA, qB, qC, qD, diag, in ? ( diag ? -2.0f : -1.0f ) : NINF );
                     }
-            }
-            const float inv = frcp( weightSum ), invSpec = frcp( weightSumSpec ), invIndir = frcp( weightSumIndir );
-            outDiff     = make_float3( outDiff.x * inv, outDiff.y * inv, outDiff.z * inv );
-            outVariance = outVariance * ( inv * inv );
-            outSpec     = make_float3( outSpec.x * invSpec, outSpec.y * invSpec, outSpec.z * invSpec );
-            outIndir    = make_float3( outIndir.x * invIndir, outIndir.y * invIndir, outIndir.z * invIndir );
+                    if( t >= 1 && !( t == 2 && xx == 0 ) ) // pixel 1: dy = t - 2
+                    {
+                        const int  yy = t - 2;
+                        const bool diag = xx != 0 && yy != 0;
+                        const bool in = tileInterior || ( okX && ( yy < 0 ? okT1 : yy > 0 ? okB1 : true ) );
+                        s1.tap( qA, qB, qC, qD, diag, in ? ( diag ? -2.0f : -1.0f ) : NINF );
+                    }
+                }
         }
-
-        if( !LAST )
-        {
-            const __half2 o0 = __floats2half2_rn( outDiff.x, outDiff.y ), o1 = __floats2half2_rn( outDiff.z, outVariance );
-            *atW< uint2 >( a.dstDiff, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
-            *atW< uint32_t >( a.dstSpec, px, py )  = encodeE5Fast( outSpec );
-            *atW< uint32_t >( a.dstIndir, px, py ) = encodeE5Fast( outIndir );
-            continue;
-        }
-
-        // composition, CmSVGFAtrous.comp:278-348 (the extra centre-only inputs are loaded here: one pixel at a time keeps the
-        // registers of the tap loop free)
-        const int      isOdd = px >= sep ? 1 : 0;
-        const int      regX  = ( px - isOdd * sep ) * 2 + ( ( isOdd + py ) & 1 ); // ShaderCommonGLSLFunc.h:331-342
-        const uint32_t albedoBits = __ldg( at< uint32_t >( a.albedo, regX, py ) );
-        const uint2    tp     = __ldg( at< uint2 >( a.throughput, px, py ) );
-        const uint32_t sky    = __ldg( at< uint8_t >( a.isSky, px, py ) );
-        const uint32_t metBits = __ldg( at< uint16_t >( a.metRough, px, py ) );
-        float3        albedo = unpackUfloat111110Fast( albedoBits );
-        const float2  tp01   = __half22float2( *reinterpret_cast< const __half2* >( &tp.x ) );
-        const float3  throughput = make_float3( tp01.x, tp01.y, __low2float( *reinterpret_cast< const __half2* >( &tp.y ) ) );
-        if( ( u.debugShowFlags & ( 1u << 9 ) ) != 0 ) albedo = make_float3( 1.0f, 1.0f, 1.0f );
-
-        float3 illuminated;
-        if( sky == 0u )
-        {
-            const float metallic = unorm8ToFloatFast( metBits & 0xffu );
-            const float rough    = unorm8ToFloatFast( metBits >> 8 );
-            const float t  = saturatef( ( rough - 0.5f ) * 4.0f );            // smoothstep(0.5, 0.75, roughness)
-            const float sm = t * t * ( 3.0f - 2.0f * t );
-            const float3 specular = fmix3( outSpec, outIndir, sm );
-            const float3 roS = fmix3( make_float3( 0.04f, 0.04f, 0.04f ), albedo, metallic ); // BRDF.h:49-53
-            const float  om  = 1.0f - metallic;
-            illuminated = make_float3( fmaf( ( outDiff.x + outIndir.x ) * albedo.x, om, specular.x * roS.x ), fmaf( ( outDiff.y + outIndir.y ) * albedo.y, om, specular.y * roS.y ),
-                                       fmaf( ( outDiff.z + outIndir.z ) * albedo.z, om, specular.z * roS.z ) );
-            if( ( u.debugShowFlags & ( 1u << 5 ) ) != 0 ) illuminated = make_float3( outDiff.x * albedo.x, outDiff.y * albedo.y, outDiff.z * albedo.z );
-            else if( ( u.debugShowFlags & ( 1u << 6 ) ) != 0 ) illuminated = make_float3( specular.x * roS.x, specular.y * roS.y, specular.z * roS.z );
-            else if( ( u.debugShowFlags & ( 1u << 7 ) ) != 0 ) illuminated = outIndir;
-            const float la = flum( albedo ); // BRDF.h:57-64
-            float       ambient = 1.0f;
-            if( !( la > 0.02f ) ) { const float q = ( la - 0.02f ) * 50.0f; ambient = 1.0f - q * q; }
-            illuminated = make_float3( illuminated.x * throughput.x * ambient, illuminated.y * throughput.y * ambient, illuminated.z * throughput.z * ambient );
-        }
-        else
-        {
-            illuminated = make_float3( albedo.x * throughput.x, albedo.y * throughput.y, albedo.z * throughput.z );
-        }
-        *atW< uint16_t >( a.histogramInput, regX, py ) = f2h( fmaxf( 0.0f, flum( illuminated ) ) );
-        if( ( float )regX < mulr( u.lightmapScreenCoverage, u.renderWidth ) ) illuminated = make_float3( albedo.x * throughput.x, albedo.y * throughput.y, albedo.z * throughput.z ); // classicShading
-        *atW< uint32_t >( a.preFinal, regX, py ) =
-            packUfloat111110Fast( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) );
+        finish( s0, py0 );
+        if( have1 ) finish( s1, py1 );
     }
 }
 

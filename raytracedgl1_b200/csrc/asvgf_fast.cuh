@@ -73,6 +73,25 @@ ASVGF_DEVICE uint32_t encodeE5Fast( float3 c )
     return encodeE5Unclamped( fminf( fmaxf( c.x, 0.0f ), 65408.0f ), fminf( fmaxf( c.y, 0.0f ), 65408.0f ), fminf( fmaxf( c.z, 0.0f ), 65408.0f ) );
 }
 
+// E5B9G9R9 encoder (Utils.h:162-192) for components already clamped to [0, 65408], NaN-free.
+//   shared exponent: floor(log2 max) + 1 + 15, one more when the 9-bit mantissa of max rounds up to 512, i.e. when the
+//   top ten bits of max's fraction are all ones and the next is set: adding 0x4000 to the bit pattern carries into the exponent.
+//   mantissas: x * 2^(24-e) rounded to nearest even = the low bits of x + 1.5 * 2^(e-1) (the sum's ulp is 2^(e-24)).
+ASVGF_DEVICE uint32_t encodeE5Magic( float r, float g, float b )
+{
+    const float maxC = fmaxf( r, fmaxf( g, b ) );
+    if( maxC == 0.0f ) return 0u;
+    const uint32_t e     = max( ( __float_as_uint( maxC ) + 0x4000u ) >> 23, 111u ) - 111u; // max(-16, floor(log2)) + 16, bumped
+    const uint32_t mbits = ( ( e + 126u ) << 23 ) | 0x400000u;                               // 1.5 * 2^(e-1)
+    const float    m     = __uint_as_float( mbits );
+    const uint32_t ri = __float_as_uint( __fadd_rn( r, m ) ) - mbits, gi = __float_as_uint( __fadd_rn( g, m ) ) - mbits, bi = __float_as_uint( __fadd_rn( b, m ) ) - mbits;
+    return ( e << 27 ) | ( bi << 18 ) | ( gi << 9 ) | ri;
+}
+ASVGF_DEVICE uint32_t encodeE5MagicClamped( float3 c ) // NaN -> 0 like the oracle's clamp
+{
+    return encodeE5Magic( fminf( fmaxf( c.x, 0.0f ), 65408.0f ), fminf( fmaxf( c.y, 0.0f ), 65408.0f ), fminf( fmaxf( c.z, 0.0f ), 65408.0f ) );
+}
+
 // row addressing: all full-resolution images share (W, H) and the stored row range
 struct Rows
 {

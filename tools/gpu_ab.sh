@@ -1,8 +1,6 @@
 #!/bin/bash
-# A/B: tests with the default build, then bench variants selected by environment variables
+# A/B on the GPU: per-pass parity with each variant (environment variables select them), then the 4K bench per variant
 mkdir -p gpurun_out
-if [ -z "$SKIP_TESTS" ]; then timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; fi
-tail -15 gpurun_out/pytest_gpu.log
 summ() { python - "$1" <<'PY'
 import json, sys
 try:
@@ -14,6 +12,10 @@ PY
 }
 for v in "$@"; do
   name=$(echo "$v" | tr '= /' '___')
-  env $v timeout 600 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --frames 4 > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
+  if [ -z "$SKIP_TESTS" ]; then
+    env $v timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "${TESTS:-per_pass or tiny or edges}" > gpurun_out/pytest_$name.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$name.log
+    tail -4 gpurun_out/pytest_$name.log | cut -c1-300
+  fi
+  env $v timeout 600 python bench.py --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
   summ gpurun_out/bench_$name.json
 done

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call B: GPU tests (all, no -x: collect achieved parity), 4K bench, optional ncu
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -m gpu -q --durations=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+[ -n "$SKIP_TESTS" ] || timeout 1800 python -m pytest tests -m gpu -q --durations=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log | cut -c1-400
 timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_4k.json 2> gpurun_out/bench_4k.err
 python - <<'PY'
