@@ -173,7 +173,8 @@ struct AsvgfDenoiser_T
     NormalLut lut{};
     bool      haveLut     = false;
     // internal per-frame scratch: the decoded geometry of the current frame (asvgf_atrous_tiled.cuh, k_guide)
-    Img       guide{};
+    Img       guide{}, centre{};
+    bool      centreValid = false; // `centre` holds the weight constants of the frame being denoised (written by a-trous iteration 0)
     // cross-stream ordering of the gradient chain (asvgfGradientSamples may be given another stream than asvgfDenoise):
     // the gradient-sample pass of frame t+1 waits for the temporal pass of frame t, the temporal pass waits for the gradient chain
     cudaEvent_t evTemporalDone = nullptr, evGradientsDone = nullptr;
@@ -306,6 +307,11 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.outIndirAccum = d.get( ASVGF_IMAGE_INDIR_ACCUM, fi ); a.outMask = d.get( ASVGF_IMAGE_DEBUG_MASK, fi );
     a.lut = d.lut;
     a.writeMask = ( ( d.info.flags & ASVGF_CREATE_EXPORT_DEBUG_MASK ) && a.outMask.p ) ? 1 : 0;
+    // the a-trous iterations read the guide plane up to their reach beyond the rows they compute: this launch covers those rows
+    // when it runs on the whole frame or with the band apron (18 rows >= 14 + 1); otherwise k_guide fills every stored row
+    a.guide = d.guide;
+    a.writeGuide = ( d.info.bandRowEnd == 0 || ( d.info.flags & ASVGF_CREATE_BAND_APRON ) ) ? 1 : 0;
+    d.guideValid = a.writeGuide != 0;
     // one texel offset serves every image when they all hold the same number of texels per row (the library's own allocation)
     bool uniformPitch = true;
     for( const Img* im : { &a.unfDirect, &a.unfIndir, &a.unfSpec, &a.viewDir, &a.motion, &a.depth, &a.normal, &a.metRough, &a.surfPos, &a.depthPrev, &a.normalPrev,
@@ -394,6 +400,8 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.histogramInput = d.get( ASVGF_IMAGE_HISTOGRAM_INPUT, fi );
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
     a.guide = d.guide;
+    a.centre = d.centre; a.centreValid = d.centreValid ? 1 : 0;
+    if( iteration == 0 ) d.centreValid = true; // this launch writes it
 
     const int step = 1 << iteration;
 #ifdef ASVGF_WITH_LITERAL
@@ -754,6 +762,16 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             return fail( rr, msg );
         }
         setImgStorage( g, mem, pitch, 16 );
+        Img& c = d->centre;
+        c = g;
+        uint8_t* memC = nullptr;
+        if( cudaMalloc( ( void** )&memC, ( size_t )pitch * ( size_t )g.rows ) != cudaSuccess || cudaMemset( memC, 0, ( size_t )pitch * ( size_t )g.rows ) != cudaSuccess )
+        {
+            if( memC ) cudaFree( memC );
+            asvgfDestroy( d );
+            return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(centre plane)" );
+        }
+        setImgStorage( c, memC, pitch, 16 );
     }
     *pDenoiser = d;
     return ASVGF_SUCCESS;
@@ -767,6 +785,7 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
         if( d->owned[ i ] && d->img[ i ].p ) cudaFree( d->img[ i ].p );
     if( d->haveLut ) releaseLut( d->device );
     if( d->guide.p ) cudaFree( d->guide.p );
+    if( d->centre.p ) cudaFree( d->centre.p );
     if( d->evTemporalDone ) cudaEventDestroy( d->evTemporalDone );
     if( d->evGradientsDone ) cudaEventDestroy( d->evGradientsDone );
     if( d->log2Half ) cudaFree( d->log2Half );
@@ -806,7 +825,7 @@ AsvgfResult asvgfBindExternalImage( AsvgfDenoiser d, uint32_t imageIndex, void* 
         d->owned[ imageIndex ] = false;
     }
     setImgStorage( im, ( uint8_t* )pDevice, ( uint32_t )pitchBytes, desc.bpp );
-    d->guideValid = false;
+    d->guideValid = d->centreValid = false;
     return ASVGF_SUCCESS;
 }
 
@@ -820,7 +839,7 @@ static AsvgfResult copyImage( AsvgfDenoiser d, AsvgfStream stream, uint32_t imag
     if( hostPitch == 0 ) hostPitch = rowBytes;
     if( hostPitch < rowBytes ) return fail( ASVGF_WRONG_ARGUMENT, "host pitch smaller than a row" );
     DeviceGuard guard( d->device );
-    if( upload ) d->guideValid = false;
+    if( upload ) d->guideValid = d->centreValid = false;
     if( upload ) CUDA_TRY( cudaMemcpy2DAsync( im.p, im.pitch, pHost, hostPitch, rowBytes, ( size_t )im.rows, cudaMemcpyHostToDevice, ( cudaStream_t )stream ) );
     else CUDA_TRY( cudaMemcpy2DAsync( pHost, hostPitch, im.p, im.pitch, rowBytes, ( size_t )im.rows, cudaMemcpyDeviceToHost, ( cudaStream_t )stream ) );
     return ASVGF_SUCCESS;
@@ -840,7 +859,7 @@ AsvgfResult asvgfResetHistory( AsvgfDenoiser d, AsvgfStream stream )
     DeviceGuard guard( d->device );
     for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
         if( d->owned[ i ] && d->img[ i ].p ) CUDA_TRY( cudaMemsetAsync( d->img[ i ].p, 0, ( size_t )d->img[ i ].pitch * d->img[ i ].rows, ( cudaStream_t )stream ) );
-    d->guideValid = false;
+    d->guideValid = d->centreValid = false;
     return ASVGF_SUCCESS;
 }
 
@@ -854,7 +873,7 @@ AsvgfResult asvgfGradientSamples( AsvgfDenoiser d, AsvgfStream stream, uint32_t 
     // this pass reads what the previous frame's temporal pass wrote (IndirAccum_Prev) and overwrites what it read
     // (DISPingGradient): when the two are enqueued on different streams the order must be made explicit
     if( d->temporalRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evTemporalDone, 0 ) );
-    d->guideValid = false; // a new frame starts
+    d->guideValid = d->centreValid = false; // a new frame starts
     r = runPass( *d, s, frameIndex, u, ASVGF_PASS_GRADIENT_SAMPLES );
     if( r != ASVGF_SUCCESS ) return r;
     d->gradientAtrousDone = false;
@@ -876,9 +895,12 @@ AsvgfResult asvgfDenoise( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameInd
     DeviceGuard        guard( d->device );
     const cudaStream_t s = ( cudaStream_t )stream;
     const Uniform      u = makeUniform( *d, *pUniform );
-    r = runGuide( *d, s, frameIndex ); // independent of the gradient chain: overlaps it when that runs on another stream
-    if( r != ASVGF_SUCCESS ) return r;
-    d->guideValid = true;
+    d->guideValid = d->centreValid = false;
+    if( d->info.bandRowEnd != 0 && !( d->info.flags & ASVGF_CREATE_BAND_APRON ) )
+    {
+        r = runGuide( *d, s, frameIndex ); // per-pass band schedule: the temporal pass covers the owned rows only
+        if( r != ASVGF_SUCCESS ) return r;
+    }
     if( d->gradientsRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evGradientsDone, 0 ) );
     if( !d->gradientAtrousDone )
     {
@@ -923,14 +945,15 @@ AsvgfResult asvgfDenoisePass( AsvgfDenoiser d, AsvgfStream stream, uint32_t fram
             d->guideValid = true;
         }
     }
-    else
+    else if( pass == ASVGF_PASS_TEMPORAL )
     {
-        d->guideValid = false;
-        if( pass == ASVGF_PASS_TEMPORAL )
-        {
-            d->gradientAtrousDone = false;
-            if( d->gradientsRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evGradientsDone, 0 ) );
-        }
+        d->guideValid = d->centreValid = false; // (the pass re-validates the guide when it covers the rows, runTemporal)
+        d->gradientAtrousDone = false;
+        if( d->gradientsRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evGradientsDone, 0 ) );
+    }
+    else if( pass < ASVGF_PASS_TEMPORAL )
+    {
+        d->guideValid = d->centreValid = false; // a new frame starts
     }
     r = runPass( *d, s, frameIndex, makeUniform( *d, *pUniform ), pass );
     if( r == ASVGF_SUCCESS && pass == ASVGF_PASS_TEMPORAL )

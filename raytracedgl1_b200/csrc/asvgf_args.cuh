@@ -31,8 +31,10 @@ struct TemporalArgs
     Img unfDirect, unfIndir, unfSpec, viewDir, motion, depth, normal, metRough, surfPos, disPing;
     Img depthPrev, normalPrev, diffHistory, momentsPrev, histLenPrev, specPrev, indirPrev, surfPosPrev;
     Img outDiffTemporary, outMoments, outHistLen, outSpecAccum, outIndirAccum, outMask;
+    Img guide;               // (n.xyz, depth | roughness byte) of the frame for the a-trous iterations (asvgf_atrous_tiled.cuh)
     NormalLut lut;
     int32_t   writeMask;
+    int32_t   writeGuide;    // this launch covers every row the a-trous iterations will read: write the guide plane here
 };
 
 // F: anti-firefly, CmAntiFirefly.comp:47-159
@@ -55,7 +57,9 @@ struct AtrousArgs
     Img       srcDiff, srcSpec, srcIndir, dstDiff, dstSpec, dstIndir;
     Img       depth, depthGrad, normal, metRough, histLen, filteredVariance;
     Img       albedo, throughput, isSky, preFinal, histogramInput;
-    Img       guide;       // (n.xyz, depth | roughness byte) of the current frame, written by k_guide
+    Img       guide;       // (n.xyz, depth | roughness byte) of the current frame, written by the temporal pass or k_guide
+    Img       centre;      // (kLum, invK1, invK2, P) per pixel: the iteration-independent weight constants, written by iteration 0
+    int32_t   centreValid; // iterations >= 1: read `centre` instead of re-deriving the constants from three more images
     NormalLut lut;
     int32_t   iteration;
     int32_t   uniformPitch; // guide and the three source images hold the same number of texels per row

@@ -257,6 +257,17 @@ struct AtrousPix
         const float rgd = frcp( gradDepth );
         invK1 = SQRT_LOG2E * fminf( rgd, 100.0f ); invK2 = SQRT_LOG2E * fminf( 0.5f * rgd, 100.0f );
     }
+    // iterations >= 1 with the centre plane of iteration 0: only the roughness weight depends on the iteration
+    ASVGF_DEVICE void initFromCentre( const float4 cA, const float4 cB, const float4 cC, const float4 cD, const float4 k, int iteration )
+    {
+        n = make_float3( cA.x, cA.y, cA.z ); depth = cA.w; l = cC.w; roughByte = cD.w;
+        diff = make_float3( cB.x, cB.y, cB.z ); spec = make_float3( cC.x, cC.y, cC.z ); indir = make_float3( cD.x, cD.y, cD.z );
+        variance = cB.w; wSum = wSumSpec = wSumIndir = 1.0f;
+        invalid  = depth < 0.0f || depth > 10000.0f;
+        wRough = saturatef( fmaf( roughByte, 30.0f / 255.0f, -( float )iteration ) );
+        wR10   = wRough * ( 10.0f / 255.0f );
+        kLum = k.x; invK1 = k.y; invK2 = k.z; P = k.w;
+    }
     // one tap: lk = log2 of the wavelet weight, or -inf outside the render area
     ASVGF_DEVICE void tap( const float4 qA, const float4 qB, const float4 qC, const float4 qD, const bool diag, const float lk )
     {
@@ -377,15 +388,24 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
     const int px = xBase + c;
 
     // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----
+    // iterations >= 1 read the constants iteration 0 derived (one 16-byte load) unless the plane is stale (a.centreValid)
+    const bool useCentre = !ITER0 && a.centreValid;
     uint16_t cGrad[ PIX ], cSigma[ PIX ], cSpecLen[ PIX ];
+    float4   cK[ PIX ];
 #pragma unroll
     for( int k = 0; k < PIX; k++ )
     {
         const int  py = yBase + jOf( k ) * STEP;
         const bool ok = px < u.W && py < u.yEnd;
-        cGrad[ k ]    = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
-        cSpecLen[ k ] = ok ? __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.histLen, px, py ) ) + 2 ) : ( uint16_t )0; // .b of rgba16f
-        cSigma[ k ]   = ITER0 ? ( uint16_t )0 : ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
+        cK[ k ] = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+        cGrad[ k ] = cSpecLen[ k ] = cSigma[ k ] = 0;
+        if( useCentre ) cK[ k ] = ldIf< float4 >( a.centre, px, py, ok, make_float4( 0.0f, 0.0f, 0.0f, 0.0f ) );
+        else
+        {
+            cGrad[ k ]    = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
+            cSpecLen[ k ] = ok ? __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.histLen, px, py ) ) + 2 ) : ( uint16_t )0; // .b of rgba16f
+            cSigma[ k ]   = ITER0 ? ( uint16_t )0 : ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
+        }
     }
 
     atrousStage< STEP >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
@@ -411,6 +431,17 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
                 r = fmaf( sB[ ce + yy * RP + xx * dC ].w, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
         return __fsqrt_rn( fmaxf( r, 0.0f ) );
     };
+    // centre of pixel k at slot ce: derive (or fetch) the weight constants; iteration 0 publishes them and the filtered sigma
+    auto begin = [ & ]( AtrousPix& s, int ce, int k, int py, bool inFrame ) {
+        if( useCentre ) { s.initFromCentre( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], cK[ k ], a.iteration ); return; }
+        const float sigmaL = sigmaOf( ce, k );
+        s.init( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], h2f( cGrad[ k ] ), sigmaL, h2f( cSpecLen[ k ] ), a.iteration );
+        if( ITER0 && inFrame )
+        {
+            if( !s.invalid ) *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( sigmaL );
+            *atW< float4 >( a.centre, px, py ) = make_float4( s.kLum, s.invK1, s.invK2, s.P );
+        }
+    };
     auto finish = [ & ]( AtrousPix& s, int py ) {
         if( s.invalid )
         {
@@ -429,11 +460,7 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
             if( px >= u.W || py >= u.yEnd ) continue;
             const int ce = G::slot( j + 1, c + HALO );
             AtrousPix s;
-            {
-                const float sigmaL = sigmaOf( ce, k );
-                s.init( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], h2f( cGrad[ k ] ), sigmaL, h2f( cSpecLen[ k ] ), a.iteration );
-                if( ITER0 && !s.invalid ) *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( sigmaL );
-            }
+            begin( s, ce, k, py, true );
             if( !s.invalid )
             {
                 const bool okT = py - STEP >= 0, okB = py + STEP < u.H;
@@ -459,13 +486,8 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
         const bool have1 = py1 < u.yEnd;
         const int  ce0 = G::slot( j0 + 1, c + HALO ), ce1 = ce0 + RP;
         AtrousPix  s0, s1;
-        {
-            const float sg0 = sigmaOf( ce0, 0 ), sg1 = sigmaOf( ce1, 1 );
-            s0.init( sA[ ce0 ], sB[ ce0 ], sC[ ce0 ], sD[ ce0 ], h2f( cGrad[ 0 ] ), sg0, h2f( cSpecLen[ 0 ] ), a.iteration );
-            s1.init( sA[ ce1 ], sB[ ce1 ], sC[ ce1 ], sD[ ce1 ], h2f( cGrad[ 1 ] ), sg1, h2f( cSpecLen[ 1 ] ), a.iteration );
-            if( ITER0 && !s0.invalid ) *atW< uint16_t >( a.filteredVariance, px, py0 ) = f2h( sg0 );
-            if( ITER0 && !s1.invalid && have1 ) *atW< uint16_t >( a.filteredVariance, px, py1 ) = f2h( sg1 );
-        }
+        begin( s0, ce0, 0, py0, true );
+        begin( s1, ce1, 1, py1, have1 );
         if( !( s0.invalid && s1.invalid ) )
         {
             // staged rows j0 .. j0+3 (= tile rows j0-1 .. j0+2): row t feeds pixel 0 as dy = t-1 and pixel 1 as dy = t-2

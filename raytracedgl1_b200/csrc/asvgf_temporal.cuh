@@ -80,17 +80,39 @@ ASVGF_DEVICE uint32_t consistency2x2( const TemporalArgs& a, const Rows& rows, u
             nOk |= dot3r( normal, nPrev ) > 0.95f ? ( 1u << t ) : 0u;
         }
     }
-    uint32_t    bits = 0;
-    const float az   = fabsf( depth );
+    // a / b < 0.1f (ShaderCommonGLSLFunc.h:368-371) from an approximate quotient; only a quotient within 1e-5 of the threshold
+    // (or a non-finite one) needs the IEEE division -- one branch for the four taps
+    const float az = fabsf( depth ), raz = frcp( az );
+    float       num[ 4 ], q[ 4 ];
+    bool        near = false;
 #pragma unroll
     for( int t = 0; t < 4; t++ )
     {
-        const float num = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
-        const bool  ok  = in[ t ] && ( ( nOk >> t ) & 1u ) && quotientBelowTenth( num, az );
-        bits |= ok ? ( 1u << t ) : 0u;
+        num[ t ] = fabsf( addr( subr( depth, h2f( ( uint16_t )dz[ t ] ) ), motionZ ) );
+        q[ t ]   = num[ t ] * raz;
+        near     = near || !( fabsf( q[ t ] - 0.1f ) > 1.0e-5f ); // NaN counts as near
     }
+    uint32_t zOk = 0u;
+    if( !near )
+    {
+#pragma unroll
+        for( int t = 0; t < 4; t++ ) zOk |= q[ t ] < 0.1f ? ( 1u << t ) : 0u;
+    }
+    else
+    {
+#pragma unroll
+        for( int t = 0; t < 4; t++ ) zOk |= divr( num[ t ], az ) < 0.1f ? ( 1u << t ) : 0u;
+    }
+    uint32_t bits = zOk & nOk;
+#pragma unroll
+    for( int t = 0; t < 4; t++ ) bits &= in[ t ] ? ~0u : ~( 1u << t );
     return bits;
 }
+
+// float -> int of a tap coordinate.  The pin (oracle: saturate at +-1e9, NaN -> -1e9) only matters through "is the tap inside the
+// image": the hardware conversion saturates huge values to INT_MIN / INT_MAX (outside, like +-1e9; x + 1 may wrap to INT_MIN:
+// still outside), and NaN is sent outside explicitly (the hardware would give 0, a valid column).
+ASVGF_DEVICE int f2iTap( float f ) { return f == f ? __float2int_rz( f ) : -1000000000; }
 
 // exact reprojected tap position and bilinear weights (ShaderCommonGLSLFunc.h:271-277, CmSVGFTemporalAccumulation.comp:126-137)
 ASVGF_DEVICE void reproject( const Uniform& u, int px, int py, float mx, float my, int& bx, int& by, float ( &bw )[ 4 ] )
@@ -99,7 +121,7 @@ ASVGF_DEVICE void reproject( const Uniform& u, int px, int py, float mx, float m
     const float ppy = mulr( addr( mulr( addr( ( float )py, 0.5f ), u.invH ), my ), u.renderHeight );
     const float qx = subr( ppx, 0.5f ), qy = subr( ppy, 0.5f );
     const float fx = floorf( qx ), fy = floorf( qy );
-    bx = f2i( fx ); by = f2i( fy );
+    bx = f2iTap( fx ); by = f2iTap( fy );
     const float sx = subr( qx, fx ), sy = subr( qy, fy );
     const float ox = subr( 1.0f, sx ), oy = subr( 1.0f, sy );
     bw[ 0 ] = mulr( ox, oy ); bw[ 1 ] = mulr( sx, oy ); bw[ 2 ] = mulr( ox, sy ); bw[ 3 ] = mulr( sx, sy );
@@ -131,6 +153,8 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
     const float  motionZ = __low2float( *reinterpret_cast< const __half2* >( &mv.y ) );
     const float  depth   = h2f( dv );
     const float3 normal  = decodeNormal( a.lut, nv32 );
+    if( a.writeGuide ) // the decoded geometry the a-trous iterations stage instead of re-decoding it four times
+        *atW< float4 >( a.guide, px, py ) = make_float4( normal.x, normal.y, normal.z, __uint_as_float( __float_as_uint( depth ) | ( ( uint32_t )mr >> 8 ) ) );
 
     const int sep = u.W / 2, ax0 = px >= sep ? sep : 0, ax1 = ax0 + sep;
 
