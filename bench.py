@@ -543,161 +543,223 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_baseline(W, H, N, None)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+    # ---- the other BASELINE configurations, in the same line (explanatory legs; `value` above stays the headline metric) ----
     d.close()
+    del resident, staging, host
+    torch.cuda.empty_cache()
+    legs = [] if args.legs == "none" else [x for x in args.legs.split(",") if x]
+    gloo = None
+    if dist is not None:
+        gloo = dist.new_group(backend="gloo")         # host-side barrier: the idle ranks must not spin on their GPUs
+    if "view_streams" in legs:                         # config 5: 48 x 1080p streams, 48 / N handles per GPU
+        try:
+            vs = leg_view_streams(rank, world, local_rank, dist)
+        except Exception as e:  # noqa: BLE001
+            vs = {"error": repr(e)}
+        if rank == 0:
+            line["view_streams"] = vs
+    if "bands" in legs:                                # config 4: one 8K frame as bands over all the GPUs of this run
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=gloo)                   # every rank has released its GPU memory
+        if rank == 0:
+            try:
+                line["bands"] = leg_bands(list(range(world)), "8k-bands", max(10, min(args.steps, 40)), max(3, min(args.warmup, 5)))
+            except Exception as e:  # noqa: BLE001
+                line["bands"] = {"error": repr(e)}
+        if dist is not None:
+            dist.barrier(group=gloo)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def run_bands(args, rank, world, local_rank):
-    """One frame per step, split into `world` horizontal bands (raytracedgl1_b200/bands.py).  value = frame pixels x
-    steps / time (strong scaling); every rank holds its band + 48-row halo of a short cycled sequence in HBM."""
+def leg_bands(devices, workload, steps, warmup, n_frames=4, log=None):
+    """BASELINE config 4: ONE frame per step, split into horizontal bands across `devices` (asvgfBandSet*, include/asvgf.h):
+    a single process drives every GPU, halos travel as peer copies behind the producing passes.  Returns the `bands`
+    object of the JSON line.  Device-timed (events on every band's stream, the longest band counts)."""
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     import synth
-    from raytracedgl1_b200 import bands, layout
+    from raytracedgl1_b200 import bands as bands_mod
     from raytracedgl1_b200 import denoiser as dn
+    from raytracedgl1_b200 import layout
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    W, H, N, desc = WORKLOADS[args.workload]
-    n_frames = max(2, min(args.frames, 8) // 2 * 2)
-    swappable = {n for n in layout.PRODUCER_IMAGES if n + "_Prev" in layout.IMAGES}
+    W, H, N, desc = WORKLOADS[workload]
+    n = len(devices)
+    swappable = {name for name in layout.PRODUCER_IMAGES if name + "_Prev" in layout.IMAGES}
     uniforms = [synth.uniform(W, H, f) for f in range(n_frames)]
+    host = [synth.generate(W, H, f) for f in range(n_frames)]          # whole frames once; every band takes its rows
 
-    def build(boundaries):
-        """One rank's band handle + its band-plus-halo rows of the cycled synthetic sequence, resident in HBM."""
-        bd = bands.BandedDenoiser(W, H, N, rank=rank, world=world, device=local_rank, apron=(args.band_schedule == "apron"),
-                                  boundaries=boundaries)
-        s0, s1 = bd.plan.stored if world > 1 else (0, H)
+    def build(devs, boundaries, exchange=True):
+        os.environ["ASVGF_BAND_NO_EXCHANGE"] = "0" if exchange else "1"
+        bs = dn.BandSet(W, H, devs, N, boundaries=boundaries)
         resident = []
         for f in range(n_frames):
-            g = synth.generate_rows(W, H, f, s0, s1)
-            dev = {}
-            for name in layout.PRODUCER_IMAGES:
-                _, pitch, _, _, rows = bd.d.image(name, 0)
-                a = g[name]
-                row_bytes = a.nbytes // rows
-                dt = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
-                dt[:, :row_bytes].copy_(torch.from_numpy(a.view(np.uint8).reshape(rows, row_bytes)))
-                dev[name] = (dt, pitch)
-            resident.append(dev)
-        return bd, resident
+            per_band = []
+            for k, b in enumerate(bs.bands):
+                dev = {}
+                for name in layout.PRODUCER_IMAGES:
+                    _, pitch, _, r0, rows = b["denoiser"].image(name, 0)
+                    a = host[f][name][r0:r0 + rows]
+                    row_bytes = a.nbytes // rows
+                    t = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda:%d" % b["device"])
+                    t[:, :row_bytes].copy_(torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(rows, row_bytes)))
+                    dev[name] = (t, pitch)
+                per_band.append(dev)
+            resident.append(per_band)
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        return bs, resident
 
-    def make_step(bd, resident):
-        def step(i, events=None):
+    def run(bs, resident, k_steps, w_steps):
+        def step(i):
             f, fi = i % n_frames, i & 1
+            for k, b in enumerate(bs.bands):
+                for name in layout.PRODUCER_IMAGES:
+                    t, pitch = resident[f][k][name]
+                    b["denoiser"].bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
+            bs.frame(fi, uniforms[f])
+        for i in range(w_steps):
+            step(i)
+        bs.synchronize()
+        bs.begin_timing()
+        t0 = time.perf_counter()
+        for i in range(k_steps):
+            step(w_steps + i)
+        ms, per = bs.end_timing()
+        bs.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        return ms / k_steps, [p / k_steps for p in per], wall_ms / k_steps
+
+    out = {"workload": desc.replace("with per-pass halo exchange over NCCL/NVLink", "halos pushed between neighbours as peer copies behind the producing pass"),
+           "width": W, "height": H, "atrous_iterations": N, "n_gpus": len(set(devices)), "bands": n, "steps": steps}
+    k_cal = max(4, steps // 4)
+    # one band on the first device: the single-GPU time of the same frame
+    bs, res = build(devices[:1], None)
+    t1, _, _ = run(bs, res, max(4, steps // 2) if n > 1 else steps, warmup)
+    bs.close(); del res
+    out["ms_per_step_n1"] = t1
+    if n == 1:
+        out.update({"ms_per_step": t1, "value": W * H / (t1 * 1e-3) / 1e6, "unit": UNIT})
+        return out
+    # equal bands without exchange: every band's own kernel time -> boundaries of equal cost (rows are not equally expensive:
+    # sky rows skip the taps), rounded to multiples of 3
+    bs, res = build(devices, None, exchange=False)
+    halo = bs.stored_rows(1, "Normal")[0]
+    halo = bs.bands[1]["rows"][0] - halo
+    _, per_equal, _ = run(bs, res, k_cal, warmup)
+    equal_boundaries = [b["rows"][0] for b in bs.bands] + [H]
+    bs.close(); del res
+    boundaries = bands_mod.rebalanced_rows(equal_boundaries, per_equal, min_rows=halo)
+    # the measured configuration, and the same without exchange (what the halo traffic and its waits cost)
+    bs, res = build(devices, boundaries, exchange=False)
+    t_compute, per_compute, _ = run(bs, res, k_cal, warmup)
+    bs.close(); del res
+    bs, res = build(devices, boundaries, exchange=True)
+    tN, per, wall = run(bs, res, steps, warmup)
+    bs.close(); del res
+    out.update({"ms_per_step": tN, "value": W * H / (tN * 1e-3) / 1e6, "unit": UNIT, "speedup_vs_n1": t1 / tN,
+                "efficiency_vs_n1": t1 / (tN * len(set(devices))), "per_band_ms": [round(x, 4) for x in per],
+                "per_band_kernel_ms_equal_bands": [round(x, 4) for x in per_equal],
+                "per_band_kernel_ms": [round(x, 4) for x in per_compute], "ms_per_step_without_exchange": t_compute,
+                "exchange_exposed_ms": tN - t_compute, "exchange_exposed_frac": (tN - t_compute) / tN,
+                "host_wall_ms_per_step": wall, "boundaries": boundaries, "halo_rows": halo,
+                "scaling": "strong"})
+    return out
+
+
+def leg_view_streams(rank, world, local_rank, dist, steps_per_stream=64, total_streams=48, n_frames=4):
+    """BASELINE config 5: 48 independent 1920x1080 view streams sharded over the GPUs (48 / N handles per GPU, each with its own
+    CUDA stream and its own gradient stream), 64 frames each, no inter-GPU communication.  Returns the `view_streams`
+    object of the JSON line (rank 0) -- device-timed, max over ranks."""
+    import numpy as np
+    import torch
+
+    import synth
+    from raytracedgl1_b200 import denoiser as dn
+    from raytracedgl1_b200 import layout
+
+    W, H, N = 1920, 1080, 4
+    per_gpu = total_streams // world
+    torch.cuda.set_device(local_rank)
+    swappable = {name for name in layout.PRODUCER_IMAGES if name + "_Prev" in layout.IMAGES}
+    handles = [dn.Denoiser(W, H, N, device=local_rank, flags=dn.CREATE_EAGER_GRADIENT_ATROUS) for _ in range(per_gpu)]
+    streams = [(torch.cuda.Stream(), torch.cuda.Stream()) for _ in range(per_gpu)]
+    uniforms = [synth.uniform(W, H, f) for f in range(n_frames)]
+    resident = []                                  # the views share one synthetic sequence (read-only inputs)
+    for f in range(n_frames):
+        g = synth.generate(W, H, f, synth.DEFAULT_SEED + 100 + rank)
+        dev = {}
+        for name in layout.PRODUCER_IMAGES:
+            _, pitch, _, _, rows = handles[0].image(name, 0)
+            row_bytes = g[name].nbytes // rows
+            t = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
+            t[:, :row_bytes].copy_(torch.from_numpy(g[name].view(np.uint8).reshape(rows, row_bytes)))
+            dev[name] = (t, pitch)
+        resident.append(dev)
+    torch.cuda.synchronize()
+
+    def step(i):
+        f, fi = i % n_frames, i & 1
+        for d, (st, gst) in zip(handles, streams):
             for name in layout.PRODUCER_IMAGES:
                 t, pitch = resident[f][name]
-                bd.d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
-            bd.frame(fi, uniforms[f], events=events)
-        return step
+                d.bind_external(name + "_Prev" if (fi == 1 and name in swappable) else name, t.data_ptr(), pitch)
+            d.gradient_samples(fi, uniforms[f], stream=gst.cuda_stream)
+            d.denoise(fi, uniforms[f], stream=st.cuda_stream)
 
-    def kernel_and_exchange_ms(step, first, frames=4):
-        evs = []
-        for i in range(frames):
-            step(first + i, events=evs)
-        torch.cuda.synchronize()
-        return (sum(a.elapsed_time(b) for k, a, b in evs if k == "pass") / frames,
-                sum(a.elapsed_time(b) for k, a, b in evs if k == "exchange") / frames)
-
-    # Rows are not equally expensive (sky pixels skip the a-trous taps, disoccluded ones take the longer variance path),
-    # so equal-height bands leave the cheap ranks waiting in the exchanges.  The band boundaries are therefore taken from
-    # a measured cost profile: run a few frames on equal bands, gather each rank's own kernel time, re-split so that the
-    # bands carry equal time (cost per row constant inside each old band), rebuild, and repeat once.
-    boundaries = bands.band_rows(H, world)
-    calibration = []
-    bd, resident = build(boundaries)
-    step = make_step(bd, resident)
-    if world > 1 and args.band_balance == "measured":
-        for _ in range(2):
-            for i in range(4):
-                step(i)
-            own_ms, _ = kernel_and_exchange_ms(step, 4)
-            t = torch.tensor([own_ms], device="cuda", dtype=torch.float64)
-            every = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(every, t)
-            band_ms = [float(x[0]) for x in every]
-            calibration.append({"band_rows": list(boundaries), "kernel_ms": [round(x, 4) for x in band_ms]})
-            new = bands.rebalanced_rows(boundaries, band_ms, bd.plan.halo)
-            if new == boundaries:
-                break
-            boundaries = new
-            bd.close()
-            del bd, resident, step
-            torch.cuda.empty_cache()
-            bd, resident = build(boundaries)
-            step = make_step(bd, resident)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
+    main = torch.cuda.current_stream()
+    for i in range(4):
         step(i)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    launches0 = bd.d.launch_count
-    sampler.start() if sampler.ok else None
-    e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    e1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
-    launches = bd.d.launch_count - launches0
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    # where a rank's time goes: its own kernels vs waiting in the exchanges (content makes bands unequally expensive)
-    own_ms, exch_ms = kernel_and_exchange_ms(step, args.warmup + args.steps)
-    split = [[own_ms, exch_ms]]
-    rank_ms = [total_ms / args.steps]
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        every = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(every, t)
-        rank_ms = [float(x[0]) / args.steps for x in every]
-        t2 = torch.tensor([own_ms, exch_ms], device="cuda", dtype=torch.float64)
-        every2 = [torch.zeros_like(t2) for _ in range(world)]
-        dist.all_gather(every2, t2)
-        split = [[float(x[0]), float(x[1])] for x in every2]
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for st, gst in streams:
+        st.wait_event(e0); gst.wait_event(e0)
+    for i in range(steps_per_stream):
+        step(4 + i)
+    for st, gst in streams:
+        main.wait_stream(st); main.wait_stream(gst)
+    e1.record(main)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t[0])
-        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(ln)
-        launches = int(ln[0])
-    if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        frame_ms = total_ms / args.steps
-        chain_bpp = dn.chain_bytes_per_pixel(N)
-        gbs = chain_bpp * W * H / (frame_ms * 1e-3) / 1e9
-        exchanges = [x for x in bd.schedule if x[0] == "exchange"]
-        line = {
-            "metric": METRIC, "value": W * H * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": W, "height": H, "atrous_iterations": N,
-                       "parallelism": "%d horizontal bands (rows multiple of 3), %d-row halo, %s schedule: %d neighbour exchanges per frame "
-                                      "(torch.distributed batch_isend_irecv, NCCL)" % (world, bd.plan.halo, "apron" if bd.apron else "per-pass",
-                                                                                       len(exchanges) if world > 1 else 0),
-                       "sequence": "%d consecutive synthetic frames, cycled" % n_frames,
-                       "l2": "no flush: the frame's images exceed the 126 MB L2", "algorithmic_bytes_per_px": chain_bpp},
-            "clocks": clocks, "e2e": None, "gpu_launches": launches,
-            "rank_ms_per_step": [round(x, 4) for x in rank_ms], "band_rows": list(boundaries), "band_calibration": calibration,
-            "rank_kernel_ms_and_exchange_ms": [[round(a, 4), round(b, 4)] for a, b in split],
-            "roofline": {"bound": "hbm", "kernel": "whole chain", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
-                         "frac": gbs / (peak * world), "traffic": None, "peak_source": peak_src + " x n_gpus"},
-            "cpu_baseline": None,
-        }
-        print(json.dumps(line), flush=True)
-    bd.close()
-    if world > 1:
-        dist.destroy_process_group()
+        ms = float(t[0])
+    for d in handles:
+        d.close()
+    del resident
+    torch.cuda.empty_cache()
+    frames = per_gpu * world * steps_per_stream
+    return {"workload": "48 independent 1920x1080 view streams, full chain (4 a-trous iterations), %d frames each, sharded over the GPUs, "
+                        "no inter-GPU communication" % steps_per_stream,
+            "streams": per_gpu * world, "streams_per_gpu": per_gpu, "frames_per_stream": steps_per_stream, "n_gpus": world,
+            "ms_total": ms, "ms_per_frame_per_stream": ms / steps_per_stream / per_gpu, "value": frames * W * H / (ms * 1e-3) / 1e6, "unit": UNIT,
+            "scaling": "strong (48 streams in total)"}
+
+
+def run_bands(args, rank, world, local_rank):
+    """--workload 8k-bands / 4k-bands: the band leg alone, as the line's metric.  One process drives --gpus devices."""
+    if rank != 0:
+        return
+    import torch
+    n = args.gpus
+    if torch.cuda.device_count() < n:
+        raise SystemExit("bench.py: --gpus %d but %d visible" % (n, torch.cuda.device_count()))
+    b = leg_bands(list(range(n)), args.workload, args.steps, args.warmup, n_frames=max(2, min(args.frames, 4) // 2 * 2))
+    W, H, N, desc = WORKLOADS[args.workload]
+    line = {"metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": b["workload"], "width": W, "height": H, "atrous_iterations": N,
+                                            "parallelism": "one frame as %d horizontal bands, one process, peer copies" % n},
+            "bands": b}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -709,23 +771,26 @@ def main():
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frames", type=int, default=32, help="distinct synthetic frames in the cycled sequence (even)")
-    ap.add_argument("--band-balance", default="measured", choices=["measured", "equal"],
-                    help="band workloads: boundaries from a measured per-band cost profile, or equal heights")
-    ap.add_argument("--band-schedule", default="apron", choices=["apron", "per-pass"],
-                    help="band workloads: redundant apron rows + 2 exchanges per frame, or one exchange before each pass")
+    ap.add_argument("--legs", default="bands,view_streams",
+                    help="extra workloads reported in the same line: bands (BASELINE config 4: the 8K frame as bands over the "
+                         "--gpus devices) and view_streams (config 5: 48 x 1080p streams); 'none' to skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the synthetic-input generator and the CPU oracle are OpenMP code and
+    # would take minutes per rank: give every rank its share of the cores (set before anything loads libgomp)
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if world == 1 and args.gpus > 1:
-        raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
     if args.workload.endswith("-bands"):
         run_bands(args, rank, world, local_rank)
         return
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
     run_ours(args, rank, world, local_rank)
 
 

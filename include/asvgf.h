@@ -44,7 +44,11 @@ typedef enum AsvgfResult
     ASVGF_CUDA_ERROR      = 2,
     ASVGF_OUT_OF_MEMORY   = 3,
     ASVGF_UNSUPPORTED     = 4,
-    ASVGF_NOT_BOUND       = 5 /* a pass needs an image that is neither owned nor bound */
+    ASVGF_NOT_BOUND       = 5, /* a pass needs an image that is neither owned nor bound */
+    ASVGF_HALO_EXCEEDED   = 6  /* band handles: a reprojected history tap (temporal pass, gradient samples) lay inside the frame
+                                  but outside the rows the band stores -- motion reached further than bandHaloRows allows, so the
+                                  banded frame is NOT the single-GPU frame.  Reported by asvgfSynchronize / asvgfBandSetSynchronize;
+                                  the motion budget of a halo is bandHaloRows - asvgfBandApronRows(N, ASVGF_PASS_TEMPORAL) rows */
 } AsvgfResult;
 
 typedef enum AsvgfCreateFlagBits
@@ -184,6 +188,35 @@ ASVGF_API AsvgfResult asvgfDownloadTonemapping( AsvgfDenoiser denoiser, AsvgfStr
 /* Blocks the host until everything enqueued on `stream` has finished (= waiting for the frame fence,
    Source/VulkanDevice.cpp:791-796).  Surfaces asynchronous kernel faults as ASVGF_CUDA_ERROR. */
 ASVGF_API AsvgfResult asvgfSynchronize( AsvgfDenoiser denoiser, AsvgfStream stream );
+
+/* ---- one frame across several GPUs (BASELINE config 4; the reference has no multi-GPU path) ----
+   A band set owns one band handle per entry of pDevices -- a device may be listed more than once (several bands on one
+   GPU) -- created with ASVGF_CREATE_BAND_APRON, a stream per band, and the halo exchange between neighbouring bands
+   (peer copies over NVLink, issued behind the producing pass so that they overlap the rest of the frame).  The result is
+   bit-identical to the single-GPU frame as long as per-frame vertical motion stays within the halo
+   (ASVGF_HALO_EXCEEDED otherwise).  The caller fills each band's producer images through the band's handle
+   (asvgfGetImage reports the rows the band stores: its rows plus the halo) on the band's stream. */
+typedef struct AsvgfBandSet_T* AsvgfBandSet;
+typedef struct AsvgfBandSetCreateInfo
+{
+    uint32_t        renderWidth, renderHeight, atrousIterations;
+    uint32_t        flags;              /* ASVGF_CREATE_EXPORT_DEBUG_MASK, ASVGF_CREATE_EXTERNAL_IMAGES                    */
+    uint32_t        deviceCount;        /* number of bands                                                               */
+    const int32_t*  pDevices;           /* CUDA ordinal of every band, top to bottom                                     */
+    const uint32_t* pBandRowBoundaries; /* deviceCount + 1 rows: 0 ... renderHeight, multiples of 3; NULL = equal bands  */
+    uint32_t        bandHaloRows;       /* 0 = apron rows + 48 rows of motion; bands must be at least this tall          */
+} AsvgfBandSetCreateInfo;
+ASVGF_API AsvgfResult asvgfBandSetCreate( const AsvgfBandSetCreateInfo* pInfo, AsvgfBandSet* pSet );
+ASVGF_API AsvgfResult asvgfBandSetDestroy( AsvgfBandSet set );
+ASVGF_API uint32_t    asvgfBandSetGetBandCount( AsvgfBandSet set );
+ASVGF_API AsvgfResult asvgfBandSetGetBand( AsvgfBandSet set, uint32_t band, AsvgfDenoiser* pDenoiser, AsvgfStream* pStream,
+                                           uint32_t* pRowBegin, uint32_t* pRowEnd );
+/* = CalculateGradientsSamples + Denoiser::Denoise of the whole frame.  Enqueues only. */
+ASVGF_API AsvgfResult asvgfBandSetFrame( AsvgfBandSet set, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform );
+ASVGF_API AsvgfResult asvgfBandSetSynchronize( AsvgfBandSet set );
+/* device-side timing of the frames enqueued between the two calls: the longest band interval (and each band's) in ms */
+ASVGF_API AsvgfResult asvgfBandSetBeginTiming( AsvgfBandSet set );
+ASVGF_API AsvgfResult asvgfBandSetEndTiming( AsvgfBandSet set, float* pMaxMilliseconds, float* pPerBandMilliseconds );
 
 /* ASVGF_CREATE_BAND_APRON: rows (full-resolution rows; gradient rows for the gradient a-trous passes) a pass computes
    beyond the owned band.  For ASVGF_PASS_GRADIENT_SAMPLES (computed on owned rows only) it is the depth in gradient

@@ -174,6 +174,7 @@ struct AsvgfDenoiser_T
     bool      haveLut     = false;
     // internal per-frame scratch: the decoded geometry of the current frame (asvgf_atrous_tiled.cuh, k_guide)
     Img       guide{}, centre{};
+    uint32_t* haloMiss = nullptr;  // band handles: device flag set by a reprojected tap outside the stored rows (asvgf_args.cuh)
     bool      centreValid = false; // `centre` holds the weight constants of the frame being denoised (written by a-trous iteration 0)
     // cross-stream ordering of the gradient chain (asvgfGradientSamples may be given another stream than asvgfDenoise):
     // the gradient-sample pass of frame t+1 waits for the temporal pass of frame t, the temporal pass waits for the gradient chain
@@ -266,6 +267,7 @@ AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi,
     a.gradientInputsPrev = d.get( ASVGF_IMAGE_GRADIENT_INPUTS_PREV, fi ); a.isSky = d.get( ASVGF_IMAGE_IS_SKY, fi );
     a.indirAccumPrev = d.get( ASVGF_IMAGE_INDIR_ACCUM_PREV, fi ); a.fwdLum = d.get( ASVGF_IMAGE_FWD_LUM, fi );
     a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
+    a.haloMiss = d.haloMiss;
     ASVGF_LITERAL_OR( d, ( k_gradient_samples<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ),
                       ( k_gradient_samples_fast<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_gradient_samples" );
@@ -319,8 +321,20 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
                            &a.outSpecAccum, &a.outIndirAccum } )
         uniformPitch = uniformPitch && im->pitchT == a.depth.pitchT;
     const dim3 grid = gridFor( ( int )d.W, u.yEnd - u.yBegin );
-    ASVGF_LITERAL_OR( d, ( k_temporal<<< grid, kBlock, 0, s >>>( a, u ) ),
-                      ( uniformPitch ? k_temporal_fast< true ><<< grid, kBlock, 0, s >>>( a, u ) : k_temporal_fast< false ><<< grid, kBlock, 0, s >>>( a, u ) ) );
+    a.haloMiss = d.haloMiss;
+    auto production = [ & ]() {
+        if( d.haloMiss )
+        {
+            if( uniformPitch ) k_temporal_fast< true, true ><<< grid, kBlock, 0, s >>>( a, u );
+            else k_temporal_fast< false, true ><<< grid, kBlock, 0, s >>>( a, u );
+        }
+        else
+        {
+            if( uniformPitch ) k_temporal_fast< true, false ><<< grid, kBlock, 0, s >>>( a, u );
+            else k_temporal_fast< false, false ><<< grid, kBlock, 0, s >>>( a, u );
+        }
+    };
+    ASVGF_LITERAL_OR( d, ( k_temporal<<< grid, kBlock, 0, s >>>( a, u ) ), production() );
     return launchCheck( d, "k_temporal" );
 }
 
@@ -772,6 +786,14 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(centre plane)" );
         }
         setImgStorage( c, memC, pitch, 16 );
+        if( pInfo->bandRowEnd != 0 )
+        {
+            if( cudaMalloc( ( void** )&d->haloMiss, sizeof( uint32_t ) ) != cudaSuccess || cudaMemset( d->haloMiss, 0, sizeof( uint32_t ) ) != cudaSuccess )
+            {
+                asvgfDestroy( d );
+                return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(halo flag)" );
+            }
+        }
     }
     *pDenoiser = d;
     return ASVGF_SUCCESS;
@@ -786,6 +808,7 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
     if( d->haveLut ) releaseLut( d->device );
     if( d->guide.p ) cudaFree( d->guide.p );
     if( d->centre.p ) cudaFree( d->centre.p );
+    if( d->haloMiss ) cudaFree( d->haloMiss );
     if( d->evTemporalDone ) cudaEventDestroy( d->evTemporalDone );
     if( d->evGradientsDone ) cudaEventDestroy( d->evGradientsDone );
     if( d->log2Half ) cudaFree( d->log2Half );
@@ -1030,6 +1053,16 @@ AsvgfResult asvgfSynchronize( AsvgfDenoiser d, AsvgfStream stream )
     if( !d ) return fail( ASVGF_WRONG_ARGUMENT, "null denoiser" );
     DeviceGuard guard( d->device );
     CUDA_TRY( cudaStreamSynchronize( ( cudaStream_t )stream ) );
+    if( d->haloMiss )
+    {
+        uint32_t miss = 0;
+        CUDA_TRY( cudaMemcpy( &miss, d->haloMiss, sizeof( miss ), cudaMemcpyDeviceToHost ) );
+        if( miss )
+        {
+            CUDA_TRY( cudaMemset( d->haloMiss, 0, sizeof( miss ) ) );
+            return fail( ASVGF_HALO_EXCEEDED, "a motion vector reached beyond the band's halo rows: the banded frame differs from the single-GPU frame (recreate with a larger bandHaloRows)" );
+        }
+    }
     return ASVGF_SUCCESS;
 }
 
@@ -1086,9 +1119,12 @@ const char* asvgfResultString( AsvgfResult r )
         case ASVGF_OUT_OF_MEMORY: return "ASVGF_OUT_OF_MEMORY";
         case ASVGF_UNSUPPORTED: return "ASVGF_UNSUPPORTED";
         case ASVGF_NOT_BOUND: return "ASVGF_NOT_BOUND";
+        case ASVGF_HALO_EXCEEDED: return "ASVGF_HALO_EXCEEDED";
         default: return "ASVGF_?";
     }
 }
 const char* asvgfLastErrorMessage( void ) { return g_lastError.c_str(); }
 
 } // extern "C"
+
+#include "asvgf_bandset.inl"

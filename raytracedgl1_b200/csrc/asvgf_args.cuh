@@ -15,6 +15,9 @@ struct GradientSamplesArgs
 {
     Img     gradientPrevPix, disPing, disHistory, motion, gradientInputsPrev, isSky, indirAccumPrev, fwdLum;
     int32_t gyBegin, gyEnd; // gradient rows to compute
+    // band handles: set to 1 when a reprojected tap lies inside the frame but outside the rows this band stores (the motion
+    // reached beyond the halo: the band would silently diverge from the single-GPU frame); nullptr on whole-frame handles
+    uint32_t* haloMiss;
 };
 
 // GA: gradient a-trous, CmASVGFGradientAtrous.comp:42-105
@@ -35,6 +38,7 @@ struct TemporalArgs
     NormalLut lut;
     int32_t   writeMask;
     int32_t   writeGuide;    // this launch covers every row the a-trous iterations will read: write the guide plane here
+    uint32_t* haloMiss;      // band handles: see GradientSamplesArgs
 };
 
 // F: anti-firefly, CmAntiFirefly.comp:47-159

@@ -442,10 +442,12 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
             *atW< float4 >( a.centre, px, py ) = make_float4( s.kLum, s.invK1, s.invK2, s.P );
         }
     };
-    auto finish = [ & ]( AtrousPix& s, int py ) {
-        if( s.invalid )
+    auto finish = [ & ]( AtrousPix& s, int py, int ce ) {
+        if( s.invalid ) // :96-99 pass-through of the centre (iteration 0, Iter0.comp:208-216: zeros); in the pair form the sums may hold taps
         {
-            if( ITER0 ) { s.variance = 0.0f; s.diff = s.spec = s.indir = make_float3( 0.0f, 0.0f, 0.0f ); } // else pass-through of the centre
+            const float4 cB = sB[ ce ], cC = sC[ ce ], cD = sD[ ce ];
+            s.diff = make_float3( cB.x, cB.y, cB.z ); s.variance = cB.w; s.spec = make_float3( cC.x, cC.y, cC.z ); s.indir = make_float3( cD.x, cD.y, cD.z );
+            if( ITER0 ) { s.variance = 0.0f; s.diff = s.spec = s.indir = make_float3( 0.0f, 0.0f, 0.0f ); }
         }
         else s.normalise();
         atrousStore< LAST >( a, u, px, py, s.diff, s.variance, s.spec, s.indir );
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
                         s.tap( sA[ qe ], sB[ qe ], sC[ qe ], sD[ qe ], diag, in ? ( diag ? -2.0f : -1.0f ) : NINF );
                     }
             }
-            finish( s, py );
+            finish( s, py, ce );
         }
     }
     else
@@ -516,8 +518,8 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
                     }
                 }
         }
-        finish( s0, py0 );
-        if( have1 ) finish( s1, py1 );
+        finish( s0, py0, ce0 );
+        if( have1 ) finish( s1, py1, ce1 );
     }
 }
 

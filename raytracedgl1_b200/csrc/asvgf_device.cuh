@@ -183,7 +183,8 @@ ASVGF_DEVICE float3 decodeNormal( const NormalLut& lut, uint32_t p ) // Utils.h:
 }
 
 // ---- image access: out-of-image fetch -> 0, out-of-image store discarded ----
-ASVGF_DEVICE bool inImage( const Img& im, int x, int y ) { return ( unsigned )x < ( unsigned )im.w && ( unsigned )y < ( unsigned )im.h; }
+// inside the frame AND inside the rows this handle stores (a band handle holds rows [row0, row0 + rows) only)
+ASVGF_DEVICE bool inImage( const Img& im, int x, int y ) { return ( unsigned )x < ( unsigned )im.w && ( unsigned )y < ( unsigned )im.h && ( unsigned )( y - im.row0 ) < ( unsigned )im.rows; }
 template< typename T > ASVGF_DEVICE const T* texel( const Img& im, int x, int y )
 {
     return reinterpret_cast< const T* >( im.p + ( size_t )( y - im.row0 ) * im.pitch ) + x;

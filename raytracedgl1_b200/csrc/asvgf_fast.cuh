@@ -161,6 +161,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples_fast( c
         const float  fy = mulr( addr( mulr( addr( ( float )cy, 0.5f ), u.invH ), m.y ), u.renderHeight );
         ppx[ k ] = f2i( floorf( fx ) ); ppy[ k ] = f2i( floorf( fy ) );
         lum[ k ] = ldIf< uint32_t >( a.gradientInputsPrev, ppx[ k ], ppy[ k ], ( uint32_t )k != prevStrataPos && full.in( ppx[ k ], ppy[ k ] ), 0u );
+        if( a.haloMiss && ( unsigned )ppx[ k ] < ( unsigned )u.W && ( unsigned )ppy[ k ] < ( unsigned )u.H && !full.in( ppx[ k ], ppy[ k ] ) ) atomicOr( a.haloMiss, 1u );
     }
     int      prevX = 0, prevY = 0, curX = 0, curY = 0;
     uint32_t curStrataPos = 0;

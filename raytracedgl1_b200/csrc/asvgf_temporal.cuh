@@ -46,7 +46,7 @@ template< bool UNIFORM, typename T > ASVGF_DEVICE T ldOff( const Img& im, uint32
 // encN = the centre pixel's packed normal: a tap with the same bits decodes to the same unit vector, whose dot product with
 // itself is 1 up to rounding, i.e. > 0.95 -- when all four taps match (flat surfaces, most pixels) the sin/cos gathers are
 // skipped; the result is identical by construction.
-template< bool UNIFORM >
+template< bool UNIFORM, bool BAND >
 ASVGF_DEVICE uint32_t consistency2x2( const TemporalArgs& a, const Rows& rows, uint32_t pitchT, int bx, int by, int ax0, int ax1, int H, float depth, float motionZ,
                                       float3 normal, uint32_t encN, uint32_t& off00 )
 {
@@ -58,6 +58,7 @@ ASVGF_DEVICE uint32_t consistency2x2( const TemporalArgs& a, const Rows& rows, u
     {
         const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
         in[ t ] = y >= 0 && y < H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
+        if( BAND && !in[ t ] && y >= 0 && y < H && x >= ax0 && x < ax1 ) atomicOr( a.haloMiss, 1u ); // a tap of the frame this band does not hold
         const uint32_t o = off00 + ( t & 1 ) + ( t >> 1 ) * pitchT;
         dz[ t ] = ldOff< UNIFORM, uint16_t >( a.depthPrev, o, x, y, in[ t ], ( uint16_t )0 );
         en[ t ] = ldOff< UNIFORM, uint32_t >( a.normalPrev, o, x, y, in[ t ], encN ); // taps outside never count: let them match
@@ -127,7 +128,7 @@ ASVGF_DEVICE void reproject( const Uniform& u, int px, int py, float mx, float m
     bw[ 0 ] = mulr( ox, oy ); bw[ 1 ] = mulr( sx, oy ); bw[ 2 ] = mulr( ox, sy ); bw[ 3 ] = mulr( sx, sy );
 }
 
-template< bool UNIFORM >
+template< bool UNIFORM, bool BAND >
 __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_temporal_fast( const __grid_constant__ TemporalArgs a, const __grid_constant__ Uniform u )
 {
     const int px = blockIdx.x * kBlockW + threadIdx.x;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
     float bw[ 4 ];
     reproject( u, px, py, mot01.x, mot01.y, pixPrevX, pixPrevY, bw );
     uint32_t o00;
-    uint32_t mask = consistency2x2< UNIFORM >( a, rows, pitchT, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal, nv32, o00 );
+    uint32_t mask = consistency2x2< UNIFORM, BAND >( a, rows, pitchT, pixPrevX, pixPrevY, ax0, ax1, u.H, depth, motionZ, normal, nv32, o00 );
 
     // ---- history of the consistent taps: all in flight together; a rejected tap reads as zeros and weighs 0 ----
     uint2    hDiff[ 4 ], hLen[ 4 ];
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
         bw[ t ]    = ok ? bw[ t ] : 0.0f;
     }
     const bool   sppOk = rows.in( pixPrevX, pixPrevY );
+    if( BAND && !sppOk && ( unsigned )pixPrevX < ( unsigned )u.W && ( unsigned )pixPrevY < ( unsigned )u.H ) atomicOr( a.haloMiss, 1u );
     const float4 spp4  = ldOff< UNIFORM, float4 >( a.surfPosPrev, o00, pixPrevX, pixPrevY, sppOk, make_float4( 0.0f, 0.0f, 0.0f, 0.0f ) );
 
     float4 historyLengthDIS = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH, ASVGF_T_MIN_CTAS ) k_tempor
         uint32_t oSpec;
         const uint32_t vbits = ( pixPrevSpecX == pixPrevX && pixPrevSpecY == pixPrevY )
                                    ? ( mask & 15u )
-                                   : consistency2x2< UNIFORM >( a, rows, pitchT, pixPrevSpecX, pixPrevSpecY, ax0, ax1, u.H, depth, motionZ, normal, nv32, oSpec );
+                                   : consistency2x2< UNIFORM, BAND >( a, rows, pitchT, pixPrevSpecX, pixPrevSpecY, ax0, ax1, u.H, depth, motionZ, normal, nv32, oSpec );
         float weightSumVirtual = 0.0f;
 #pragma unroll
         for( int t = 0; t < 4; t++ ) weightSumVirtual = addr( weightSumVirtual, ( ( vbits >> t ) & 1u ) ? bws[ t ] : 0.0f );

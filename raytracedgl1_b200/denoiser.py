@@ -17,7 +17,7 @@ from . import layout
 _LIB_PATH = os.environ.get("ASVGF_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libasvgf.so")  # ASVGF_LIB: A/B builds
 _lib = None
 
-SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND = range(6)
+SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND, HALO_EXCEEDED = range(7)
 CREATE_EXPORT_DEBUG_MASK = 1 << 0
 CREATE_EXTERNAL_IMAGES = 1 << 1
 CREATE_LITERAL_KERNELS = 1 << 2
@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = [
     "asvgfLastErrorMessage", "asvgfPassKernelName", "asvgfBandApronRows", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
     "asvgfLuminanceAverage", "asvgfGetTonemappingBuffer", "asvgfUploadTonemapping", "asvgfDownloadTonemapping",
     "asvgfScatterAccumulate",
+    "asvgfBandSetCreate", "asvgfBandSetDestroy", "asvgfBandSetGetBandCount", "asvgfBandSetGetBand", "asvgfBandSetFrame",
+    "asvgfBandSetSynchronize", "asvgfBandSetBeginTiming", "asvgfBandSetEndTiming",
 ]
 
 
@@ -38,6 +40,12 @@ class CreateInfo(ctypes.Structure):
     _fields_ = [("renderWidth", ctypes.c_uint32), ("renderHeight", ctypes.c_uint32),
                 ("atrousIterations", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("device", ctypes.c_int32),
                 ("bandRowBegin", ctypes.c_uint32), ("bandRowEnd", ctypes.c_uint32), ("bandHaloRows", ctypes.c_uint32)]
+
+
+class BandSetCreateInfo(ctypes.Structure):
+    _fields_ = [("renderWidth", ctypes.c_uint32), ("renderHeight", ctypes.c_uint32), ("atrousIterations", ctypes.c_uint32),
+                ("flags", ctypes.c_uint32), ("deviceCount", ctypes.c_uint32), ("pDevices", ctypes.POINTER(ctypes.c_int32)),
+                ("pBandRowBoundaries", ctypes.POINTER(ctypes.c_uint32)), ("bandHaloRows", ctypes.c_uint32)]
 
 
 class AsvgfError(RuntimeError):
@@ -87,6 +95,15 @@ def lib():
         L.asvgfPassKernelName.restype = ctypes.c_char_p
         L.asvgfPassBytesPerPixel.argtypes = [u32, u32]
         L.asvgfPassBytesPerPixel.restype = ctypes.c_double
+        L.asvgfBandSetCreate.argtypes = [ctypes.POINTER(BandSetCreateInfo), ctypes.POINTER(vp)]
+        L.asvgfBandSetDestroy.argtypes = [vp]
+        L.asvgfBandSetGetBandCount.argtypes = [vp]
+        L.asvgfBandSetGetBandCount.restype = u32
+        L.asvgfBandSetGetBand.argtypes = [vp, u32, ctypes.POINTER(vp), ctypes.POINTER(vp), pu32, pu32]
+        L.asvgfBandSetFrame.argtypes = [vp, u32, puni]
+        L.asvgfBandSetSynchronize.argtypes = [vp]
+        L.asvgfBandSetBeginTiming.argtypes = [vp]
+        L.asvgfBandSetEndTiming.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         L.asvgfResultString.argtypes = [ctypes.c_int]
         L.asvgfResultString.restype = ctypes.c_char_p
         L.asvgfLastErrorMessage.restype = ctypes.c_char_p
@@ -121,16 +138,21 @@ def chain_bytes_per_pixel(iterations=4, with_gradient_samples=True):
 class Denoiser:
     """One view stream (= one RTGL1 instance's Denoiser + its Framebuffers)."""
 
-    def __init__(self, width, height, atrous_iterations=4, flags=0, device=-1, band=None, halo_rows=0):
+    def __init__(self, width, height, atrous_iterations=4, flags=0, device=-1, band=None, halo_rows=0, _borrowed=None):
         self._h = ctypes.c_void_p()
+        self._owns = _borrowed is None
         self.width, self.height, self.iterations = width, height, atrous_iterations
+        if _borrowed is not None:          # a band handle that belongs to a BandSet
+            self._h = ctypes.c_void_p(_borrowed)
+            return
         info = CreateInfo(width, height, atrous_iterations, flags, device,
                           band[0] if band else 0, band[1] if band else 0, halo_rows)
         _check(lib().asvgfCreate(ctypes.byref(info), ctypes.byref(self._h)), "asvgfCreate")
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().asvgfDestroy(self._h)
+            if self._owns:
+                lib().asvgfDestroy(self._h)
             self._h = ctypes.c_void_p()
 
     __del__ = close
@@ -224,3 +246,79 @@ class Denoiser:
     @property
     def launch_count(self):
         return lib().asvgfGetLaunchCount(self._h)
+
+
+class BandSet:
+    """One frame split into horizontal bands across GPUs (include/asvgf.h, asvgfBandSet*): a band handle, a stream and the
+    halo pushes per entry of `devices` (a device may repeat: several bands on one GPU)."""
+
+    def __init__(self, width, height, devices, atrous_iterations=4, flags=0, boundaries=None, halo_rows=0):
+        self._h = ctypes.c_void_p()
+        self.width, self.height, self.iterations = width, height, atrous_iterations
+        n = len(devices)
+        dev = (ctypes.c_int32 * n)(*devices)
+        bnd = (ctypes.c_uint32 * (n + 1))(*boundaries) if boundaries is not None else None
+        info = BandSetCreateInfo(width, height, atrous_iterations, flags, n, dev,
+                                 ctypes.cast(bnd, ctypes.POINTER(ctypes.c_uint32)) if bnd is not None else None, halo_rows)
+        _check(lib().asvgfBandSetCreate(ctypes.byref(info), ctypes.byref(self._h)), "asvgfBandSetCreate")
+        self.bands = []
+        for k in range(n):
+            h, st, r0, r1 = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint32(), ctypes.c_uint32()
+            _check(lib().asvgfBandSetGetBand(self._h, k, ctypes.byref(h), ctypes.byref(st), ctypes.byref(r0), ctypes.byref(r1)),
+                   "asvgfBandSetGetBand")
+            d = Denoiser(width, height, atrous_iterations, _borrowed=h.value)
+            self.bands.append({"denoiser": d, "stream": st.value or 0, "rows": (r0.value, r1.value), "device": devices[k]})
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            for b in self.bands:
+                b["denoiser"].close()
+            lib().asvgfBandSetDestroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def stored_rows(self, k, name, frame_index=0):
+        """(first stored row, number of stored rows) of an image of band k: its rows plus the halo."""
+        _, _, _, r0, rows = self.bands[k]["denoiser"].image(name, frame_index)
+        return r0, rows
+
+    def upload(self, name, frame_index, full_image):
+        """full_image: numpy array of the WHOLE frame; every band gets the rows it stores, on its own stream."""
+        for k, b in enumerate(self.bands):
+            r0, rows = self.stored_rows(k, name, frame_index)
+            b["denoiser"].upload(name, frame_index, np.ascontiguousarray(full_image[r0:r0 + rows]), stream=b["stream"])
+        # (the host arrays above are temporaries: finish the copies before they go away)
+        for b in self.bands:
+            lib().asvgfSynchronize(b["denoiser"]._h, b["stream"])
+
+    def download(self, name, frame_index):
+        """The whole frame, assembled from the rows every band OWNS."""
+        dtype, shape = layout.image_numpy_shape(name, self.width, self.height)
+        third = layout.IMAGES[name][2] if isinstance(name, str) else False
+        out = np.zeros(shape, dtype=dtype)
+        for k, b in enumerate(self.bands):
+            r0, rows = self.stored_rows(k, name, frame_index)
+            a = b["denoiser"].download(name, frame_index, stream=b["stream"])
+            o0, o1 = b["rows"]
+            if third:
+                o0, o1 = o0 // 3, (shape[0] if o1 == self.height else o1 // 3)
+            out[o0:o1] = a[o0 - r0:o1 - r0]
+        return out
+
+    def frame(self, frame_index, uniform):
+        """= CalculateGradientsSamples + Denoiser::Denoise of the whole frame (enqueues only)."""
+        _check(lib().asvgfBandSetFrame(self._h, frame_index, ctypes.byref(uniform)), "asvgfBandSetFrame")
+
+    def synchronize(self):
+        _check(lib().asvgfBandSetSynchronize(self._h), "asvgfBandSetSynchronize")
+
+    def begin_timing(self):
+        _check(lib().asvgfBandSetBeginTiming(self._h), "asvgfBandSetBeginTiming")
+
+    def end_timing(self):
+        """(longest band interval, [each band's interval]) in milliseconds since begin_timing()."""
+        worst = ctypes.c_float()
+        per = (ctypes.c_float * len(self.bands))()
+        _check(lib().asvgfBandSetEndTiming(self._h, ctypes.byref(worst), per), "asvgfBandSetEndTiming")
+        return worst.value, list(per)

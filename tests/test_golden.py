@@ -36,7 +36,7 @@ def test_oracle_reproduces_reference_shader_fixtures():
 def test_cuda_path_matches_reference_shader_fixtures():
     """Every frame from the fixture's own frame-start state (the previous frame's reference outputs)."""
     import synth
-    from _harness import compare_image, OUTLIER_FACTOR, OUTLIER_FRAC
+    from _harness import compare_image, OUTLIER_FACTOR, OUTLIER_FRAC, branch_flip_allowance
     from raytracedgl1_b200 import denoiser as dn
     from raytracedgl1_b200 import layout
     ref = np.load(mg.PATH)
@@ -63,10 +63,10 @@ def test_cuda_path_matches_reference_shader_fixtures():
                 if n == "AtrousFilteredVariance":   # a luminance standard deviation: tolerance relative to luminance
                     lum = layout.luminance(np.abs(ref["f%d_DiffColorHistory" % f][..., :3].astype(np.float32)))
                 r = compare_image(n, ref["f%d_%s" % (f, n)], d.download(n, fi), outlier_factor=OUTLIER_FACTOR,
-                                  outlier_frac=OUTLIER_FRAC, lum_scale=lum)
+                                  outlier_frac=OUTLIER_FRAC, lum_scale=lum, bad_allow=branch_flip_allowance(mg.W * mg.H))
                 assert r["ok"], (f, n, r)
                 if r["kind"] == "int":
-                    assert r["n_bad"] == 0, (f, n)
+                    assert r["n_bad"] == 0, (f, n)      # GradientPrevPix exact; DebugMask bits 0-4 exact (bit 5: _harness.py)
             # the post dispatches are bit-exact by construction: run them on the fixture's own PreFinal / HistogramInput
             for n in ("PreFinal", "HistogramInput"):
                 d.upload(n, fi, np.ascontiguousarray(ref["f%d_%s" % (f, n)]))
