@@ -183,7 +183,7 @@ struct AsvgfDenoiser_T
     bool        gradientAtrousDone = false; // ASVGF_CREATE_EAGER_GRADIENT_ATROUS: the chain already ran behind the gradient samples
     bool        guideValid = false;         // the guide plane matches the geometry images of the frame being denoised
     uint64_t  launchCount = 0;
-    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 4 ] = {}; // cudaFuncSetAttribute done for (iteration, composing + 2 * pair)
+    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 8 ] = {}; // cudaFuncSetAttribute done for (iteration, composing + 2 * pair + 4 * centre)
     bool      atrousPair = true; // a thread filters two vertically adjacent pixels together (ASVGF_ATROUS_PAIR=0: one after the other)
     int       smCount     = 0;
     int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
@@ -448,13 +448,15 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         return cudaSuccess;
     };
     cudaError_t e = cudaErrorInvalidValue;
-    bool&       opted = d.atrousOptIn[ iteration ][ ( last ? 1 : 0 ) + ( pair ? 2 : 0 ) ];
-#define ASVGF_ATROUS_LAUNCH( S, I0, L ) ( pair ? launch( k_atrous_tiled< S, I0, L, true >, opted ) : launch( k_atrous_tiled< S, I0, L, false >, opted ) )
+    const bool  centre = a.centreValid != 0 && iteration > 0;
+    bool&       opted = d.atrousOptIn[ iteration ][ ( last ? 1 : 0 ) + ( pair ? 2 : 0 ) + ( centre ? 4 : 0 ) ];
+#define ASVGF_ATROUS_LAUNCH2( S, I0, L, C ) ( pair ? launch( k_atrous_tiled< S, I0, L, true, C >, opted ) : launch( k_atrous_tiled< S, I0, L, false, C >, opted ) )
+#define ASVGF_ATROUS_LAUNCH( S, I0, L ) ( centre ? ASVGF_ATROUS_LAUNCH2( S, I0, L, true ) : ASVGF_ATROUS_LAUNCH2( S, I0, L, false ) )
 #define ASVGF_ATROUS_CASE( S ) \
     case S: e = last ? ASVGF_ATROUS_LAUNCH( S, false, true ) : ASVGF_ATROUS_LAUNCH( S, false, false ); break;
     switch( step )
     {
-        case 1: e = ASVGF_ATROUS_LAUNCH( 1, true, false ); break; // iteration 0 is never the last (atrousIterations >= 2)
+        case 1: e = ASVGF_ATROUS_LAUNCH2( 1, true, false, false ); break; // iteration 0 is never the last (atrousIterations >= 2)
         ASVGF_ATROUS_CASE( 2 )
         ASVGF_ATROUS_CASE( 4 )
         ASVGF_ATROUS_CASE( 8 )
@@ -466,6 +468,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     }
 #undef ASVGF_ATROUS_CASE
 #undef ASVGF_ATROUS_LAUNCH
+#undef ASVGF_ATROUS_LAUNCH2
     if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_tiled)" );
     return launchCheck( d, "k_atrous_tiled" );
 }

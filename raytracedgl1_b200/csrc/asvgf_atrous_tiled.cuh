@@ -363,7 +363,8 @@ ASVGF_DEVICE void atrousStore( const AtrousArgs& a, const Uniform& u, int px, in
 #ifndef ASVGF_AT_PAIR_MIN_CTAS
     #define ASVGF_AT_PAIR_MIN_CTAS 3
 #endif
-template< int STEP, bool ITER0, bool LAST, bool PAIR >
+// CENTRE = true (iterations >= 1 inside asvgfDenoise): the per-pixel weight constants come from the plane iteration 0 wrote.
+template< int STEP, bool ITER0, bool LAST, bool PAIR, bool CENTRE >
 __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
     extern __shared__ __align__( 128 ) uint8_t smemRaw[];
@@ -388,20 +389,15 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
     const int px = xBase + c;
 
     // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----
-    // iterations >= 1 read the constants iteration 0 derived (one 16-byte load) unless the plane is stale (a.centreValid)
-    const bool useCentre = !ITER0 && a.centreValid;
+    static_assert( !( ITER0 && CENTRE ), "iteration 0 writes the centre plane" );
     uint16_t cGrad[ PIX ], cSigma[ PIX ], cSpecLen[ PIX ];
-    float4   cK[ PIX ];
-#pragma unroll
-    for( int k = 0; k < PIX; k++ )
+    if constexpr( !CENTRE )
     {
-        const int  py = yBase + jOf( k ) * STEP;
-        const bool ok = px < u.W && py < u.yEnd;
-        cK[ k ] = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-        cGrad[ k ] = cSpecLen[ k ] = cSigma[ k ] = 0;
-        if( useCentre ) cK[ k ] = ldIf< float4 >( a.centre, px, py, ok, make_float4( 0.0f, 0.0f, 0.0f, 0.0f ) );
-        else
+#pragma unroll
+        for( int k = 0; k < PIX; k++ )
         {
+            const int  py = yBase + jOf( k ) * STEP;
+            const bool ok = px < u.W && py < u.yEnd;
             cGrad[ k ]    = ldIf< uint16_t >( a.depthGrad, px, py, ok, ( uint16_t )0 );
             cSpecLen[ k ] = ok ? __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.histLen, px, py ) ) + 2 ) : ( uint16_t )0; // .b of rgba16f
             cSigma[ k ]   = ITER0 ? ( uint16_t )0 : ldIf< uint16_t >( a.filteredVariance, px, py, ok, ( uint16_t )0 );
@@ -422,6 +418,7 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
 
     // Iter0.comp:158-187: 3x3 Gaussian {1/4,1/8,1/16} of the variance (products by powers of two are exact)
     auto sigmaOf = [ & ]( int ce, int k ) {
+        if constexpr( CENTRE ) return 0.0f;
         if( !ITER0 ) return h2f( cSigma[ k ] );
         float r = 0.0f;
 #pragma unroll
@@ -433,13 +430,20 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
     };
     // centre of pixel k at slot ce: derive (or fetch) the weight constants; iteration 0 publishes them and the filtered sigma
     auto begin = [ & ]( AtrousPix& s, int ce, int k, int py, bool inFrame ) {
-        if( useCentre ) { s.initFromCentre( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], cK[ k ], a.iteration ); return; }
-        const float sigmaL = sigmaOf( ce, k );
-        s.init( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], h2f( cGrad[ k ] ), sigmaL, h2f( cSpecLen[ k ] ), a.iteration );
-        if( ITER0 && inFrame )
+        if constexpr( CENTRE )
         {
-            if( !s.invalid ) *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( sigmaL );
-            *atW< float4 >( a.centre, px, py ) = make_float4( s.kLum, s.invK1, s.invK2, s.P );
+            const float4 cK = inFrame ? __ldg( at< float4 >( a.centre, px, py ) ) : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+            s.initFromCentre( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], cK, a.iteration );
+        }
+        else
+        {
+            const float sigmaL = sigmaOf( ce, k );
+            s.init( sA[ ce ], sB[ ce ], sC[ ce ], sD[ ce ], h2f( cGrad[ k ] ), sigmaL, h2f( cSpecLen[ k ] ), a.iteration );
+            if( ITER0 && inFrame )
+            {
+                if( !s.invalid ) *atW< uint16_t >( a.filteredVariance, px, py ) = f2h( sigmaL );
+                *atW< float4 >( a.centre, px, py ) = make_float4( s.kLum, s.invK1, s.invK2, s.P );
+            }
         }
     };
     auto finish = [ & ]( AtrousPix& s, int py, int ce ) {

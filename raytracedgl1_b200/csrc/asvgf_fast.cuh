@@ -121,7 +121,7 @@ ASVGF_DEVICE bool quotientBelowTenth( float a, float b )
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// G: gradient samples.  Integer outputs (slot, positions) exact; alpha arithmetic fast.
+// G: gradient samples.  Bit-exact: slot, positions and the unorm8 alphas.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples_fast( const __grid_constant__ GradientSamplesArgs a, const __grid_constant__ Uniform u )
 {
@@ -190,23 +190,24 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples_fast( c
     }
     const float2 fwd = fetchRG16F( a.fwdLum, curX, curY );
 
-    auto antilag = []( float gradSample, float normFactor ) { return normFactor > 0.0001f ? saturatef( fabsf( gradSample ) * frcp( normFactor ) ) : 0.0f; };
-    float gD = antilag( fwd.x - prevLum.x, fmaxf( fwd.x, prevLum.x ) );
+    // the three anti-lag alphas in the oracle's explicitly rounded operation order (RtGradients.rgen:139-177): the unorm8 codes
+    // stored here feed (1 - alpha)^10 in the temporal pass, where one code of difference is a 4 % change of the history length --
+    // so this pass is bit-exact, like the gradient a-trous passes behind it (1/9 of the pixels: the IEEE divisions cost nothing)
+    float gD = antilagAlpha( subr( fwd.x, prevLum.x ), fmaxf( fwd.x, prevLum.x ) );
     float gI;
     {
-        float       gradSample = fmaxf( 0.0f, prevLum.x - fwd.x );
-        const float brightness = flum( fetchE5( a.indirAccumPrev, prevX, prevY ) );
-        const float t          = saturatef( ( brightness - 1.0f ) * ( 1.0f / 9.0f ) );
-        gradSample *= 1.0f - t * t * ( 3.0f - 2.0f * t );
-        gI = antilag( gradSample, fmaxf( fwd.x, prevLum.x ) );
+        float       gradSample = fmaxf( 0.0f, subr( prevLum.x, fwd.x ) );
+        const float brightness = luminance( fetchE5( a.indirAccumPrev, prevX, prevY ) );
+        gradSample             = mulr( gradSample, subr( 1.0f, smoothstepr( 1.0f, 10.0f, brightness ) ) );
+        gI                     = antilagAlpha( gradSample, fmaxf( fwd.x, prevLum.x ) );
     }
-    float gS = antilag( fwd.y - prevLum.y, fmaxf( fwd.y, prevLum.y ) );
-    gD *= u.gradientMult[ 0 ]; gI *= u.gradientMult[ 1 ]; gS *= u.gradientMult[ 2 ];
+    float gS = antilagAlpha( subr( fwd.y, prevLum.y ), fmaxf( fwd.y, prevLum.y ) );
+    gD = mulr( gD, u.gradientMult[ 0 ] ); gI = mulr( gI, u.gradientMult[ 1 ] ); gS = mulr( gS, u.gradientMult[ 2 ] );
     {
         const uint32_t h = fetchU32( a.disHistory, prevX / S, prevY / S ); // prevX,prevY >= 0 here
-        gD = 0.5f * gD + 0.5f * unorm8ToFloatFast( h & 0xffu );
-        gI = 0.5f * gI + 0.5f * unorm8ToFloatFast( ( h >> 8 ) & 0xffu );
-        gS = 0.5f * gS + 0.5f * unorm8ToFloatFast( ( h >> 16 ) & 0xffu );
+        gD = mixr( gD, unorm8ToFloat( h & 0xffu ), 0.5f );
+        gI = mixr( gI, unorm8ToFloat( ( h >> 8 ) & 0xffu ), 0.5f );
+        gS = mixr( gS, unorm8ToFloat( ( h >> 16 ) & 0xffu ), 0.5f );
     }
     *outGrad = floatToUnorm8( gD ) | ( floatToUnorm8( gI ) << 8 ) | ( floatToUnorm8( gS ) << 16 );
     *outSlot = ( uint8_t )curStrataPos;
