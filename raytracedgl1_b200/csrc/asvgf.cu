@@ -184,6 +184,7 @@ struct AsvgfDenoiser_T
     bool        guideValid = false;         // the guide plane matches the geometry images of the frame being denoised
     uint64_t  launchCount = 0;
     bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 8 ] = {}; // cudaFuncSetAttribute done for (iteration, composing + 2 * pair + 4 * centre)
+    bool      atrousCentre = true; // iterations >= 1 read the weight constants iteration 0 published (ASVGF_ATROUS_CENTRE=0: re-derive them)
     bool      atrousPair = true; // a thread filters two vertically adjacent pixels together (ASVGF_ATROUS_PAIR=0: one after the other)
     int       smCount     = 0;
     int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
@@ -448,7 +449,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         return cudaSuccess;
     };
     cudaError_t e = cudaErrorInvalidValue;
-    const bool  centre = a.centreValid != 0 && iteration > 0;
+    const bool  centre = a.centreValid != 0 && iteration > 0 && d.atrousCentre;
     bool&       opted = d.atrousOptIn[ iteration ][ ( last ? 1 : 0 ) + ( pair ? 2 : 0 ) + ( centre ? 4 : 0 ) ];
 #define ASVGF_ATROUS_LAUNCH2( S, I0, L, C ) ( pair ? launch( k_atrous_tiled< S, I0, L, true, C >, opted ) : launch( k_atrous_tiled< S, I0, L, false, C >, opted ) )
 #define ASVGF_ATROUS_LAUNCH( S, I0, L ) ( centre ? ASVGF_ATROUS_LAUNCH2( S, I0, L, true ) : ASVGF_ATROUS_LAUNCH2( S, I0, L, false ) )
@@ -667,6 +668,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     d->info = *pInfo; d->device = device;
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     if( const char* e = std::getenv( "ASVGF_ATROUS_PAIR" ) ) d->atrousPair = std::atoi( e ) != 0;
+    if( const char* e = std::getenv( "ASVGF_ATROUS_CENTRE" ) ) d->atrousCentre = std::atoi( e ) != 0;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
     if( pInfo->bandRowEnd == 0 )

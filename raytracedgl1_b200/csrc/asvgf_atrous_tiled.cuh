@@ -391,7 +391,17 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
     // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----
     static_assert( !( ITER0 && CENTRE ), "iteration 0 writes the centre plane" );
     uint16_t cGrad[ PIX ], cSigma[ PIX ], cSpecLen[ PIX ];
-    if constexpr( !CENTRE )
+    if constexpr( CENTRE )
+    {
+        // no registers held across the staging phase: the plane is prefetched now and loaded (from L1) when the pixel starts
+#pragma unroll
+        for( int k = 0; k < PIX; k++ )
+        {
+            const int py = yBase + jOf( k ) * STEP;
+            if( px < u.W && py < u.yEnd ) asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< float4 >( a.centre, px, py ) ) );
+        }
+    }
+    else
     {
 #pragma unroll
         for( int k = 0; k < PIX; k++ )

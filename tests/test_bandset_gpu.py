@@ -47,6 +47,15 @@ def test_band_set_is_bit_identical_to_the_single_handle(bands, boundaries):
     _run(640, 360, [0] * bands, boundaries, frames=5)
 
 
+def test_band_set_across_devices_is_bit_identical():
+    """The same gate with the bands on DIFFERENT GPUs (peer copies over NVLink); needs at least two devices."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU: the multi-band schedule itself is covered by the single-device cases above")
+    _run(640, 720, list(range(min(n, 4))), None, frames=5)
+
+
 def test_band_set_five_iterations_and_ragged_size():
     """N = 5 (stride-16 apron: 30 + 2 + 1 + 1 rows) on a frame whose width and height do not divide by 3."""
     _run(322, 362, [0, 0], None, frames=3, iterations=5)

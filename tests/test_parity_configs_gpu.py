@@ -12,7 +12,7 @@ Tolerances: tests/_harness.py.  The oracle takes ~0.6 s (1080p) / 2.4 s (4K) / 1
 import numpy as np
 import pytest
 
-from _harness import Pair, assert_all_ok
+from _harness import Pair, assert_all_ok, WRITTEN_IMAGES
 from test_parity_gpu import OUTPUTS_PER_PASS, _summary
 
 pytestmark = pytest.mark.gpu
@@ -24,12 +24,12 @@ def test_config2_1080p_64_frames_locked():
         disoccluded = 0
         for frame in range(64):
             fi, u = p.run_frame(frame)
-            res = p.compare(fi)
+            res = p.compare(fi, WRITTEN_IMAGES)      # (the producer's inputs are the same arrays on both sides)
             assert_all_ok(res, "1080p frame %d %s" % (frame, _summary(res)))
             assert res["DebugMask"]["n_bad"] == 0 and res["GradientPrevPix"]["n_bad"] == 0
             disoccluded += int((p.oracle.image("DebugMask", fi) != 63).sum())
-            # re-lock what the frame wrote (every image but the producer's inputs)
-            p.sync_state_to_cuda()
+            # re-lock what the frame wrote
+            p.sync_images(WRITTEN_IMAGES, fi)
         assert disoccluded > 64 * 1000          # camera motion and moving objects do disocclude
     finally:
         p.close()

@@ -16,6 +16,6 @@ for v in "$@"; do
     env $v timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "${TESTS:-per_pass or tiny or edges}" > gpurun_out/pytest_$name.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$name.log
     tail -4 gpurun_out/pytest_$name.log | cut -c1-300
   fi
-  env $v timeout 600 python bench.py --steps 60 --warmup 10 --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
+  env $v timeout 600 python bench.py --steps 60 --warmup 10 --no-cpu-baseline --legs none > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
   summ gpurun_out/bench_$name.json
 done
