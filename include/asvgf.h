@@ -152,17 +152,19 @@ ASVGF_API AsvgfResult asvgfDenoisePass( AsvgfDenoiser denoiser, AsvgfStream stre
 /* ---- the two dispatches that consume the denoiser's outputs right after it ---- */
 
 /* = ImageComposition::PrepareForRaster -> ProcessCheckerboard (Source/ImageComposition.cpp:87-92, 157-222), shader
-   CmCheckerboard.comp:43-78 restricted to the denoiser's own image: ASVGF_IMAGE_PRE_FINAL -> ASVGF_IMAGE_FINAL, with
-   the cross-shaped resolve where ASVGF_IMAGE_THROUGHPUT.a marks a split (reflect/refract) pixel.  The shader's two
-   other image pairs (ScreenEmisRT, AcidFogRT) belong to the rasteriser / fog producers and are not part of this
-   library.  Enqueues only. */
+   CmCheckerboard.comp:43-78: ASVGF_IMAGE_PRE_FINAL -> ASVGF_IMAGE_FINAL with the cross-shaped resolve where
+   ASVGF_IMAGE_THROUGHPUT.a marks a split (reflect/refract) pixel, and the same for the shader's two other image pairs,
+   ASVGF_IMAGE_SCREEN_EMIS_RT -> ASVGF_IMAGE_SCREEN_EMISSION and ASVGF_IMAGE_ACID_FOG_RT -> ASVGF_IMAGE_ACID_FOG (written by the
+   rasteriser / fog producers; skipped when those four images have no storage).  Enqueues only. */
 ASVGF_API AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                                 const AsvgfGlobalUniform* pUniform );
 
 /* = Tonemapping::CalculateExposure (Source/Tonemapping.cpp:59-175): the 256-bin log-luminance histogram of
    ASVGF_IMAGE_HISTOGRAM_INPUT (CmLuminanceHistogram.comp:41-86) followed by the eye-adaptation update of
    AsvgfTonemapping.avgLuminance, which also clears the histogram for the next frame (CmLuminanceAvg.comp:37-89).
-   Band handles histogram their owned rows only.  Enqueues only. */
+   Enqueues only.  Whole-frame handles only: on a band handle this call, asvgfLuminanceHistogram / Average and
+   asvgfResolveCheckerboard return ASVGF_UNSUPPORTED (a band holds part of the histogram, and the resolve reads one row of
+   PreFinal beyond the band). */
 ASVGF_API AsvgfResult asvgfCalculateExposure( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                               const AsvgfGlobalUniform* pUniform );
 /* The two dispatches of asvgfCalculateExposure separately (parity tests look at the histogram in between). */

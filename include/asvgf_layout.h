@@ -68,6 +68,10 @@ enum AsvgfImageIndex
     ASVGF_IMAGE_SCATTERING_PREV              = 49,
     ASVGF_IMAGE_SCATTERING_HISTORY           = 50, /* R16_SFLOAT, regular layout: its history length */
     ASVGF_IMAGE_SCATTERING_HISTORY_PREV      = 51,
+    ASVGF_IMAGE_ACID_FOG_RT                  = 52, /* B10G11R11_UFLOAT, regular layout: the fog producer's checkerboarded image ...  */
+    ASVGF_IMAGE_ACID_FOG                     = 53, /* ... and its resolved form (asvgfResolveCheckerboard, CmCheckerboard.comp:65-77) */
+    ASVGF_IMAGE_SCREEN_EMIS_RT               = 54, /* B10G11R11_UFLOAT, regular layout: screen-space emission, checkerboarded ...      */
+    ASVGF_IMAGE_SCREEN_EMISSION              = 55, /* ... and resolved                                                                 */
     ASVGF_IMAGE_GRADIENT_INPUTS              = 70, /* R16G16_SFLOAT                               */
     ASVGF_IMAGE_GRADIENT_INPUTS_PREV         = 71,
     ASVGF_IMAGE_DIS_PING_GRADIENT            = 72, /* R8G8B8A8_UNORM, 1/3 resolution              */

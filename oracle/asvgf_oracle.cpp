@@ -447,6 +447,7 @@ int bytesPerPixelOf( uint32_t i )
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: return 16;
         case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV:
         case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR: case ASVGF_IMAGE_UNFILTERED_INDIR:
+        case ASVGF_IMAGE_ACID_FOG_RT: case ASVGF_IMAGE_ACID_FOG: case ASVGF_IMAGE_SCREEN_EMIS_RT: case ASVGF_IMAGE_SCREEN_EMISSION:
         case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR:
         case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV:
         case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR:
@@ -1306,29 +1307,35 @@ void scatterAccumulate( AsvgfOracle_T& o, uint32_t fi, const Ctx& c, float maxHi
 // ---------------------------------------------------------------------------------------------------------------
 void resolveCheckerboard( AsvgfOracle_T& o, uint32_t fi, const Ctx& c )
 {
-    Img& preFinal   = o.get( ASVGF_IMAGE_PRE_FINAL, fi );
+    // the shader's three image pairs (CmCheckerboard.comp:62-77)
+    const uint32_t srcs[ 3 ] = { ASVGF_IMAGE_PRE_FINAL, ASVGF_IMAGE_SCREEN_EMIS_RT, ASVGF_IMAGE_ACID_FOG_RT };
+    const uint32_t dsts[ 3 ] = { ASVGF_IMAGE_FINAL, ASVGF_IMAGE_SCREEN_EMISSION, ASVGF_IMAGE_ACID_FOG };
     Img& throughput = o.get( ASVGF_IMAGE_THROUGHPUT, fi );
-    Img& final_     = o.get( ASVGF_IMAGE_FINAL, fi );
     const int sep   = getCheckerboardSeparatorX( c );
-#pragma omp parallel for schedule( static )
-    for( int y = 0; y < c.H; y++ )
+    for( int i = 0; i < 3; i++ )
     {
-        for( int x = 0; x < c.W; x++ )
+        Img& src = o.get( srcs[ i ], fi );
+        Img& dst = o.get( dsts[ i ], fi );
+#pragma omp parallel for schedule( static )
+        for( int y = 0; y < c.H; y++ )
         {
-            const ivec2 pix = { x, y };
-            const ivec2 cb  = getCheckerboardPix( c, pix );                    // :55
-            vec3        hdr = unpackUfloat111110( fetchU32( preFinal, pix ) ); // :62
-            if( fetchRGBA16F( throughput, cb ).w > 0.5f )                      // needResolveCheckerboard, ShaderCommonGLSLFunc.h:434-444
+            for( int x = 0; x < c.W; x++ )
             {
-                const float fl = ( cb.x == 0 || cb.x == sep ) ? 0.0f : 1.0f;               // !isLeftOutOfBounds  :29-34
-                const float fr = ( cb.x == sep || cb.x == ( int )c.u->renderWidth ) ? 0.0f : 1.0f; // !isRightOutOfBounds :36-41
-                const vec3 l = unpackUfloat111110( fetchU32( preFinal, { x - 1, y } ) ), r = unpackUfloat111110( fetchU32( preFinal, { x + 1, y } ) );
-                const vec3 d = unpackUfloat111110( fetchU32( preFinal, { x, y + 1 } ) ), t = unpackUfloat111110( fetchU32( preFinal, { x, y - 1 } ) );
-                auto cross = [ & ]( float vl, float vr, float vd, float vt ) { return 0.25f * vl * fl + 0.25f * vr * fr + 0.25f * vd + 0.25f * vt; }; // :45-49
-                const vec3 k = { cross( l.x, r.x, d.x, t.x ), cross( l.y, r.y, d.y, t.y ), cross( l.z, r.z, d.z, t.z ) };
-                hdr          = mix3( hdr, k, 0.5f );                           // :51
+                const ivec2 pix = { x, y };
+                const ivec2 cb  = getCheckerboardPix( c, pix );               // :55
+                vec3        hdr = unpackUfloat111110( fetchU32( src, pix ) ); // :62-64
+                if( fetchRGBA16F( throughput, cb ).w > 0.5f )                 // needResolveCheckerboard, ShaderCommonGLSLFunc.h:434-444
+                {
+                    const float fl = ( cb.x == 0 || cb.x == sep ) ? 0.0f : 1.0f;               // !isLeftOutOfBounds  :29-34
+                    const float fr = ( cb.x == sep || cb.x == ( int )c.u->renderWidth ) ? 0.0f : 1.0f; // !isRightOutOfBounds :36-41
+                    const vec3 l = unpackUfloat111110( fetchU32( src, { x - 1, y } ) ), r = unpackUfloat111110( fetchU32( src, { x + 1, y } ) );
+                    const vec3 d = unpackUfloat111110( fetchU32( src, { x, y + 1 } ) ), t = unpackUfloat111110( fetchU32( src, { x, y - 1 } ) );
+                    auto cross = [ & ]( float vl, float vr, float vd, float vt ) { return 0.25f * vl * fl + 0.25f * vr * fr + 0.25f * vd + 0.25f * vt; }; // :45-49
+                    const vec3 k = { cross( l.x, r.x, d.x, t.x ), cross( l.y, r.y, d.y, t.y ), cross( l.z, r.z, d.z, t.z ) };
+                    hdr          = mix3( hdr, k, 0.5f );                      // :51
+                }
+                storeU32( dst, pix, packUfloat111110( hdr ) );               // :73-77
             }
-            storeU32( final_, pix, packUfloat111110( hdr ) );                  // :73
         }
     }
 }

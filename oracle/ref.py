@@ -74,8 +74,6 @@ class RefDenoiser:
         for name, info in layout.IMAGES.items():
             dtype, shape = layout.image_numpy_shape(name, width, height)
             self._arrays[name] = np.zeros(shape, dtype=dtype)
-        # the two extra image pairs of CmCheckerboard.comp:65-77 (b10g11r11, regular layout)
-        self._extra = {i: np.zeros((height, width), dtype=np.uint32) for i in (52, 53, 54, 55)}
         self.tonemapping = layout.Tonemapping()
         self._local = {}
 
@@ -95,8 +93,6 @@ class RefDenoiser:
                 continue          # images this repo adds (FwdLum, DebugMask, ScatterCurrent) are not in the reference's table
             a = self.image(name, frame_index)
             descs[idx] = _ImageDesc(a.ctypes.data, a.shape[1], a.shape[0], _SHIM_FORMAT[info[1]])
-        for idx, a in self._extra.items():
-            descs[idx] = _ImageDesc(a.ctypes.data, a.shape[1], a.shape[0], 12)
         return descs
 
     def dispatch(self, shader, frame_index, uniform, size_x, size_y, spec_constant=0, push=None):

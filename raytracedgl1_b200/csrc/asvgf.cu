@@ -13,6 +13,8 @@
     #include "../../experiments/asvgf_literal_kernels.cuh"
 #endif
 
+#include <nvtx3/nvToolsExt.h> // header-only in CUDA 12: ranges are no-ops unless a profiler is attached
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -66,7 +68,8 @@ bool describe( uint32_t i, ImageDesc* d )
         case ASVGF_IMAGE_DIFF_PONG_COLOR_AND_VARIANCE: case ASVGF_IMAGE_SCATTERING: case ASVGF_IMAGE_SCATTERING_PREV: case ASVGF_IMAGE_SCATTER_CURRENT:
             *d = { ASVGF_FORMAT_R16G16B16A16_SFLOAT, 8, false }; return true;
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: *d = { ASVGF_FORMAT_R32G32B32A32_SFLOAT, 16, false }; return true;
-        case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
+        case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: case ASVGF_IMAGE_ACID_FOG_RT: case ASVGF_IMAGE_ACID_FOG:
+        case ASVGF_IMAGE_SCREEN_EMIS_RT: case ASVGF_IMAGE_SCREEN_EMISSION: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
         case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR:
         case ASVGF_IMAGE_UNFILTERED_INDIR: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR: case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV:
         case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR: case ASVGF_IMAGE_SPEC_PONG_COLOR:
@@ -145,6 +148,14 @@ void setImgStorage( Img& im, uint8_t* p, uint32_t pitch, uint32_t bpp )
     im.pitchT = pitch / bpp;
     im.p0 = p ? p - ( ptrdiff_t )im.row0 * ( ptrdiff_t )pitch : nullptr;
 }
+
+// profiler ranges named like the reference's command-buffer labels (CmdLabel: Source/Denoiser.cpp:90,130,162,184,205,
+// Source/PathTracer.cpp:198, Source/Tonemapping.cpp:63, Source/ImageComposition.cpp:162, Source/Volumetric.cpp:78)
+struct NvtxRange
+{
+    explicit NvtxRange( const char* name ) { nvtxRangePushA( name ); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard
 {
@@ -477,8 +488,13 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
 AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
 {
     NEED( ASVGF_IMAGE_PRE_FINAL, ASVGF_IMAGE_THROUGHPUT, ASVGF_IMAGE_FINAL );
+    const NvtxRange range( "Framebuf checkerboard interpolate" );
     ResolveArgs a;
-    a.preFinal = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.final_ = d.get( ASVGF_IMAGE_FINAL, fi );
+    a.src[ 0 ] = d.get( ASVGF_IMAGE_PRE_FINAL, fi ); a.throughput = d.get( ASVGF_IMAGE_THROUGHPUT, fi ); a.dst[ 0 ] = d.get( ASVGF_IMAGE_FINAL, fi );
+    // the shader's two other image pairs (CmCheckerboard.comp:63-64,70-77) when the caller keeps them in this table
+    a.src[ 1 ] = d.get( ASVGF_IMAGE_SCREEN_EMIS_RT, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SCREEN_EMISSION, fi );
+    a.src[ 2 ] = d.get( ASVGF_IMAGE_ACID_FOG_RT, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_ACID_FOG, fi );
+    a.pairs = ( a.src[ 1 ].p && a.dst[ 1 ].p && a.src[ 2 ].p && a.dst[ 2 ].p ) ? 3 : 1;
     k_checkerboard_resolve<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_checkerboard_resolve" );
 }
@@ -488,6 +504,7 @@ AsvgfResult runScatterAccumulate( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t f
     NEED( ASVGF_IMAGE_MOTION, ASVGF_IMAGE_DEPTH_WORLD, ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_DEPTH_WORLD_PREV, ASVGF_IMAGE_NORMAL_PREV, ASVGF_IMAGE_SCATTERING_PREV,
           ASVGF_IMAGE_SCATTERING_HISTORY_PREV, ASVGF_IMAGE_SCATTERING, ASVGF_IMAGE_SCATTERING_HISTORY );
     if( g.volumeEnableType == ASVGF_VOLUME_ENABLE_VOLUMETRIC ) NEED( ASVGF_IMAGE_SCATTER_CURRENT );
+    const NvtxRange range( "Volumetric Process" );
     ScatterArgs a;
     a.motion = d.get( ASVGF_IMAGE_MOTION, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi );
     a.depthPrev = d.get( ASVGF_IMAGE_DEPTH_WORLD_PREV, fi ); a.normalPrev = d.get( ASVGF_IMAGE_NORMAL_PREV, fi );
@@ -513,6 +530,7 @@ LumArgs lumArgs( const AsvgfDenoiser_T& d, uint32_t fi, const AsvgfGlobalUniform
 AsvgfResult runLuminanceHistogram( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, const AsvgfGlobalUniform& g )
 {
     NEED( ASVGF_IMAGE_HISTOGRAM_INPUT );
+    const NvtxRange range( "Exposure" );
     const LumArgs a = lumArgs( d, fi, g );
     k_lum_bin_table<<< 256, 256, 0, s >>>( a );
     AsvgfResult r = launchCheck( d, "k_lum_bin_table" );
@@ -595,6 +613,12 @@ AsvgfResult runPass( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Unif
 
 AsvgfResult runPassRows( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, uint32_t pass )
 {
+    const NvtxRange range( pass == ASVGF_PASS_GRADIENT_SAMPLES ? "Gradient samples"
+                           : pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ? "Gradient Atrous"
+                           : pass == ASVGF_PASS_TEMPORAL          ? "Temporal accumulation"
+                           : pass == ASVGF_PASS_ANTIFIREFLY       ? "Antifirefly"
+                           : pass == ASVGF_PASS_VARIANCE          ? "SVGF Variance estimation"
+                                                                  : "SVGF Atrous" );
     if( pass == ASVGF_PASS_GRADIENT_SAMPLES ) return runGradientSamples( d, s, fi, u );
     if( pass >= ASVGF_PASS_GRADIENT_ATROUS_0 && pass <= ASVGF_PASS_GRADIENT_ATROUS_3 ) return runGradientAtrous( d, s, fi, u, pass - ASVGF_PASS_GRADIENT_ATROUS_0 );
     if( pass == ASVGF_PASS_TEMPORAL ) return runTemporal( d, s, fi, u );
@@ -996,6 +1020,7 @@ AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser d, AsvgfStream stream, uint3
 {
     AsvgfResult r = checkCall( d, frameIndex, pUniform );
     if( r != ASVGF_SUCCESS ) return r;
+    if( d->info.bandRowEnd != 0 ) return fail( ASVGF_UNSUPPORTED, "asvgfResolveCheckerboard on a band handle: the resolve reads PreFinal one row beyond the band, which no pass writes and no exchange fills (gather the frame on one device first)" );
     DeviceGuard guard( d->device );
     return runResolveCheckerboard( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ) );
 }
@@ -1013,6 +1038,7 @@ AsvgfResult asvgfLuminanceHistogram( AsvgfDenoiser d, AsvgfStream stream, uint32
 {
     AsvgfResult r = checkCall( d, frameIndex, pUniform );
     if( r != ASVGF_SUCCESS ) return r;
+    if( d->info.bandRowEnd != 0 ) return fail( ASVGF_UNSUPPORTED, "asvgfLuminanceHistogram on a band handle: a band would histogram its own rows only; the average needs the whole frame's histogram (gather the frame on one device first)" );
     DeviceGuard guard( d->device );
     return runLuminanceHistogram( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), *pUniform );
 }
@@ -1021,6 +1047,7 @@ AsvgfResult asvgfLuminanceAverage( AsvgfDenoiser d, AsvgfStream stream, uint32_t
 {
     AsvgfResult r = checkCall( d, frameIndex, pUniform );
     if( r != ASVGF_SUCCESS ) return r;
+    if( d->info.bandRowEnd != 0 ) return fail( ASVGF_UNSUPPORTED, "asvgfLuminanceAverage on a band handle: a band holds a partial histogram; the average needs the whole frame's (gather the frame on one device first)" );
     DeviceGuard guard( d->device );
     return runLuminanceAverage( *d, ( cudaStream_t )stream, frameIndex, *pUniform );
 }

@@ -19,7 +19,9 @@ namespace asvgf
 
 struct ResolveArgs
 {
-    Img preFinal, throughput, final_;
+    Img     src[ 3 ], dst[ 3 ]; // PreFinal -> Final, ScreenEmisRT -> ScreenEmission, AcidFogRT -> AcidFog (CmCheckerboard.comp:62-77)
+    Img     throughput;
+    int32_t pairs;              // 3, or 1 when only the denoiser's own image is resolved
 };
 
 // one thread per REGULAR pixel; arithmetic in the shader's order (products by 0.25 / 0.5 are exact, the three sums round)
@@ -28,29 +30,34 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_checkerboard_resolve( co
     const int x = blockIdx.x * kBlockW + threadIdx.x;
     const int y = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
     if( x >= u.W || y >= u.yEnd ) return;
-    const Rows rows = rowsOf( a.preFinal );
+    const Rows rows = rowsOf( a.src[ 0 ] );
     const int  sep  = u.W / 2;
     const int  isOdd = ( x + y % 2 ) % 2;                 // ShaderCommonGLSLFunc.h:311-329
     const int  cbx   = isOdd * sep + x / 2;
-    const uint32_t centre = __ldg( at< uint32_t >( a.preFinal, x, y ) );
     const uint16_t split  = __ldg( reinterpret_cast< const uint16_t* >( at< uint2 >( a.throughput, cbx, y ) ) + 3 ); // .a
-    uint32_t out = centre;
-    if( h2f( split ) > 0.5f ) // wasSplit, ShaderCommonGLSLFunc.h:434-444
+    const bool     resolve = h2f( split ) > 0.5f;                       // wasSplit, ShaderCommonGLSLFunc.h:434-444
+    const float    fl = ( cbx == 0 || cbx == sep ) ? 0.0f : 1.0f;       // !isLeftOutOfBounds
+    const float    fr = ( cbx == sep || cbx == u.W ) ? 0.0f : 1.0f;     // !isRightOutOfBounds
+    for( int i = 0; i < a.pairs; i++ )
     {
-        const float3 c = unpackUfloat111110( centre );
-        const float  fl = ( cbx == 0 || cbx == sep ) ? 0.0f : 1.0f;     // !isLeftOutOfBounds
-        const float  fr = ( cbx == sep || cbx == u.W ) ? 0.0f : 1.0f;   // !isRightOutOfBounds
-        const float3 l = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x - 1, y, rows.in( x - 1, y ), 0u ) );
-        const float3 r = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x + 1, y, rows.in( x + 1, y ), 0u ) );
-        const float3 d = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x, y + 1, rows.in( x, y + 1 ), 0u ) );
-        const float3 t = unpackUfloat111110( ldIf< uint32_t >( a.preFinal, x, y - 1, rows.in( x, y - 1 ), 0u ) );
-        auto cross = [ & ]( float vl, float vr, float vd, float vt ) {
-            return addr( addr( addr( mulr( mulr( 0.25f, vl ), fl ), mulr( mulr( 0.25f, vr ), fr ) ), mulr( 0.25f, vd ) ), mulr( 0.25f, vt ) );
-        };
-        const float3 k = make_float3( cross( l.x, r.x, d.x, t.x ), cross( l.y, r.y, d.y, t.y ), cross( l.z, r.z, d.z, t.z ) );
-        out = packUfloat111110( make_float3( mixr( c.x, k.x, 0.5f ), mixr( c.y, k.y, 0.5f ), mixr( c.z, k.z, 0.5f ) ) );
+        const Img&     src    = a.src[ i ];
+        const uint32_t centre = __ldg( at< uint32_t >( src, x, y ) );
+        uint32_t       out    = centre;
+        if( resolve )
+        {
+            const float3 c = unpackUfloat111110( centre );
+            const float3 l = unpackUfloat111110( ldIf< uint32_t >( src, x - 1, y, rows.in( x - 1, y ), 0u ) );
+            const float3 r = unpackUfloat111110( ldIf< uint32_t >( src, x + 1, y, rows.in( x + 1, y ), 0u ) );
+            const float3 d = unpackUfloat111110( ldIf< uint32_t >( src, x, y + 1, rows.in( x, y + 1 ), 0u ) );
+            const float3 t = unpackUfloat111110( ldIf< uint32_t >( src, x, y - 1, rows.in( x, y - 1 ), 0u ) );
+            auto cross = [ & ]( float vl, float vr, float vd, float vt ) {
+                return addr( addr( addr( mulr( mulr( 0.25f, vl ), fl ), mulr( mulr( 0.25f, vr ), fr ) ), mulr( 0.25f, vd ) ), mulr( 0.25f, vt ) );
+            };
+            const float3 k = make_float3( cross( l.x, r.x, d.x, t.x ), cross( l.y, r.y, d.y, t.y ), cross( l.z, r.z, d.z, t.z ) );
+            out = packUfloat111110( make_float3( mixr( c.x, k.x, 0.5f ), mixr( c.y, k.y, 0.5f ), mixr( c.z, k.z, 0.5f ) ) );
+        }
+        *atW< uint32_t >( a.dst[ i ], x, y ) = out;
     }
-    *atW< uint32_t >( a.final_, x, y ) = out;
 }
 
 // ---- exposure ----
@@ -89,9 +96,26 @@ __global__ void __launch_bounds__( kLumThreads ) k_lum_histogram( const __grid_c
     uint8_t*  sTable = lumSmem;                                            // 64 KB
     uint32_t* sHist  = reinterpret_cast< uint32_t* >( lumSmem + 65536 );   // one 256-bin histogram per warp
     constexpr int WARPS = kLumThreads / 32;
-    for( int i = threadIdx.x; i < 65536 / 16; i += kLumThreads ) reinterpret_cast< uint4* >( sTable )[ i ] = __ldg( reinterpret_cast< const uint4* >( a.binTable ) + i );
+    // the 64 KB bin table comes in as ONE bulk asynchronous copy (TMA, cp.async.bulk: no registers, no per-thread loads --
+    // ncu of the per-thread copy: the kernel spent most of its 35 us filling this table) signalled through an mbarrier,
+    // while the threads zero the per-warp histograms
+    __shared__ __align__( 8 ) uint64_t tableBarrier;
+    const uint32_t barAddr = ( uint32_t )__cvta_generic_to_shared( &tableBarrier ), dstAddr = ( uint32_t )__cvta_generic_to_shared( sTable );
+    if( threadIdx.x == 0 )
+    {
+        asm volatile( "mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"( barAddr ) );
+        asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" );
+        asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( barAddr ), "r"( 65536u ) : "memory" );
+        asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"( dstAddr ), "l"( a.binTable ), "r"( 65536u ), "r"( barAddr )
+                      : "memory" );
+    }
     for( int i = threadIdx.x; i < WARPS * 256; i += kLumThreads ) sHist[ i ] = 0u;
-    __syncthreads();
+    __syncthreads(); // the barrier word is initialised and the histograms are zero
+    {
+        uint32_t done = 0;
+        while( !done )
+            asm volatile( "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"( done ) : "r"( barAddr ) : "memory" );
+    }
 
     uint32_t* myHist = sHist + ( threadIdx.x >> 5 ) * 256;
     auto count = [ & ]( uint32_t bin, bool valid ) {

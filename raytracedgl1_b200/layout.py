@@ -62,6 +62,11 @@ IMAGES = {
     "Scattering_Prev": (49, R16G16B16A16_SFLOAT, False, "state"),
     "ScatteringHistory": (50, R16_SFLOAT, False, "state"),
     "ScatteringHistory_Prev": (51, R16_SFLOAT, False, "state"),
+    # the two other image pairs of the checkerboard resolve (CmCheckerboard.comp:62-77), regular layout
+    "AcidFogRT": (52, B10G11R11_UFLOAT, False, "in"),
+    "AcidFog": (53, B10G11R11_UFLOAT, False, "out"),
+    "ScreenEmisRT": (54, B10G11R11_UFLOAT, False, "in"),
+    "ScreenEmission": (55, B10G11R11_UFLOAT, False, "out"),
     "GradientInputs": (70, R16G16_SFLOAT, False, "in"),
     "GradientInputs_Prev": (71, R16G16_SFLOAT, False, "in"),
     "DISPingGradient": (72, R8G8B8A8_UNORM, True, "scratch"),

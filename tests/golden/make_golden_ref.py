@@ -28,7 +28,7 @@ W, H, N, FRAMES = 96, 54, 4, 4
 PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "asvgf_ref_96x54.npz")
 # everything the chain writes (state, scratch and outputs), plus the post passes' outputs
 NAMES = [n for n, info in layout.IMAGES.items() if info[3] != "in" and n not in ("DebugMask", "FwdLum", "ScatterCurrent")]
-POST = ["Final", "Scattering", "ScatteringHistory"]
+POST = ["Final", "ScreenEmission", "AcidFog", "Scattering", "ScatteringHistory"]
 
 
 def edit_uniform(u):
@@ -40,6 +40,11 @@ def inputs(frame):
     g = synth.generate(W, H, frame)
     rng = np.random.default_rng(2024 + frame)
     g["Throughput"][..., 3] = (rng.random((H, W)) < 0.4).astype(np.float16)   # split (reflect/refract) pixels
+    # the rasteriser's / fog producer's checkerboarded images that the resolve also handles (CmCheckerboard.comp:63-64):
+    # random finite B10G11R11 texels (top exponent bit of every channel cleared)
+    finite = np.uint32(~((1 << 10) | (1 << 21) | (1 << 31)) & 0xFFFFFFFF)
+    for name in ("ScreenEmisRT", "AcidFogRT"):
+        g[name] = rng.integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32) & finite
     return g
 
 

@@ -54,6 +54,10 @@ def _run_sequence(W, H, frames, edit=None, mutate=None):
         for frame in range(frames):
             fi = frame & 1
             g = synth.generate(W, H, frame)
+            rng = np.random.default_rng(99 + frame)
+            g["Throughput"][..., 3] = (rng.random((H, W)) < 0.4).astype(np.float16)       # split pixels: the resolve has work to do
+            for name in ("ScreenEmisRT", "AcidFogRT"):                                    # finite random B10G11R11 texels
+                g[name] = rng.integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32) & np.uint32(0x7FDFFBFF)
             if mutate:
                 mutate(frame, g)
             for n, a in g.items():
