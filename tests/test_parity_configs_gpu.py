@@ -19,17 +19,24 @@ pytestmark = pytest.mark.gpu
 
 
 def test_config2_1080p_64_frames_locked():
+    """Every one of the 64 frames: the integer outputs (disocclusion / history mask, GradientPrevPix) bit-exact and the frame's
+    outputs (PreFinal, HistogramInput, the history images the next frame reads) within tolerance, from identical frame-start
+    state.  Every eighth frame (and the frames around the light switch at frame 24) the whole image table is compared.  (The
+    host side of this test -- oracle, generator, numpy decoding -- is what takes the time: 0.5 s to 6 s per frame depending on
+    how busy the box's cores are.)"""
     p = Pair(1920, 1080)
+    every_frame = ["DebugMask", "GradientPrevPix", "PreFinal", "HistogramInput", "DiffColorHistory", "AccumHistoryLength", "SpecAccumColor",
+                   "IndirAccum", "DiffAccumMoments", "DISGradientHistory"]
     try:
         disoccluded = 0
         for frame in range(64):
             fi, u = p.run_frame(frame)
-            res = p.compare(fi, WRITTEN_IMAGES)      # (the producer's inputs are the same arrays on both sides)
+            full = frame % 8 == 0 or frame in (1, 23, 24, 25, 63)
+            res = p.compare(fi, WRITTEN_IMAGES if full else every_frame)   # (the producer's inputs are the same arrays on both sides)
             assert_all_ok(res, "1080p frame %d %s" % (frame, _summary(res)))
             assert res["DebugMask"]["n_bad"] == 0 and res["GradientPrevPix"]["n_bad"] == 0
             disoccluded += int((p.oracle.image("DebugMask", fi) != 63).sum())
-            # re-lock what the frame wrote
-            p.sync_images(WRITTEN_IMAGES, fi)
+            p.sync_images(WRITTEN_IMAGES, fi)        # re-lock what the frame wrote
         assert disoccluded > 64 * 1000          # camera motion and moving objects do disocclude
     finally:
         p.close()
