@@ -356,10 +356,12 @@ ASVGF_DEVICE void atrousStore( const AtrousArgs& a, const Uniform& u, int px, in
         packUfloat111110Fast( make_float3( fmaxf( 0.0f, illuminated.x ), fmaxf( 0.0f, illuminated.y ), fmaxf( 0.0f, illuminated.z ) ) );
 }
 
-// PAIR = false: a thread filters its two pixels one after the other (9 tile texels each).
+// PAIR = false (default): a thread filters its two pixels one after the other (9 tile texels each): 64 registers, 4 CTAs per SM.
+//               Bound by shared-memory bandwidth: 36 LDS.128 per pixel = 0.128 ms per iteration at 4K at 128 B/clk/SM, measured
+//               0.175-0.198 (ncu: LDS pipe 65 %, short-scoreboard + MIO stalls 41 %, issue 55 %).
 // PAIR = true:  a thread filters two vertically adjacent (dilated) pixels TOGETHER: their 3x3 neighbourhoods share two of
-//               four rows, so 12 tile texels serve 16 tap evaluations -- 2/3 of the shared-memory traffic, which is what
-//               bounds the single-pixel form (ncu: LDS pipe 65 %, short-scoreboard + MIO stalls 41 %, issue 55 %).
+//               four rows, so 12 tile texels serve 16 tap evaluations -- 2/3 of the shared-memory traffic -- but the two pixel
+//               states need 80 registers (3 CTAs per SM) and the kernel lands 2 % behind (ASVGF_ATROUS_PAIR=1).
 #ifndef ASVGF_AT_PAIR_MIN_CTAS
     #define ASVGF_AT_PAIR_MIN_CTAS 3
 #endif
@@ -414,6 +416,24 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
         }
     }
 
+    if constexpr( LAST )
+    {
+        // the composition reads four more images at the centre pixel (CmSVGFAtrous.comp:280-301); no registers to spare for them
+        // across the tap loop, so their lines are prefetched here and loaded (from L1) in the epilogue
+#pragma unroll
+        for( int k = 0; k < PIX; k++ )
+        {
+            const int py = yBase + jOf( k ) * STEP;
+            if( px < u.W && py < u.yEnd )
+            {
+                const int sepx = u.W / 2, isOdd = px >= sepx ? 1 : 0, regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 );
+                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint32_t >( a.albedo, regX, py ) ) );
+                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint2 >( a.throughput, px, py ) ) );
+                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint16_t >( a.metRough, px, py ) ) );
+                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint8_t >( a.isSky, px, py ) ) );
+            }
+        }
+    }
     atrousStage< STEP >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
     __syncthreads();
 
