@@ -191,6 +191,24 @@ ASVGF_API AsvgfResult asvgfDownloadTonemapping( AsvgfDenoiser denoiser, AsvgfStr
    Source/VulkanDevice.cpp:791-796).  Surfaces asynchronous kernel faults as ASVGF_CUDA_ERROR. */
 ASVGF_API AsvgfResult asvgfSynchronize( AsvgfDenoiser denoiser, AsvgfStream stream );
 
+/* ---- Vulkan interop, CUDA half ----
+   RTGL1 keeps the G-buffer in VkImages (Source/Framebuffers.cpp:702-804) and orders the denoiser with its command buffer and
+   frame fence (Source/VulkanDevice.cpp:551-584, 791-796).  A host that keeps that producer exports each image's memory
+   (VK_KHR_external_memory_fd, OPAQUE_FD; linear tiling, or a linear VkBuffer filled by vkCmdCopyImageToBuffer) and a semaphore per
+   direction (VK_KHR_external_semaphore_fd); these calls import the file descriptors, map the memory as linear device memory for
+   asvgfBindExternalImage, and wait / signal on a CUDA stream.  No Vulkan header is involved on this side.  On success the
+   descriptor belongs to CUDA (do not close it).  device = -1: the calling thread's current device. */
+typedef struct AsvgfExternalMemory_T*    AsvgfExternalMemory;
+typedef struct AsvgfExternalSemaphore_T* AsvgfExternalSemaphore;
+ASVGF_API AsvgfResult asvgfImportExternalMemoryFd( int32_t device, int fd, uint64_t allocationSize, uint32_t dedicated,
+                                                   AsvgfExternalMemory* pMemory );
+ASVGF_API AsvgfResult asvgfExternalMemoryGetBuffer( AsvgfExternalMemory memory, uint64_t offset, uint64_t size, void** ppDevice );
+ASVGF_API AsvgfResult asvgfDestroyExternalMemory( AsvgfExternalMemory memory );
+ASVGF_API AsvgfResult asvgfImportExternalSemaphoreFd( int32_t device, int fd, uint32_t timeline, AsvgfExternalSemaphore* pSemaphore );
+ASVGF_API AsvgfResult asvgfWaitExternalSemaphore( AsvgfExternalSemaphore semaphore, AsvgfStream stream, uint64_t value );
+ASVGF_API AsvgfResult asvgfSignalExternalSemaphore( AsvgfExternalSemaphore semaphore, AsvgfStream stream, uint64_t value );
+ASVGF_API AsvgfResult asvgfDestroyExternalSemaphore( AsvgfExternalSemaphore semaphore );
+
 /* ---- one frame across several GPUs (BASELINE config 4; the reference has no multi-GPU path) ----
    A band set owns one band handle per entry of pDevices -- a device may be listed more than once (several bands on one
    GPU) -- created with ASVGF_CREATE_BAND_APRON, a stream per band, and the halo exchange between neighbouring bands

@@ -1163,3 +1163,4 @@ const char* asvgfLastErrorMessage( void ) { return g_lastError.c_str(); }
 } // extern "C"
 
 #include "asvgf_bandset.inl"
+#include "asvgf_interop.inl"

@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = [
     "asvgfScatterAccumulate",
     "asvgfBandSetCreate", "asvgfBandSetDestroy", "asvgfBandSetGetBandCount", "asvgfBandSetGetBand", "asvgfBandSetFrame",
     "asvgfBandSetSynchronize", "asvgfBandSetBeginTiming", "asvgfBandSetEndTiming",
+    "asvgfImportExternalMemoryFd", "asvgfExternalMemoryGetBuffer", "asvgfDestroyExternalMemory", "asvgfImportExternalSemaphoreFd",
+    "asvgfWaitExternalSemaphore", "asvgfSignalExternalSemaphore", "asvgfDestroyExternalSemaphore",
 ]
 
 
@@ -104,6 +106,13 @@ def lib():
         L.asvgfBandSetSynchronize.argtypes = [vp]
         L.asvgfBandSetBeginTiming.argtypes = [vp]
         L.asvgfBandSetEndTiming.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+        L.asvgfImportExternalMemoryFd.argtypes = [ctypes.c_int32, ctypes.c_int, ctypes.c_uint64, u32, ctypes.POINTER(vp)]
+        L.asvgfExternalMemoryGetBuffer.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(vp)]
+        L.asvgfDestroyExternalMemory.argtypes = [vp]
+        L.asvgfImportExternalSemaphoreFd.argtypes = [ctypes.c_int32, ctypes.c_int, u32, ctypes.POINTER(vp)]
+        L.asvgfWaitExternalSemaphore.argtypes = [vp, vp, ctypes.c_uint64]
+        L.asvgfSignalExternalSemaphore.argtypes = [vp, vp, ctypes.c_uint64]
+        L.asvgfDestroyExternalSemaphore.argtypes = [vp]
         L.asvgfResultString.argtypes = [ctypes.c_int]
         L.asvgfResultString.restype = ctypes.c_char_p
         L.asvgfLastErrorMessage.restype = ctypes.c_char_p
@@ -322,3 +331,48 @@ class BandSet:
         per = (ctypes.c_float * len(self.bands))()
         _check(lib().asvgfBandSetEndTiming(self._h, ctypes.byref(worst), per), "asvgfBandSetEndTiming")
         return worst.value, list(per)
+
+
+class ExternalMemory:
+    """CUDA half of the Vulkan interop: an exported memory object (opaque fd) imported and mapped as linear device memory."""
+
+    def __init__(self, fd, size, device=-1, dedicated=False):
+        self._h = ctypes.c_void_p()
+        self.size = size
+        _check(lib().asvgfImportExternalMemoryFd(device, fd, size, 1 if dedicated else 0, ctypes.byref(self._h)),
+               "asvgfImportExternalMemoryFd")
+
+    def buffer(self, offset=0, size=None):
+        p = ctypes.c_void_p()
+        _check(lib().asvgfExternalMemoryGetBuffer(self._h, offset, self.size - offset if size is None else size, ctypes.byref(p)),
+               "asvgfExternalMemoryGetBuffer")
+        return p.value
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().asvgfDestroyExternalMemory(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+
+class ExternalSemaphore:
+    """An exported Vulkan semaphore (binary or timeline, fd) imported for stream-ordered wait / signal."""
+
+    def __init__(self, fd, device=-1, timeline=False):
+        self._h = ctypes.c_void_p()
+        _check(lib().asvgfImportExternalSemaphoreFd(device, fd, 1 if timeline else 0, ctypes.byref(self._h)),
+               "asvgfImportExternalSemaphoreFd")
+
+    def wait(self, stream=0, value=0):
+        _check(lib().asvgfWaitExternalSemaphore(self._h, ctypes.c_void_p(stream), value), "asvgfWaitExternalSemaphore")
+
+    def signal(self, stream=0, value=0):
+        _check(lib().asvgfSignalExternalSemaphore(self._h, ctypes.c_void_p(stream), value), "asvgfSignalExternalSemaphore")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().asvgfDestroyExternalSemaphore(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
