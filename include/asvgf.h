@@ -172,6 +172,17 @@ ASVGF_API AsvgfResult asvgfLuminanceHistogram( AsvgfDenoiser denoiser, AsvgfStre
                                                const AsvgfGlobalUniform* pUniform );
 ASVGF_API AsvgfResult asvgfLuminanceAverage( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
                                              const AsvgfGlobalUniform* pUniform );
+/* = ImageComposition::Finalize -> ApplyTonemapping (Source/ImageComposition.cpp:94-155, CmPrepareFinal.comp:144-172): the dispatch
+   that turns the resolved frame into what the raster / bloom / upscale chain consumes.  In place on ASVGF_IMAGE_FINAL:
+   Final * transmittance + in-scattering (ASVGF_IMAGE_SCATTERING), exposure from the eye-adapted average luminance this library's
+   asvgfCalculateExposure keeps (Exposure.h:36-58), AMD LPM tonemap (Uncharted 2 on the classic-shading columns), + ASVGF_IMAGE_ACID_FOG,
+   the debug views of debugShowFlags; writes ASVGF_IMAGE_BLOOM_INPUT.  pLpmControl = the 24 x uvec4 (96 x uint32) control block
+   ImageComposition::SetupLpmParams computes on the host with AMD's LpmSetup (ImageComposition.cpp:365-420); read during the call.
+   Call order of the reference frame: asvgfDenoise, asvgfScatterAccumulate, asvgfCalculateExposure, asvgfResolveCheckerboard, ...,
+   asvgfPrepareFinal (VulkanDevice.cpp:583-590, 608-612).  ASVGF_UNSUPPORTED on band handles and for DEBUG_SHOW_FLAG_LIGHT_GRID. */
+ASVGF_API AsvgfResult asvgfPrepareFinal( AsvgfDenoiser denoiser, AsvgfStream stream, uint32_t frameIndex,
+                                         const AsvgfGlobalUniform* pUniform, const uint32_t* pLpmControl );
+
 /* = Volumetric::ProcessScattering(cmd, frameIndex, uniform, ..., maxHistoryLength) (Source/Volumetric.cpp:71-195), shader
    CmScatterAccum.comp:96-163: the frame's other temporal-reprojection pass.  Reprojects
    ASVGF_IMAGE_SCATTERING_PREV / _HISTORY_PREV with the temporal pass's disocclusion tests and blends in this frame's

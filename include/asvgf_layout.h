@@ -72,6 +72,7 @@ enum AsvgfImageIndex
     ASVGF_IMAGE_ACID_FOG                     = 53, /* ... and its resolved form (asvgfResolveCheckerboard, CmCheckerboard.comp:65-77) */
     ASVGF_IMAGE_SCREEN_EMIS_RT               = 54, /* B10G11R11_UFLOAT, regular layout: screen-space emission, checkerboarded ...      */
     ASVGF_IMAGE_SCREEN_EMISSION              = 55, /* ... and resolved                                                                 */
+    ASVGF_IMAGE_BLOOM_INPUT                  = 56, /* B10G11R11_UFLOAT, regular layout: what the bloom chain reads (asvgfPrepareFinal)          */
     ASVGF_IMAGE_GRADIENT_INPUTS              = 70, /* R16G16_SFLOAT                               */
     ASVGF_IMAGE_GRADIENT_INPUTS_PREV         = 71,
     ASVGF_IMAGE_DIS_PING_GRADIENT            = 72, /* R8G8B8A8_UNORM, 1/3 resolution              */
@@ -145,13 +146,18 @@ typedef struct AsvgfGlobalUniform
     float    timeDelta;            /*  664 */
     float    minLogLuminance;      /*  668  exposure histogram range (CmLuminanceHistogram.comp, CmLuminanceAvg.comp) */
     float    maxLogLuminance;      /*  672 */
-    float    luminanceWhitePoint;  /*  676  (not read by this library) */
+    float    luminanceWhitePoint;  /*  676  asvgfPrepareFinal, classic-shading columns (CmPrepareFinal.comp:89-93) */
     uint32_t stopEyeAdaptation;    /*  680 */
     uint32_t _reserved2[ 9 ];      /*  684 */
     float    cameraPosition[ 4 ];  /*  720 */
     float    cameraPositionPrev[ 4 ]; /* 736 */
     uint32_t debugShowFlags;       /*  752 */
-    uint32_t _reserved3[ 19 ];     /*  756 */
+    uint32_t _reserved3[ 4 ];      /*  756 */
+    float    emissionMaxScreenColor; /* 772  asvgfPrepareFinal (CmPrepareFinal.comp:119) */
+    uint32_t _reserved3a[ 7 ];     /*  776 */
+    float    bloomThreshold;       /*  804  asvgfPrepareFinal (CmPrepareFinal.comp:139) */
+    float    bloomEmissionMultiplier; /* 808  (CmPrepareFinal.comp:128) */
+    uint32_t _reserved3c[ 5 ];     /*  812 */
     uint32_t volumeEnableType;     /*  832  ASVGF_VOLUME_ENABLE_* (asvgfScatterAccumulate) */
     float    volumeScattering;     /*  836 */
     uint32_t _reserved3b[ 23 ];    /*  840 */
@@ -181,6 +187,10 @@ static_assert( sizeof( AsvgfGlobalUniform ) == 2096, "must match ShGlobalUniform
 static_assert( offsetof( AsvgfGlobalUniform, minLogLuminance ) == 668, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, stopEyeAdaptation ) == 680, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, volumeEnableType ) == 832, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, emissionMaxScreenColor ) == 772, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, bloomThreshold ) == 804, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, bloomEmissionMultiplier ) == 808, "layout" );
+static_assert( offsetof( AsvgfGlobalUniform, luminanceWhitePoint ) == 676, "layout" );
 static_assert( offsetof( AsvgfGlobalUniform, volumeAmbient ) == 992, "layout" );
 static_assert( sizeof( AsvgfTonemapping ) == 1028, "must match ShTonemapping" );
 static_assert( offsetof( AsvgfGlobalUniform, viewPrev ) == 128, "layout" );

@@ -44,6 +44,7 @@ def lib():
         L.asvgfOracleDenoise.argtypes = [vp, u32, ctypes.POINTER(layout.GlobalUniform)]
         puni = ctypes.POINTER(layout.GlobalUniform)
         L.asvgfOracleResolveCheckerboard.argtypes = [vp, u32, puni]
+        L.asvgfOraclePrepareFinal.argtypes = [vp, u32, puni, ctypes.c_void_p]
         L.asvgfOracleLuminanceHistogram.argtypes = [vp, u32, puni]
         L.asvgfOracleLuminanceAverage.argtypes = [vp, puni]
         L.asvgfOracleCalculateExposure.argtypes = [vp, u32, puni]
@@ -118,6 +119,12 @@ class Oracle:
 
     def resolve_checkerboard(self, frame_index, uniform):
         lib().asvgfOracleResolveCheckerboard(self._h, frame_index, ctypes.byref(uniform))
+
+    def prepare_final(self, frame_index, uniform, lpm_control):
+        import numpy as np
+        lpm = np.ascontiguousarray(lpm_control, dtype=np.uint32)
+        assert lpm.size == 96
+        lib().asvgfOraclePrepareFinal(self._h, frame_index, ctypes.byref(uniform), lpm.ctypes.data)
 
     def luminance_histogram(self, frame_index, uniform):
         lib().asvgfOracleLuminanceHistogram(self._h, frame_index, ctypes.byref(uniform))

@@ -447,7 +447,7 @@ int bytesPerPixelOf( uint32_t i )
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: return 16;
         case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV:
         case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR: case ASVGF_IMAGE_UNFILTERED_INDIR:
-        case ASVGF_IMAGE_ACID_FOG_RT: case ASVGF_IMAGE_ACID_FOG: case ASVGF_IMAGE_SCREEN_EMIS_RT: case ASVGF_IMAGE_SCREEN_EMISSION:
+        case ASVGF_IMAGE_ACID_FOG_RT: case ASVGF_IMAGE_ACID_FOG: case ASVGF_IMAGE_SCREEN_EMIS_RT: case ASVGF_IMAGE_SCREEN_EMISSION: case ASVGF_IMAGE_BLOOM_INPUT:
         case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR:
         case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS: case ASVGF_IMAGE_DIFF_ACCUM_MOMENTS_PREV:
         case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR:
@@ -1341,6 +1341,116 @@ void resolveCheckerboard( AsvgfOracle_T& o, uint32_t fi, const Ctx& c )
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Final prepare, CmPrepareFinal.comp:99-226 (ImageComposition::ApplyTonemapping, Source/ImageComposition.cpp:110-155): Final and
+// the in-scattering are composed, exposed with the eye-adapted EV100 (Exposure.h:36-58) and tonemapped -- AMD's LPM for the
+// ray-traced columns (LpmMap of LPM/ffx_lpm.h:727-831 in the configuration LpmFilter gets at CmPrepareFinal.comp:71:
+// shoulder, con, soft, con2, clip, scaleOnly all false), Uncharted 2 for the classic-shading columns -- and the bloom input is
+// written.  lpm = the 24 x uvec4 control block ImageComposition::SetupLpmParams computes on the host (ImageComposition.cpp:365-420).
+// Pin: log2 / exp2 are the correctly rounded fp32 values, as in the exposure passes; pow() is libm's (glslPow).
+// ---------------------------------------------------------------------------------------------------------------
+struct LpmConstants // the members of the control block this configuration reads (ffx_lpm.h:913-938)
+{
+    vec3  saturation; float contrast; // map0
+    float toneScaleBiasX, toneScaleBiasY; vec3 lumaT; // map1.rg, map1.ba + map2.r
+    vec3  crosstalk; // map2.gba
+    vec3  rcpLumaT;  // map3.rgb
+};
+LpmConstants lpmConstants( const uint32_t* lpm )
+{
+    auto f = [ & ]( int vec, int comp ) { float v; std::memcpy( &v, &lpm[ vec * 4 + comp ], 4 ); return v; };
+    LpmConstants k;
+    k.saturation = { f( 0, 0 ), f( 0, 1 ), f( 0, 2 ) }; k.contrast = f( 0, 3 );
+    k.toneScaleBiasX = f( 1, 0 ); k.toneScaleBiasY = f( 1, 1 ); k.lumaT = { f( 1, 2 ), f( 1, 3 ), f( 2, 0 ) };
+    k.crosstalk = { f( 2, 1 ), f( 2, 2 ), f( 2, 3 ) };
+    k.rcpLumaT  = { f( 3, 0 ), f( 3, 1 ), f( 3, 2 ) };
+    return k;
+}
+vec3 lpmMap( vec3 c, const LpmConstants& k ) // ffx_lpm.h:747-819 with every optional stage compiled out
+{
+    float colorR = c.x, colorG = c.y, colorB = c.z;
+    float rcpMax = 1.0f / fmaxf( colorR, fmaxf( colorG, colorB ) );
+    float ratioR = colorR * rcpMax, ratioG = colorG * rcpMax, ratioB = colorB * rcpMax;
+    ratioR = glslPow( ratioR, k.saturation.x ); ratioG = glslPow( ratioG, k.saturation.y ); ratioB = glslPow( ratioB, k.saturation.z );
+    float luma = colorG * k.lumaT.y + ( colorR * k.lumaT.x + ( colorB * k.lumaT.z ) );
+    luma       = glslPow( luma, k.contrast );
+    const float lumaShoulder = luma;
+    luma = luma * ( 1.0f / ( lumaShoulder * k.toneScaleBiasX + k.toneScaleBiasY ) );
+    const float lumaRatio  = ( ratioR * k.lumaT.x + ratioG * k.lumaT.y ) + ratioB * k.lumaT.z;
+    const float ratioScale = saturate( luma * ( 1.0f / lumaRatio ) );
+    colorR = saturate( ratioR * ratioScale ); colorG = saturate( ratioG * ratioScale ); colorB = saturate( ratioB * ratioScale );
+    const float capR = ( -k.crosstalk.x ) * colorR + k.crosstalk.x;
+    const float capG = ( -k.crosstalk.y ) * colorG + k.crosstalk.y;
+    const float capB = ( -k.crosstalk.z ) * colorB + k.crosstalk.z;
+    float lumaAdd = saturate( ( -colorB ) * k.lumaT.z + ( ( -colorR ) * k.lumaT.x + ( ( -colorG ) * k.lumaT.y + luma ) ) );
+    const float t = lumaAdd * ( 1.0f / ( capG * k.lumaT.y + ( capR * k.lumaT.x + ( capB * k.lumaT.z ) ) ) );
+    colorR = saturate( t * capR + colorR ); colorG = saturate( t * capG + colorG ); colorB = saturate( t * capB + colorB );
+    lumaAdd = saturate( ( -colorB ) * k.lumaT.z + ( ( -colorR ) * k.lumaT.x + ( ( -colorG ) * k.lumaT.y + luma ) ) );
+    colorR = saturate( lumaAdd * k.rcpLumaT.x + colorR );
+    colorG = saturate( lumaAdd * k.rcpLumaT.y + colorG );
+    colorB = saturate( lumaAdd * k.rcpLumaT.z + colorB );
+    return { colorR, colorG, colorB };
+}
+float uncharted2Op( float x ) // CmPrepareFinal.comp:75-85
+{
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ( ( x * ( A * x + C * B ) + D * E ) / ( x * ( A * x + B ) + D * F ) ) - E / F;
+}
+void prepareFinal( AsvgfOracle_T& o, uint32_t fi, const Ctx& c, const uint32_t* lpm )
+{
+    Img& final = o.get( ASVGF_IMAGE_FINAL, fi ); Img& emis = o.get( ASVGF_IMAGE_SCREEN_EMISSION, fi ); Img& scat = o.get( ASVGF_IMAGE_SCATTERING, fi );
+    Img& fog = o.get( ASVGF_IMAGE_ACID_FOG, fi ); Img& bloomOut = o.get( ASVGF_IMAGE_BLOOM_INPUT, fi );
+    Img& motion = o.get( ASVGF_IMAGE_MOTION, fi ); Img& disPing = o.get( ASVGF_IMAGE_DIS_PING_GRADIENT, fi ); Img& normal = o.get( ASVGF_IMAGE_NORMAL, fi );
+    const uint32_t unf[ 3 ] = { ASVGF_IMAGE_UNFILTERED_DIRECT, ASVGF_IMAGE_UNFILTERED_SPECULAR, ASVGF_IMAGE_UNFILTERED_INDIR };
+    const LpmConstants k = lpmConstants( lpm );
+    // Exposure.h:36-58 (S = 100, K = 12.5)
+    const float ev100 = ( float )std::log2( ( double )( fmaxf( 0.0f, o.tm.avgLuminance ) * 100.0f / 12.5f ) );
+    auto luminousExposure = [ & ]( float ev ) { const float maxLuminance = 1.2f * ( float )std::exp2( ( double )ev ); return maxLuminance > 0.0f ? 1.0f / maxLuminance : 0.0f; };
+    const float exposure    = luminousExposure( ev100 );
+    const float bloomLum    = ( float )std::exp2( ( double )( ( ev100 + c.u->bloomEmissionMultiplier ) - 3.0f ) ); // ev100ToLuminance(evBloom)
+    const float whiteScale  = uncharted2Op( c.u->luminanceWhitePoint );
+    const uint32_t flags    = c.u->debugShowFlags;
+#pragma omp parallel for schedule( static )
+    for( int y = 0; y < c.H; y++ )
+    {
+        for( int x = 0; x < c.W; x++ )
+        {
+            const ivec2 pix = { x, y };
+            vec3        hdr        = fetchUf11( final, pix );       // :152
+            const vec3  screenEmis = fetchUf11( emis, pix );
+            {
+                const vec4 volumetric = fetchRGBA16F( scat, pix );  // :155-158
+                hdr = hdr * volumetric.w + vec3{ volumetric.x, volumetric.y, volumetric.z };
+            }
+            vec3 color; // finalizeColor :107-119
+            if( ( float )x < c.u->lightmapScreenCoverage * c.u->renderWidth ) // classicShading, ShaderCommonGLSLFunc.h:492-495
+            {
+                const vec3 h2 = 2.0f * hdr;
+                color = { uncharted2Op( h2.x ) / whiteScale, uncharted2Op( h2.y ) / whiteScale, uncharted2Op( h2.z ) / whiteScale };
+            }
+            else color = lpmMap( hdr * exposure + screenEmis * c.u->emissionMaxScreenColor, k );
+            vec3 bloom = ( hdr + screenEmis * bloomLum ) * exposure; // getBloomInput :123-140
+            if( std::isnan( bloom.x ) || std::isnan( bloom.y ) || std::isnan( bloom.z ) || std::isinf( bloom.x ) || std::isinf( bloom.y ) || std::isinf( bloom.z ) )
+                bloom = { 0.0f, 0.0f, 0.0f };
+            bloom = bloom * smoothstepf( 0.0f, c.u->bloomThreshold, getLuminance( bloom ) );
+            color = color + fetchUf11( fog, pix ); // SHIPPING_HACK (ShaderCommonGLSLFunc.h:49), :163-165
+            if( flags != 0 ) // processDebug :175-226
+            {
+                const ivec2 cb = getCheckerboardPix( c, pix );
+                if( flags & 1u ) { const vec4 m = fetchRGBA16F( motion, cb ); color = { fabsf( m.x ), fabsf( m.y ), 0.0f }; }
+                else if( flags & ( 1u << 2 ) ) color = fetchE5( o.get( unf[ 0 ], fi ), cb );
+                else if( flags & ( 1u << 3 ) ) color = fetchE5( o.get( unf[ 1 ], fi ), cb );
+                else if( flags & ( 1u << 4 ) ) color = fetchE5( o.get( unf[ 2 ], fi ), cb );
+                else if( flags & ( 1u << 8 ) ) { /* DEBUG_SHOW_FLAG_LIGHT_GRID needs the light grid of the ray tracer: not on this path (fallback kept) */ }
+                else if( flags & ( 1u << 1 ) ) { const vec4 g = fetchRGBA8( disPing, { cb.x / ASVGF_STRATA_SIZE, cb.y / ASVGF_STRATA_SIZE } ); color = { g.x, g.y, g.z }; }
+                else if( flags & ( 1u << 10 ) ) { const vec3 n = decodeNormal( fetchU32( normal, cb ) ); color = n * 0.5f + vec3{ 0.5f, 0.5f, 0.5f }; }
+            }
+            storeU32( final, pix, packUfloat111110( color ) );    // :170-171
+            storeU32( bloomOut, pix, packUfloat111110( bloom ) );
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Exposure: CmLuminanceHistogram.comp:38-86 and CmLuminanceAvg.comp:37-89 (Tonemapping.cpp:59-175).
 // Pin: log2 / exp2 / exp, whose GLSL precision is implementation-defined, are the correctly rounded fp32 values
 // (evaluated in double, rounded once) -- the same convention as the sin/cos of the normal codec.
@@ -1466,6 +1576,11 @@ void asvgfOracleResolveCheckerboard( AsvgfOracle o, uint32_t frameIndex, const A
 {
     Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };
     resolveCheckerboard( *o, frameIndex, c );
+}
+void asvgfOraclePrepareFinal( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u, const uint32_t* lpmControl96 ) // ImageComposition.cpp:110-155
+{
+    Ctx c = { u, ( int )u->renderWidth, ( int )u->renderHeight };
+    prepareFinal( *o, frameIndex, c, lpmControl96 );
 }
 void asvgfOracleLuminanceHistogram( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u )
 {

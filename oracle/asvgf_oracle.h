@@ -44,6 +44,9 @@ void asvgfOracleLuminanceHistogram( AsvgfOracle o, uint32_t frameIndex, const As
 void asvgfOracleLuminanceAverage( AsvgfOracle o, const AsvgfGlobalUniform* u );
 void asvgfOracleCalculateExposure( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u );
 AsvgfTonemapping* asvgfOracleGetTonemapping( AsvgfOracle o );
+/* CmPrepareFinal.comp (second half): exposure + LPM / Uncharted 2 tonemap of Final, bloom input;
+   lpmControl96 = the 24 x uvec4 block of ImageComposition::SetupLpmParams; reads the oracle's own AsvgfTonemapping state */
+void asvgfOraclePrepareFinal( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u, const uint32_t* lpmControl96 );
 /* CmScatterAccum.comp: temporal accumulation of the volumetric scattering */
 void asvgfOracleScatterAccumulate( AsvgfOracle o, uint32_t frameIndex, const AsvgfGlobalUniform* u, float maxHistoryLength );
 

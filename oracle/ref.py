@@ -95,7 +95,7 @@ class RefDenoiser:
             descs[idx] = _ImageDesc(a.ctypes.data, a.shape[1], a.shape[0], _SHIM_FORMAT[info[1]])
         return descs
 
-    def dispatch(self, shader, frame_index, uniform, size_x, size_y, spec_constant=0, push=None):
+    def dispatch(self, shader, frame_index, uniform, size_x, size_y, spec_constant=0, push=None, lpm=None):
         L = lib()
         if shader not in self._local:
             xy = (ctypes.c_uint32 * 2)()
@@ -110,6 +110,8 @@ class RefDenoiser:
         # descriptor sets as the shaders number them: global uniform = set 1 binding 0; tonemapping = set 2 binding 0
         ctx.buffers[1][0] = u
         ctx.buffers[2][0] = tm
+        if lpm is not None:     # DESC_SET_LPM_PARAMS = 3 (CmPrepareFinal.comp:26), BINDING_LPM_PARAMS = 0
+            ctx.buffers[3][0] = lpm.ctypes.data
         ctx.specConstant[0] = spec_constant
         if push is not None:
             raw = np.frombuffer(np.asarray(push, dtype=np.float32).tobytes(), dtype=np.uint32)
@@ -155,3 +157,21 @@ class RefDenoiser:
     def scatter_accumulate(self, frame_index, uniform, max_history_length):   # Volumetric.cpp:71-195
         self.dispatch("CmScatterAccum", frame_index, uniform, uniform.renderWidth, uniform.renderHeight,
                       push=[max_history_length])
+
+    def prepare_final(self, frame_index, uniform, lpm_control):  # ImageComposition.cpp:110-155 (ApplyTonemapping)
+        lpm = np.ascontiguousarray(lpm_control, dtype=np.uint32)
+        assert lpm.size == 96
+        self.dispatch("CmPrepareFinal", frame_index, uniform, uniform.renderWidth, uniform.renderHeight, lpm=lpm)
+
+
+def lpm_setup(saturation=(0.0, 0.0, 0.0), crosstalk=(1.0, 1.0, 1.0)):
+    """The 24 x uvec4 LPM control block as ImageComposition::SetupLpmParams computes it (ImageComposition.cpp:365-420; AMD's LpmSetup
+    from the reference's vendored headers, compiled in their CPU mode by oracle/ref_glsl/lpm_setup_ref.cpp).  Defaults =
+    RgDrawFrameTonemappingParams' defaults (Source/DrawFrameInfo.h:104-105)."""
+    out = np.zeros(96, dtype=np.uint32)
+    sat = (ctypes.c_float * 3)(*saturation)
+    cro = (ctypes.c_float * 3)(*crosstalk)
+    fn = lib().asvgfRefLpmSetup
+    fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    fn(out.ctypes.data, sat, cro)
+    return out

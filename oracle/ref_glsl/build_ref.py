@@ -43,6 +43,7 @@ SHADERS = [
     "CmLuminanceHistogram.comp",
     "CmLuminanceAvg.comp",
     "CmScatterAccum.comp",
+    "CmPrepareFinal.comp",
 ]
 
 FORMATS = ["r8ui", "r32ui", "rgba32ui", "rg8", "rgba8", "r8", "r16f", "rg16f", "rgba16f", "r32f", "rgba32f", "r11f_g11f_b10f"]
@@ -193,6 +194,8 @@ def transform(glsl, name):
     if info["local"] is None:
         raise RuntimeError(name + ": no local size")
 
+    # GLM declares these two as well and argument-dependent lookup would find both: name the shim's (pinned rounding) explicitly
+    t = re.sub(r"(?<![\w:])(packHalf2x16|unpackHalf2x16)\s*\(", r"glslshim::\1(", t)
     t = re.sub(r"\bshared\s+", "inline static thread_local ", t)
     # parameter qualifiers (the text has no comments any more)
     t = re.sub(r"([(,]\s*)(?:const\s+)?(?:inout|out)\s+(\w+)\s+(\w+)", r"\1\2& \3", t)
@@ -279,6 +282,11 @@ def main():
         return 1
     shim_obj = os.path.join(OUT, "gen", "glsl_shim.o")
     subprocess.run(cxx + ["-c", os.path.join(HERE, "glsl_shim.cpp"), "-o", shim_obj], check=True)
+    # the host-side LPM setup of ImageComposition::SetupLpmParams: AMD's headers compiled in their CPU mode where they lie
+    lpm_obj = os.path.join(OUT, "gen", "lpm_setup_ref.o")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", os.path.join(shaders_dir, "LPM"),
+                    "-c", os.path.join(HERE, "lpm_setup_ref.cpp"), "-o", lpm_obj], check=True)
+    objs.append(lpm_obj)
     lib = os.path.join(OUT, "libasvgf_ref.so")
     subprocess.run(cxx + ["-shared", "-o", lib] + objs + [shim_obj], check=True)
     open(os.path.join(OUT, "shaders.txt"), "w").write("\n".join(built) + "\n")

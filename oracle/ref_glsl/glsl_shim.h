@@ -385,6 +385,11 @@ inline vec2  unpackHalf2x16( uint p ) { return vec2( fromSmallFloat( p & 0xffffu
 inline uint  packUnorm4x8( const vec4& v ) { return toUnorm8( v.x ) | ( toUnorm8( v.y ) << 8 ) | ( toUnorm8( v.z ) << 16 ) | ( toUnorm8( v.w ) << 24 ); }
 inline vec4  unpackUnorm4x8( uint p ) { return vec4( ( float )( p & 0xffu ) / 255.0f, ( float )( ( p >> 8 ) & 0xffu ) / 255.0f, ( float )( ( p >> 16 ) & 0xffu ) / 255.0f, ( float )( p >> 24 ) / 255.0f ); }
 inline uint  bitfieldExtract( uint v, int offset, int bits ) { return bits >= 32 ? v >> offset : ( v >> offset ) & ( ( 1u << bits ) - 1u ); }
+inline uint  bitfieldInsert( uint base, uint insert, int offset, int bits )
+{
+    const uint mask = ( bits >= 32 ? ~0u : ( ( 1u << bits ) - 1u ) ) << offset;
+    return ( base & ~mask ) | ( ( insert << offset ) & mask );
+}
 inline int   findMSB( uint v ) { return v ? 31 - __builtin_clz( v ) : -1; }
 inline int   bitCount( uint v ) { return __builtin_popcount( v ); }
 inline mat4  inverse( const mat4& m ) { return glm::inverse( m ); }
@@ -403,6 +408,14 @@ template< int N, typename T, glm::qualifier Q, int E0, int E1, int E2, int E3 >
 inline void operator+=( glm::detail::_swizzle< N, T, Q, E0, E1, E2, E3 >& s, T f ) { s = s() + f; }
 template< int N, typename T, glm::qualifier Q, int E0, int E1, int E2, int E3 >
 inline void operator-=( glm::detail::_swizzle< N, T, Q, E0, E1, E2, E3 >& s, T f ) { s = s() - f; }
+
+// vec (op)= swizzle: GLM's compound assignments take the swizzle proxy for a scalar
+template< int N, typename T, glm::qualifier Q, int E0, int E1, int E2, int E3 >
+inline glm::vec< N, T, Q >& operator+=( glm::vec< N, T, Q >& a, const glm::detail::_swizzle< N, T, Q, E0, E1, E2, E3 >& b ) { return a += b(); }
+template< int N, typename T, glm::qualifier Q, int E0, int E1, int E2, int E3 >
+inline glm::vec< N, T, Q >& operator-=( glm::vec< N, T, Q >& a, const glm::detail::_swizzle< N, T, Q, E0, E1, E2, E3 >& b ) { return a -= b(); }
+template< int N, typename T, glm::qualifier Q, int E0, int E1, int E2, int E3 >
+inline glm::vec< N, T, Q >& operator*=( glm::vec< N, T, Q >& a, const glm::detail::_swizzle< N, T, Q, E0, E1, E2, E3 >& b ) { return a *= b(); }
 
 // atomics on shared / buffer memory (work groups run on several OS threads)
 inline uint atomicAdd( uint& mem, uint v ) { return __atomic_fetch_add( &mem, v, __ATOMIC_RELAXED ); }

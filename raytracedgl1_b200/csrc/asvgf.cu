@@ -69,7 +69,7 @@ bool describe( uint32_t i, ImageDesc* d )
             *d = { ASVGF_FORMAT_R16G16B16A16_SFLOAT, 8, false }; return true;
         case ASVGF_IMAGE_SURFACE_POSITION: case ASVGF_IMAGE_SURFACE_POSITION_PREV: *d = { ASVGF_FORMAT_R32G32B32A32_SFLOAT, 16, false }; return true;
         case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_PRE_FINAL: case ASVGF_IMAGE_FINAL: case ASVGF_IMAGE_ACID_FOG_RT: case ASVGF_IMAGE_ACID_FOG:
-        case ASVGF_IMAGE_SCREEN_EMIS_RT: case ASVGF_IMAGE_SCREEN_EMISSION: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
+        case ASVGF_IMAGE_SCREEN_EMIS_RT: case ASVGF_IMAGE_SCREEN_EMISSION: case ASVGF_IMAGE_BLOOM_INPUT: *d = { ASVGF_FORMAT_B10G11R11_UFLOAT, 4, false }; return true;
         case ASVGF_IMAGE_NORMAL: case ASVGF_IMAGE_NORMAL_PREV: case ASVGF_IMAGE_UNFILTERED_DIRECT: case ASVGF_IMAGE_UNFILTERED_SPECULAR:
         case ASVGF_IMAGE_UNFILTERED_INDIR: case ASVGF_IMAGE_DIFF_TEMPORARY: case ASVGF_IMAGE_DIFF_ACCUM_COLOR: case ASVGF_IMAGE_DIFF_ACCUM_COLOR_PREV:
         case ASVGF_IMAGE_SPEC_ACCUM_COLOR: case ASVGF_IMAGE_SPEC_ACCUM_COLOR_PREV: case ASVGF_IMAGE_SPEC_PING_COLOR: case ASVGF_IMAGE_SPEC_PONG_COLOR:
@@ -185,6 +185,11 @@ struct AsvgfDenoiser_T
     bool      haveLut     = false;
     // internal per-frame scratch: the decoded geometry of the current frame (asvgf_atrous_tiled.cuh, k_guide)
     Img       guide{}, centre{};
+    // V split (asvgf_args.cuh, VarianceArgs): queue of the pixels that need the spatial estimate
+    uint32_t* vList = nullptr;
+    uint32_t* vCount = nullptr;
+    uint32_t  vCapacity = 0;
+    bool      varianceSplit = true;  // ASVGF_NO_VSPLIT=1 at asvgfCreate: the variance pass stays one full-frame dispatch (A/B; identical results)
     uint32_t* haloMiss = nullptr;  // band handles: device flag set by a reprojected tap outside the stored rows (asvgf_args.cuh)
     bool      centreValid = false; // `centre` holds the weight constants of the frame being denoised (written by a-trous iteration 0)
     // cross-stream ordering of the gradient chain (asvgfGradientSamples may be given another stream than asvgfDenoise):
@@ -374,8 +379,19 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.color = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
     a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
     a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
+    a.vList = d.vList; a.vCount = d.vCount; a.vCapacity = d.vCapacity;
+    if( d.varianceSplit && d.vList )
+    {
+        cudaError_t e = cudaMemsetAsync( d.vCount, 0, sizeof( uint32_t ), s );
+        if( e != cudaSuccess ) return cudaFail( e, "cudaMemsetAsync(variance queue)" );
+        k_variance_fast< true ><<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+        AsvgfResult r = launchCheck( d, "k_variance" );
+        if( r != ASVGF_SUCCESS ) return r;
+        k_variance_fallback<<< ( unsigned )std::max( d.smCount, 1 ) * 4u, 256, 0, s >>>( a, u );
+        return launchCheck( d, "k_variance_fallback" );
+    }
     ASVGF_LITERAL_OR( d, ( k_variance<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_variance_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
+                      ( k_variance_fast< false ><<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_variance" );
 }
 
@@ -500,6 +516,30 @@ AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t
     a.pairs = ( a.src[ 1 ].p && a.dst[ 1 ].p && a.src[ 2 ].p && a.dst[ 2 ].p ) ? 3 : 1;
     k_checkerboard_resolve<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_checkerboard_resolve" );
+}
+
+AsvgfResult runPrepareFinal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, const AsvgfGlobalUniform& g, const uint32_t* lpm )
+{
+    NEED( ASVGF_IMAGE_FINAL, ASVGF_IMAGE_SCREEN_EMISSION, ASVGF_IMAGE_SCATTERING, ASVGF_IMAGE_ACID_FOG, ASVGF_IMAGE_BLOOM_INPUT );
+    if( g.debugShowFlags != 0 ) NEED( ASVGF_IMAGE_MOTION, ASVGF_IMAGE_DIS_PING_GRADIENT, ASVGF_IMAGE_NORMAL, ASVGF_IMAGE_UNFILTERED_DIRECT, ASVGF_IMAGE_UNFILTERED_SPECULAR, ASVGF_IMAGE_UNFILTERED_INDIR );
+    const NvtxRange range( "Prefinal framebuf compose" ); // ImageComposition.cpp:116
+    PrepareFinalArgs a;
+    a.final = d.get( ASVGF_IMAGE_FINAL, fi ); a.screenEmission = d.get( ASVGF_IMAGE_SCREEN_EMISSION, fi ); a.scattering = d.get( ASVGF_IMAGE_SCATTERING, fi );
+    a.acidFog = d.get( ASVGF_IMAGE_ACID_FOG, fi ); a.bloomInput = d.get( ASVGF_IMAGE_BLOOM_INPUT, fi );
+    a.motion = d.get( ASVGF_IMAGE_MOTION, fi ); a.disPing = d.get( ASVGF_IMAGE_DIS_PING_GRADIENT, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi );
+    a.unfiltered[ 0 ] = d.get( ASVGF_IMAGE_UNFILTERED_DIRECT, fi ); a.unfiltered[ 1 ] = d.get( ASVGF_IMAGE_UNFILTERED_SPECULAR, fi ); a.unfiltered[ 2 ] = d.get( ASVGF_IMAGE_UNFILTERED_INDIR, fi );
+    a.lut = d.lut; a.tm = d.tm;
+    // the members of the 24 x uvec4 control block LpmFilter hands to LpmMap in this configuration (LPM/ffx_lpm.h:913-938)
+    auto f = [ & ]( int vec, int comp ) { float v; std::memcpy( &v, &lpm[ vec * 4 + comp ], 4 ); return v; };
+    for( int i = 0; i < 3; i++ ) { a.saturation[ i ] = f( 0, i ); a.crosstalk[ i ] = f( 2, 1 + i ); a.rcpLumaT[ i ] = f( 3, i ); }
+    a.contrast = f( 0, 3 ); a.toneScaleBias[ 0 ] = f( 1, 0 ); a.toneScaleBias[ 1 ] = f( 1, 1 );
+    a.lumaT[ 0 ] = f( 1, 2 ); a.lumaT[ 1 ] = f( 1, 3 ); a.lumaT[ 2 ] = f( 2, 0 );
+    a.luminanceWhitePoint = g.luminanceWhitePoint; a.emissionMaxScreenColor = g.emissionMaxScreenColor;
+    a.bloomThreshold = g.bloomThreshold; a.bloomEmissionMultiplier = g.bloomEmissionMultiplier;
+    a.classicEdge = g.lightmapScreenCoverage * g.renderWidth;
+    a.debugShowFlags = g.debugShowFlags;
+    k_prepare_final<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    return launchCheck( d, "k_prepare_final" );
 }
 
 AsvgfResult runScatterAccumulate( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u, const AsvgfGlobalUniform& g, float maxHistoryLength )
@@ -696,6 +736,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     if( const char* e = std::getenv( "ASVGF_ATROUS_PAIR" ) ) d->atrousPair = std::atoi( e ) != 0;
     if( const char* e = std::getenv( "ASVGF_ATROUS_CENTRE" ) ) d->atrousCentre = std::atoi( e ) != 0;
+    if( const char* e = std::getenv( "ASVGF_NO_VSPLIT" ) ) d->varianceSplit = std::atoi( e ) == 0;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
     if( pInfo->bandRowEnd == 0 )
@@ -818,6 +859,13 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(centre plane)" );
         }
         setImgStorage( c, memC, pitch, 16 );
+        d->vCapacity = d->W * ( uint32_t )g.rows;
+        if( cudaMalloc( ( void** )&d->vList, ( size_t )d->vCapacity * sizeof( uint32_t ) ) != cudaSuccess || cudaMalloc( ( void** )&d->vCount, sizeof( uint32_t ) ) != cudaSuccess ||
+            cudaMemset( d->vCount, 0, sizeof( uint32_t ) ) != cudaSuccess )
+        {
+            asvgfDestroy( d );
+            return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(variance queue)" );
+        }
         if( pInfo->bandRowEnd != 0 )
         {
             if( cudaMalloc( ( void** )&d->haloMiss, sizeof( uint32_t ) ) != cudaSuccess || cudaMemset( d->haloMiss, 0, sizeof( uint32_t ) ) != cudaSuccess )
@@ -840,6 +888,8 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
     if( d->haveLut ) releaseLut( d->device );
     if( d->guide.p ) cudaFree( d->guide.p );
     if( d->centre.p ) cudaFree( d->centre.p );
+    if( d->vList ) cudaFree( d->vList );
+    if( d->vCount ) cudaFree( d->vCount );
     if( d->haloMiss ) cudaFree( d->haloMiss );
     if( d->evTemporalDone ) cudaEventDestroy( d->evTemporalDone );
     if( d->evGradientsDone ) cudaEventDestroy( d->evGradientsDone );
@@ -1026,6 +1076,17 @@ AsvgfResult asvgfResolveCheckerboard( AsvgfDenoiser d, AsvgfStream stream, uint3
     if( d->info.bandRowEnd != 0 ) return fail( ASVGF_UNSUPPORTED, "asvgfResolveCheckerboard on a band handle: the resolve reads PreFinal one row beyond the band, which no pass writes and no exchange fills (gather the frame on one device first)" );
     DeviceGuard guard( d->device );
     return runResolveCheckerboard( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ) );
+}
+
+AsvgfResult asvgfPrepareFinal( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform, const uint32_t* pLpmControl )
+{
+    AsvgfResult r = checkCall( d, frameIndex, pUniform );
+    if( r != ASVGF_SUCCESS ) return r;
+    if( !pLpmControl ) return fail( ASVGF_WRONG_ARGUMENT, "null LPM control block" );
+    if( d->info.bandRowEnd != 0 ) return fail( ASVGF_UNSUPPORTED, "asvgfPrepareFinal on a band handle: Final is the resolved frame, which band handles do not produce (asvgfResolveCheckerboard)" );
+    if( pUniform->debugShowFlags & ( 1u << 8 ) ) return fail( ASVGF_UNSUPPORTED, "DEBUG_SHOW_FLAG_LIGHT_GRID needs the ray tracer's light grid (LightGrid.h): not an image-space input of this library" );
+    DeviceGuard guard( d->device );
+    return runPrepareFinal( *d, ( cudaStream_t )stream, frameIndex, makeUniform( *d, *pUniform ), *pUniform, pLpmControl );
 }
 
 AsvgfResult asvgfScatterAccumulate( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform, float maxHistoryLength )

@@ -22,6 +22,8 @@
 //  * 64 registers, 41-51 KB of shared memory: four CTAs = 32 warps per SM.
 #pragma once
 
+#include <type_traits>
+
 #include "asvgf_fast.cuh"
 
 namespace asvgf
@@ -390,6 +392,44 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
     auto      jOf = [ & ]( int k ) { return PAIR ? 2 * m + k : m + 4 * k; };
     const int px = xBase + c;
 
+    // ---- tiles without a single valid surface (sky): every pixel passes its centre texel through (CmSVGFAtrous.comp:96-99;
+    //      iteration 0 stores zeros, CmSVGFAtrous_Iter0.comp:208-216) and no neighbourhood is read: skip staging and taps ----
+#ifndef ASVGF_AT_NO_SKY_TILES
+    {
+        bool anyValid = false;
+#pragma unroll
+        for( int k = 0; k < PIX; k++ )
+        {
+            const int  py = yBase + jOf( k ) * STEP;
+            const bool ok = px < u.W && py < u.yEnd;
+            const float dz = h2f( ldIf< uint16_t >( a.depth, px, py, ok, ( uint16_t )0x7c00 ) ); // the depth the guide plane carries
+            anyValid = anyValid || ( ok && !( dz < 0.0f || dz > 10000.0f ) );
+        }
+        if( !__syncthreads_or( anyValid ) )
+        {
+#pragma unroll
+            for( int k = 0; k < PIX; k++ )
+            {
+                const int py = yBase + jOf( k ) * STEP;
+                if( px >= u.W || py >= u.yEnd ) continue;
+                float3 oDiff = make_float3( 0.0f, 0.0f, 0.0f ), oSpec = oDiff, oIndir = oDiff;
+                float  oVar  = 0.0f;
+                if( !ITER0 )
+                {
+                    const uint2  dd = __ldg( at< uint2 >( a.srcDiff, px, py ) );
+                    const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd.x ) );
+                    const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd.y ) );
+                    oDiff = make_float3( rg.x, rg.y, bv.x ); oVar = bv.y;
+                    oSpec  = decodeE5( __ldg( at< uint32_t >( a.srcSpec, px, py ) ) );
+                    oIndir = decodeE5( __ldg( at< uint32_t >( a.srcIndir, px, py ) ) );
+                }
+                atrousStore< LAST >( a, u, px, py, oDiff, oVar, oSpec, oIndir );
+            }
+            return;
+        }
+    }
+#endif
+
     // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----
     static_assert( !( ITER0 && CENTRE ), "iteration 0 writes the centre plane" );
     uint16_t cGrad[ PIX ], cSigma[ PIX ], cSpecLen[ PIX ];
@@ -499,18 +539,24 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
             begin( s, ce, k, py, true );
             if( !s.invalid )
             {
-                const bool okT = py - STEP >= 0, okB = py + STEP < u.H;
+                // interior tiles (all but the frame / checkerboard-separator borders): every tap is inside, lk is an immediate
+                auto taps = [ & ]( auto interior ) {
+                    constexpr bool INTERIOR = decltype( interior )::value;
+                    const bool okT = py - STEP >= 0, okB = py + STEP < u.H;
 #pragma unroll
-                for( int yy = -1; yy <= 1; yy++ )
+                    for( int yy = -1; yy <= 1; yy++ )
 #pragma unroll
-                    for( int xx = -1; xx <= 1; xx++ )
-                    {
-                        if( xx == 0 && yy == 0 ) continue;
-                        const bool  diag = xx != 0 && yy != 0;
-                        const int   qe   = ce + yy * RP + xx * dC;
-                        const bool  in   = tileInterior || ( ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true ) );
-                        s.tap( sA[ qe ], sB[ qe ], sC[ qe ], sD[ qe ], diag, in ? ( diag ? -2.0f : -1.0f ) : NINF );
-                    }
+                        for( int xx = -1; xx <= 1; xx++ )
+                        {
+                            if( xx == 0 && yy == 0 ) continue;
+                            const bool  diag = xx != 0 && yy != 0;
+                            const int   qe   = ce + yy * RP + xx * dC;
+                            const bool  in   = INTERIOR || ( ( xx < 0 ? okL : xx > 0 ? okR : true ) && ( yy < 0 ? okT : yy > 0 ? okB : true ) );
+                            s.tap( sA[ qe ], sB[ qe ], sC[ qe ], sD[ qe ], diag, in ? ( diag ? -2.0f : -1.0f ) : NINF );
+                        }
+                };
+                if( tileInterior ) taps( std::true_type{} );
+                else taps( std::false_type{} );
             }
             finish( s, py, ce );
         }

@@ -292,6 +292,9 @@ ASVGF_DEVICE float specAccumSpeedFast( float minFrames, float Amax, float roughn
 // runs as packed half2 min/max: separable (row windows of 5, and of 4 without the centre, for two adjacent output
 // columns per lane from three 8-byte shared loads; then a sliding vertical combine in registers).
 // ------------------------------------------------------------------------------------------------------------
+#ifndef ASVGF_AF_MIN_CTAS
+    #define ASVGF_AF_MIN_CTAS 4
+#endif
 constexpr int kAfTile = 64, kAfR = 2, kAfT = kAfTile + 2 * kAfR, kAfThreads = 256, kAfStrip = 8;
 constexpr int kAfBPitch = kAfT + 4; // halves per row of the B plane (keeps rows 8-byte aligned)
 
@@ -311,7 +314,7 @@ struct AfRow // one tile row's contribution for a lane's two output columns: win
     uint32_t rg0, rg1, b;
 };
 
-__global__ void __launch_bounds__( kAfThreads ) k_antifirefly_fast( const __grid_constant__ AntiFireflyArgs a, const __grid_constant__ Uniform u )
+__global__ void __launch_bounds__( kAfThreads, ASVGF_AF_MIN_CTAS ) k_antifirefly_fast( const __grid_constant__ AntiFireflyArgs a, const __grid_constant__ Uniform u )
 {
     __shared__ __align__( 16 ) uint32_t sRG[ kAfT ][ kAfT ];
     __shared__ __align__( 16 ) uint16_t sB[ kAfT ][ kAfBPitch ];
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__( kAfThreads ) k_antifirefly_fast( const __grid
                 const float2 f0 = __half22float2( *reinterpret_cast< const __half2* >( &c.rg0 ) );
                 const float2 f1 = __half22float2( *reinterpret_cast< const __half2* >( &c.rg1 ) );
                 const float2 fb = __half22float2( *reinterpret_cast< const __half2* >( &c.b ) );
-                const uint2  o  = make_uint2( encodeE5Unclamped( f0.x, f0.y, fb.x ), encodeE5Unclamped( f1.x, f1.y, fb.y ) );
+                const uint2  o  = make_uint2( encodeE5Magic( f0.x, f0.y, fb.x ), encodeE5Magic( f1.x, f1.y, fb.y ) );
                 *reinterpret_cast< uint2* >( atW< uint32_t >( dst, gx, gy ) ) = o;
             }
         }
@@ -428,6 +431,49 @@ __global__ void __launch_bounds__( kAfThreads ) k_antifirefly_fast( const __grid
 // ------------------------------------------------------------------------------------------------------------
 // V: variance estimation
 // ------------------------------------------------------------------------------------------------------------
+// the spatial estimate of CmSVGFEstimateVariance.comp:163-205 for a pixel with too little history: 3x3 bilateral moments; also
+// filters the colour
+ASVGF_DEVICE float varianceSpatial( const VarianceArgs& a, const Rows& rows, int px, int py, float pixDepth, float historyLength, float2 temporalMoments, float3& color )
+{
+    float variance;
+    const float  l  = flum( color );
+    float        m1 = l + temporalMoments.x, m2 = fmaf( l, l, temporalMoments.y );
+    float        weightSum = 1.0f;
+    const float3 n = decodeNormal( a.lut, __ldg( at< uint32_t >( a.normal, px, py ) ) );
+    constexpr float LOG2E = 1.4426950408889634f;
+#pragma unroll
+    for( int k = 0; k < 9; k++ ) // :168-196; out-of-image and cross-separator neighbours participate as zeros
+    {
+        if( k == 4 ) continue;
+        const int      qx = px + k % 3 - 1, qy = py + k / 3 - 1;
+        const bool     ok = rows.in( qx, qy );
+        const float3   colorQ = decodeE5( ldIf< uint32_t >( a.color, qx, qy, ok, 0u ) );
+        const float    depthQ = h2f( ldIf< uint16_t >( a.depth, qx, qy, ok, ( uint16_t )0 ) );
+        const float3   nQ     = decodeNormal( a.lut, ldIf< uint32_t >( a.normal, qx, qy, ok, 0u ) );
+        const float    lQ     = flum( colorQ );
+        const float    zm     = fmaxf( pixDepth, depthQ );
+        const float    ez     = fabsf( pixDepth - depthQ ) * ( zm <= 0.0f ? 0.0f : frcp( zm ) );
+        const float    nN     = fmaxf( 0.0f, n.x * nQ.x + n.y * nQ.y + n.z * nQ.z );
+        const float    w      = fex2( fmaf( 128.0f, fmaxf( flg2( nN ), -1.0e4f ), -ez * LOG2E ) ); // exp(-ez) * nN^128
+        if( !isnan( w ) )
+        {
+            m1 = fmaf( lQ, w, m1 );
+            m2 = fmaf( lQ * lQ, w, m2 );
+            color.x = fmaf( colorQ.x, w, color.x ); color.y = fmaf( colorQ.y, w, color.y ); color.z = fmaf( colorQ.z, w, color.z );
+            weightSum += w;
+        }
+    }
+    const float inv = weightSum <= 0.0f ? 0.0f : frcp( weightSum );
+    m1 *= inv; m2 *= inv;
+    color = make_float3( color.x * inv, color.y * inv, color.z * inv );
+    variance = fmaxf( 0.0f, subr( m2, mulr( m1, m1 ) ) ) * fmaf( 2.0f, 1.0f - historyLength * 0.25f, 1.0f );
+    return variance;
+}
+
+// QUEUE = true (asvgfDenoise): a pixel with too little history is not estimated here -- one such lane would hold its whole warp for the
+// ~500 instructions of the 3x3 estimate -- but queued (warp-aggregated append) for k_variance_fallback, which runs the estimate on
+// full warps.  QUEUE = false: the single dispatch of the reference (asvgfDenoisePass).  Same results bit for bit.
+template< bool QUEUE >
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance_fast( const __grid_constant__ VarianceArgs a, const __grid_constant__ Uniform u )
 {
     const int px = blockIdx.x * kBlockW + threadIdx.x;
@@ -455,41 +501,46 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance_fast( const __g
         }
         else
         {
-            const float  l  = flum( color );
-            float        m1 = l + temporalMoments.x, m2 = fmaf( l, l, temporalMoments.y );
-            float        weightSum = 1.0f;
-            const float3 n = decodeNormal( a.lut, __ldg( at< uint32_t >( a.normal, px, py ) ) );
-            constexpr float LOG2E = 1.4426950408889634f;
-#pragma unroll
-            for( int k = 0; k < 9; k++ ) // :168-196; out-of-image and cross-separator neighbours participate as zeros
+            // (a warp where at least half of the lanes need the estimate -- the first frames after a reset -- runs it in place: queueing
+            //  would only add the round trip through the list)
+            const uint32_t act = QUEUE ? __activemask() : 0u;
+            if( QUEUE && __popc( act ) < 16 )
             {
-                if( k == 4 ) continue;
-                const int      qx = px + k % 3 - 1, qy = py + k / 3 - 1;
-                const bool     ok = rows.in( qx, qy );
-                const float3   colorQ = decodeE5( ldIf< uint32_t >( a.color, qx, qy, ok, 0u ) );
-                const float    depthQ = h2f( ldIf< uint16_t >( a.depth, qx, qy, ok, ( uint16_t )0 ) );
-                const float3   nQ     = decodeNormal( a.lut, ldIf< uint32_t >( a.normal, qx, qy, ok, 0u ) );
-                const float    lQ     = flum( colorQ );
-                const float    zm     = fmaxf( pixDepth, depthQ );
-                const float    ez     = fabsf( pixDepth - depthQ ) * ( zm <= 0.0f ? 0.0f : frcp( zm ) );
-                const float    nN     = fmaxf( 0.0f, n.x * nQ.x + n.y * nQ.y + n.z * nQ.z );
-                const float    w      = fex2( fmaf( 128.0f, fmaxf( flg2( nN ), -1.0e4f ), -ez * LOG2E ) ); // exp(-ez) * nN^128
-                if( !isnan( w ) )
-                {
-                    m1 = fmaf( lQ, w, m1 );
-                    m2 = fmaf( lQ * lQ, w, m2 );
-                    color.x = fmaf( colorQ.x, w, color.x ); color.y = fmaf( colorQ.y, w, color.y ); color.z = fmaf( colorQ.z, w, color.z );
-                    weightSum += w;
-                }
+                const uint32_t lane = threadIdx.x & 31u, leader = ( uint32_t )( __ffs( ( int )act ) - 1 );
+                uint32_t       base = 0u;
+                if( lane == leader ) base = atomicAdd( a.vCount, ( uint32_t )__popc( act ) );
+                base = __shfl_sync( act, base, ( int )leader );
+                const uint32_t idx = base + ( uint32_t )__popc( act & ( ( 1u << lane ) - 1u ) );
+                if( idx < a.vCapacity ) a.vList[ idx ] = ( uint32_t )px | ( ( uint32_t )py << 16 );
+                return; // k_variance_fallback writes this texel
             }
-            const float inv = weightSum <= 0.0f ? 0.0f : frcp( weightSum );
-            m1 *= inv; m2 *= inv;
-            color = make_float3( color.x * inv, color.y * inv, color.z * inv );
-            variance = fmaxf( 0.0f, subr( m2, mulr( m1, m1 ) ) ) * fmaf( 2.0f, 1.0f - historyLength * 0.25f, 1.0f );
+            else variance = varianceSpatial( a, rows, px, py, pixDepth, historyLength, temporalMoments, color );
         }
     }
     const __half2 o0 = __floats2half2_rn( color.x, color.y ), o1 = __floats2half2_rn( color.z, variance );
     *atW< uint2 >( a.out, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
+}
+
+// V split, second half: the pixels k_variance_fast<true> queued.  Grid-stride over the queue: under one percent of the frame in
+// steady state, every valid pixel in the first four frames after a reset.
+__global__ void __launch_bounds__( 256 ) k_variance_fallback( const __grid_constant__ VarianceArgs a, const __grid_constant__ Uniform u )
+{
+    const Rows     rows = rowsOf( a.depth );
+    const uint32_t n    = min( __ldg( a.vCount ), a.vCapacity );
+    for( uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u )
+    {
+        const uint32_t e  = __ldg( a.vList + i );
+        const int      px = ( int )( e & 0xffffu ), py = ( int )( e >> 16 );
+        const float  pixDepth        = h2f( __ldg( at< uint16_t >( a.depth, px, py ) ) );
+        float3       color           = decodeE5( __ldg( at< uint32_t >( a.color, px, py ) ) );
+        const uint2  hl              = __ldg( at< uint2 >( a.histLen, px, py ) );
+        const uint32_t mo            = __ldg( at< uint32_t >( a.moments, px, py ) );
+        const float  historyLength   = __low2float( *reinterpret_cast< const __half2* >( &hl.x ) );
+        const float2 temporalMoments = __half22float2( *reinterpret_cast< const __half2* >( &mo ) );
+        const float  variance        = varianceSpatial( a, rows, px, py, pixDepth, historyLength, temporalMoments, color );
+        const __half2 o0 = __floats2half2_rn( color.x, color.y ), o1 = __floats2half2_rn( color.z, variance );
+        *atW< uint2 >( a.out, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
+    }
 }
 
 } // namespace asvgf

@@ -324,4 +324,128 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __g
     *atW< uint16_t >( a.hist, regX, py ) = f2h( historyLen );
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Final prepare: CmPrepareFinal.comp:99-226 (ImageComposition::ApplyTonemapping, Source/ImageComposition.cpp:110-155).
+// One thread per regular pixel: Final * transmittance + in-scattering, exposure from the eye-adapted average luminance
+// (Exposure.h:36-58), AMD LPM tonemap of the ray-traced columns (LpmMap, LPM/ffx_lpm.h:747-819, in the 709 -> 709 configuration
+// the shader instantiates: every optional stage off) or Uncharted 2 on the classic-shading columns, + AcidFog, the debug views,
+// and the bloom input.  Arithmetic in the shader's order (explicitly rounded); pow() is powf.  The three scalars every pixel
+// shares -- luminous exposure, bloom luminance, the white-point scale -- need log2 / exp2 at the pinned precision (correctly
+// rounded fp32): one thread per CTA evaluates them in double.
+// ------------------------------------------------------------------------------------------------------------
+struct PrepareFinalArgs
+{
+    Img       final, screenEmission, scattering, acidFog, bloomInput;
+    Img       motion, disPing, normal, unfiltered[ 3 ]; // the debug views (CmPrepareFinal.comp:175-226)
+    NormalLut lut;
+    const AsvgfTonemapping* tm;
+    float     saturation[ 3 ], contrast, toneScaleBias[ 2 ], lumaT[ 3 ], crosstalk[ 3 ], rcpLumaT[ 3 ]; // LPM control block, ffx_lpm.h:913-938
+    float     luminanceWhitePoint, emissionMaxScreenColor, bloomThreshold, bloomEmissionMultiplier;
+    float     classicEdge; // lightmapScreenCoverage * renderWidth (ShaderCommonGLSLFunc.h:492-495)
+    uint32_t  debugShowFlags;
+};
+
+ASVGF_DEVICE float uncharted2Op( float x ) // CmPrepareFinal.comp:75-85
+{
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    const float num = addr( mulr( x, addr( mulr( A, x ), mulr( C, B ) ) ), mulr( D, E ) );
+    const float den = addr( mulr( x, addr( mulr( A, x ), B ) ), mulr( D, F ) );
+    return subr( divr( num, den ), divr( E, F ) );
+}
+
+ASVGF_DEVICE float3 lpmMap709( const PrepareFinalArgs& a, float3 c )
+{
+    const float sat01lo = 0.0f;
+    auto  sat = [ & ]( float x ) { return fminf( fmaxf( x, sat01lo ), 1.0f ); };
+    float colorR = c.x, colorG = c.y, colorB = c.z;
+    const float rcpMax = divr( 1.0f, fmaxf( colorR, fmaxf( colorG, colorB ) ) );
+    float ratioR = powf( mulr( colorR, rcpMax ), a.saturation[ 0 ] ), ratioG = powf( mulr( colorG, rcpMax ), a.saturation[ 1 ] ), ratioB = powf( mulr( colorB, rcpMax ), a.saturation[ 2 ] );
+    float luma = addr( mulr( colorG, a.lumaT[ 1 ] ), addr( mulr( colorR, a.lumaT[ 0 ] ), mulr( colorB, a.lumaT[ 2 ] ) ) );
+    luma       = powf( luma, a.contrast );
+    luma       = mulr( luma, divr( 1.0f, addr( mulr( luma, a.toneScaleBias[ 0 ] ), a.toneScaleBias[ 1 ] ) ) );
+    const float lumaRatio  = addr( addr( mulr( ratioR, a.lumaT[ 0 ] ), mulr( ratioG, a.lumaT[ 1 ] ) ), mulr( ratioB, a.lumaT[ 2 ] ) );
+    const float ratioScale = sat( mulr( luma, divr( 1.0f, lumaRatio ) ) );
+    colorR = sat( mulr( ratioR, ratioScale ) ); colorG = sat( mulr( ratioG, ratioScale ) ); colorB = sat( mulr( ratioB, ratioScale ) );
+    const float capR = addr( mulr( -a.crosstalk[ 0 ], colorR ), a.crosstalk[ 0 ] );
+    const float capG = addr( mulr( -a.crosstalk[ 1 ], colorG ), a.crosstalk[ 1 ] );
+    const float capB = addr( mulr( -a.crosstalk[ 2 ], colorB ), a.crosstalk[ 2 ] );
+    auto lumaMissing = [ & ]() { return sat( addr( mulr( -colorB, a.lumaT[ 2 ] ), addr( mulr( -colorR, a.lumaT[ 0 ] ), addr( mulr( -colorG, a.lumaT[ 1 ] ), luma ) ) ) ); };
+    float       lumaAdd = lumaMissing();
+    const float t = mulr( lumaAdd, divr( 1.0f, addr( mulr( capG, a.lumaT[ 1 ] ), addr( mulr( capR, a.lumaT[ 0 ] ), mulr( capB, a.lumaT[ 2 ] ) ) ) ) );
+    colorR = sat( addr( mulr( t, capR ), colorR ) ); colorG = sat( addr( mulr( t, capG ), colorG ) ); colorB = sat( addr( mulr( t, capB ), colorB ) );
+    lumaAdd = lumaMissing();
+    return make_float3( sat( addr( mulr( lumaAdd, a.rcpLumaT[ 0 ] ), colorR ) ), sat( addr( mulr( lumaAdd, a.rcpLumaT[ 1 ] ), colorG ) ), sat( addr( mulr( lumaAdd, a.rcpLumaT[ 2 ] ), colorB ) ) );
+}
+
+__global__ void __launch_bounds__( kBlockW* kBlockH ) k_prepare_final( const __grid_constant__ PrepareFinalArgs a, const __grid_constant__ Uniform u )
+{
+    __shared__ float sScalars[ 3 ];
+    if( threadIdx.x == 0 && threadIdx.y == 0 )
+    {
+        // Exposure.h:36-58: EV100 = log2(avgLuminance * S / K), S = 100, K = 12.5
+        const float ev100 = ( float )log2( ( double )divr( mulr( fmaxf( 0.0f, a.tm->avgLuminance ), 100.0f ), 12.5f ) );
+        const float maxLuminance = mulr( 1.2f, ( float )exp2( ( double )ev100 ) );
+        sScalars[ 0 ] = maxLuminance > 0.0f ? divr( 1.0f, maxLuminance ) : 0.0f;                              // ev100ToLuminousExposure
+        sScalars[ 1 ] = ( float )exp2( ( double )subr( addr( ev100, a.bloomEmissionMultiplier ), 3.0f ) );    // ev100ToLuminance(evBloom)
+        sScalars[ 2 ] = uncharted2Op( a.luminanceWhitePoint );
+    }
+    __syncthreads();
+    const int x = blockIdx.x * kBlockW + threadIdx.x;
+    const int y = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
+    if( x >= u.W || y >= u.yEnd ) return;
+    const float exposure = sScalars[ 0 ], bloomLum = sScalars[ 1 ], whiteScale = sScalars[ 2 ];
+
+    float3       hdr  = unpackUfloat111110( __ldg( at< uint32_t >( a.final, x, y ) ) );
+    const float3 emis = unpackUfloat111110( __ldg( at< uint32_t >( a.screenEmission, x, y ) ) );
+    {
+        const uint2  v   = __ldg( at< uint2 >( a.scattering, x, y ) );
+        const float2 v01 = __half22float2( *reinterpret_cast< const __half2* >( &v.x ) ), v23 = __half22float2( *reinterpret_cast< const __half2* >( &v.y ) );
+        hdr = make_float3( addr( mulr( hdr.x, v23.y ), v01.x ), addr( mulr( hdr.y, v23.y ), v01.y ), addr( mulr( hdr.z, v23.y ), v23.x ) );
+    }
+    float3 color;
+    if( ( float )x < a.classicEdge )
+        color = make_float3( divr( uncharted2Op( mulr( 2.0f, hdr.x ) ), whiteScale ), divr( uncharted2Op( mulr( 2.0f, hdr.y ) ), whiteScale ), divr( uncharted2Op( mulr( 2.0f, hdr.z ) ), whiteScale ) );
+    else
+        color = lpmMap709( a, make_float3( addr( mulr( hdr.x, exposure ), mulr( emis.x, a.emissionMaxScreenColor ) ), addr( mulr( hdr.y, exposure ), mulr( emis.y, a.emissionMaxScreenColor ) ),
+                                           addr( mulr( hdr.z, exposure ), mulr( emis.z, a.emissionMaxScreenColor ) ) ) );
+    float3 bloom = make_float3( mulr( addr( hdr.x, mulr( emis.x, bloomLum ) ), exposure ), mulr( addr( hdr.y, mulr( emis.y, bloomLum ) ), exposure ), mulr( addr( hdr.z, mulr( emis.z, bloomLum ) ), exposure ) );
+    if( !( fabsf( bloom.x ) < __uint_as_float( 0x7f800000u ) && fabsf( bloom.y ) < __uint_as_float( 0x7f800000u ) && fabsf( bloom.z ) < __uint_as_float( 0x7f800000u ) ) )
+        bloom = make_float3( 0.0f, 0.0f, 0.0f ); // any NaN or Inf
+    {
+        const float k = smoothstepr( 0.0f, a.bloomThreshold, luminance( bloom ) );
+        bloom = make_float3( mulr( bloom.x, k ), mulr( bloom.y, k ), mulr( bloom.z, k ) );
+    }
+    {
+        const float3 fog = unpackUfloat111110( __ldg( at< uint32_t >( a.acidFog, x, y ) ) ); // SHIPPING_HACK, ShaderCommonGLSLFunc.h:49
+        color = make_float3( addr( color.x, fog.x ), addr( color.y, fog.y ), addr( color.z, fog.z ) );
+    }
+    if( a.debugShowFlags != 0u )
+    {
+        const int sep = u.W / 2, isOdd = ( x + y % 2 ) % 2, cbx = isOdd * sep + x / 2; // getCheckerboardPix
+        const uint32_t f = a.debugShowFlags;
+        if( f & 1u )
+        {
+            const uint2  m   = __ldg( at< uint2 >( a.motion, cbx, y ) );
+            const float2 m01 = __half22float2( *reinterpret_cast< const __half2* >( &m.x ) );
+            color = make_float3( fabsf( m01.x ), fabsf( m01.y ), 0.0f );
+        }
+        else if( f & ( 1u << 2 ) ) color = decodeE5( __ldg( at< uint32_t >( a.unfiltered[ 0 ], cbx, y ) ) );
+        else if( f & ( 1u << 3 ) ) color = decodeE5( __ldg( at< uint32_t >( a.unfiltered[ 1 ], cbx, y ) ) );
+        else if( f & ( 1u << 4 ) ) color = decodeE5( __ldg( at< uint32_t >( a.unfiltered[ 2 ], cbx, y ) ) );
+        else if( f & ( 1u << 8 ) ) { /* light grid: rejected by the host (not on this path) */ }
+        else if( f & ( 1u << 1 ) )
+        {
+            const uint32_t g = __ldg( at< uint32_t >( a.disPing, cbx / 3, y / 3 ) );
+            color = make_float3( unorm8ToFloatFast( g & 0xffu ), unorm8ToFloatFast( ( g >> 8 ) & 0xffu ), unorm8ToFloatFast( ( g >> 16 ) & 0xffu ) );
+        }
+        else if( f & ( 1u << 10 ) )
+        {
+            const float3 n = decodeNormal( a.lut, __ldg( at< uint32_t >( a.normal, cbx, y ) ) );
+            color = make_float3( addr( mulr( n.x, 0.5f ), 0.5f ), addr( mulr( n.y, 0.5f ), 0.5f ), addr( mulr( n.z, 0.5f ), 0.5f ) );
+        }
+    }
+    *atW< uint32_t >( a.final, x, y )      = packUfloat111110( color );
+    *atW< uint32_t >( a.bloomInput, x, y ) = packUfloat111110( bloom );
+}
+
 } // namespace asvgf

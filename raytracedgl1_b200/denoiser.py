@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "asvgfSynchronize", "asvgfGetLaunchCount", "asvgfPassName", "asvgfPassBytesPerPixel", "asvgfResultString",
     "asvgfLastErrorMessage", "asvgfPassKernelName", "asvgfBandApronRows", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
     "asvgfLuminanceAverage", "asvgfGetTonemappingBuffer", "asvgfUploadTonemapping", "asvgfDownloadTonemapping",
-    "asvgfScatterAccumulate",
+    "asvgfScatterAccumulate", "asvgfPrepareFinal",
     "asvgfBandSetCreate", "asvgfBandSetDestroy", "asvgfBandSetGetBandCount", "asvgfBandSetGetBand", "asvgfBandSetFrame",
     "asvgfBandSetSynchronize", "asvgfBandSetBeginTiming", "asvgfBandSetEndTiming",
     "asvgfImportExternalMemoryFd", "asvgfExternalMemoryGetBuffer", "asvgfDestroyExternalMemory", "asvgfImportExternalSemaphoreFd",
@@ -84,6 +84,7 @@ def lib():
         for name in ("asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram", "asvgfLuminanceAverage"):
             getattr(L, name).argtypes = [vp, vp, u32, puni]
         L.asvgfScatterAccumulate.argtypes = [vp, vp, u32, puni, ctypes.c_float]
+        L.asvgfPrepareFinal.argtypes = [vp, vp, u32, puni, ctypes.c_void_p]
         L.asvgfGetTonemappingBuffer.argtypes = [vp, ctypes.POINTER(vp)]
         L.asvgfUploadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
         L.asvgfDownloadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
@@ -222,6 +223,13 @@ class Denoiser:
     def resolve_checkerboard(self, frame_index, uniform, stream=0):
         """= ImageComposition::PrepareForRaster (Source/ImageComposition.cpp:87-92): PreFinal -> Final."""
         _check(lib().asvgfResolveCheckerboard(self._h, stream, frame_index, ctypes.byref(uniform)), "asvgfResolveCheckerboard")
+
+    def prepare_final(self, frame_index, uniform, lpm_control, stream=0):
+        """lpm_control: the 96 uint32 of the host-side LPM setup (ImageComposition::SetupLpmParams)."""
+        lpm = np.ascontiguousarray(lpm_control, dtype=np.uint32)
+        if lpm.size != 96:
+            raise ValueError("the LPM control block holds 24 x uvec4")
+        _check(lib().asvgfPrepareFinal(self._h, stream, frame_index, ctypes.byref(uniform), lpm.ctypes.data), "asvgfPrepareFinal")
 
     def calculate_exposure(self, frame_index, uniform, stream=0):
         """= Tonemapping::CalculateExposure (Source/Tonemapping.cpp:59-175): histogram + eye adaptation."""

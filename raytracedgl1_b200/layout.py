@@ -67,6 +67,7 @@ IMAGES = {
     "AcidFog": (53, B10G11R11_UFLOAT, False, "out"),
     "ScreenEmisRT": (54, B10G11R11_UFLOAT, False, "in"),
     "ScreenEmission": (55, B10G11R11_UFLOAT, False, "out"),
+    "BloomInput": (56, B10G11R11_UFLOAT, False, "out"),            # asvgfPrepareFinal (CmPrepareFinal.comp:171)
     "GradientInputs": (70, R16G16_SFLOAT, False, "in"),
     "GradientInputs_Prev": (71, R16G16_SFLOAT, False, "in"),
     "DISPingGradient": (72, R8G8B8A8_UNORM, True, "scratch"),
@@ -137,7 +138,9 @@ class GlobalUniform(ctypes.Structure):
         ("_reserved2", ctypes.c_uint32 * 9),
         ("cameraPosition", ctypes.c_float * 4), ("cameraPositionPrev", ctypes.c_float * 4),
         ("debugShowFlags", ctypes.c_uint32),
-        ("_reserved3", ctypes.c_uint32 * 19),
+        ("_reserved3", ctypes.c_uint32 * 4), ("emissionMaxScreenColor", ctypes.c_float),
+        ("_reserved3a", ctypes.c_uint32 * 7), ("bloomThreshold", ctypes.c_float), ("bloomEmissionMultiplier", ctypes.c_float),
+        ("_reserved3c", ctypes.c_uint32 * 5),
         ("volumeEnableType", ctypes.c_uint32), ("volumeScattering", ctypes.c_float),
         ("_reserved3b", ctypes.c_uint32 * 23),
         ("jitterX", ctypes.c_float), ("jitterY", ctypes.c_float),

@@ -28,12 +28,17 @@ W, H, N, FRAMES = 96, 54, 4, 4
 PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "asvgf_ref_96x54.npz")
 # everything the chain writes (state, scratch and outputs), plus the post passes' outputs
 NAMES = [n for n, info in layout.IMAGES.items() if info[3] != "in" and n not in ("DebugMask", "FwdLum", "ScatterCurrent")]
-POST = ["Final", "ScreenEmission", "AcidFog", "Scattering", "ScatteringHistory"]
+POST = ["Final", "ScreenEmission", "AcidFog", "Scattering", "ScatteringHistory", "BloomInput"]
+# LPM control blocks of the reference's host-side setup (oracle.ref.lpm_setup = AMD's LpmSetup as ImageComposition::SetupLpmParams
+# calls it): RTGL1's default tonemapping parameters, and a tinted set; stored in the fixture so that they travel
+LPM_PARAMS = {"lpm_default": ((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)), "lpm_tinted": ((0.1, -0.2, 0.05), (1.0, 0.5, 0.25))}
 
 
 def edit_uniform(u):
     u.volumeEnableType, u.volumeScattering = 1, 1500.0           # VOLUME_ENABLE_SIMPLE
     u.volumeAmbient[0], u.volumeAmbient[1], u.volumeAmbient[2] = 0.7, 0.8, 1.0
+    # CmPrepareFinal.comp's uniforms at the reference's defaults (Source/DrawFrameInfo.h:103,118-119,177); a classic-shading strip
+    u.luminanceWhitePoint, u.bloomThreshold, u.bloomEmissionMultiplier, u.emissionMaxScreenColor = 10.0, 4.0, 16.0, 1.5
 
 
 def inputs(frame):
@@ -48,10 +53,10 @@ def inputs(frame):
     return g
 
 
-def run(side):
+def run(side, lpm):
     """side: an object with the Oracle surface (oracle.Oracle or oracle.ref.RefDenoiser); gradient samples come from
-    `gradient_source` when the side has none."""
-    out = {}
+    `gradient_source` when the side has none.  lpm: {name: 96 x uint32} control blocks (LPM_PARAMS)."""
+    out = {k: np.array(v, dtype=np.uint32) for k, v in lpm.items()}
     grad = oracle.Oracle(W, H, N) if not hasattr(side, "gradient_samples") else None
     for f in range(FRAMES):
         fi = f & 1
@@ -80,7 +85,12 @@ def run(side):
         out["f%d_avgLuminance" % f] = np.array([side.tonemapping.avgLuminance], dtype=np.float32)
         side.resolve_checkerboard(fi, u)
         for n in POST:
-            out["f%d_%s" % (f, n)] = np.array(side.image(n, fi), copy=True)
+            if n != "BloomInput":
+                out["f%d_%s" % (f, n)] = np.array(side.image(n, fi), copy=True)
+        # ImageComposition::Finalize (CmPrepareFinal.comp): Final is tonemapped in place, the bloom input written
+        side.prepare_final(fi, u, lpm["lpm_default" if f % 2 == 0 else "lpm_tinted"])
+        out["f%d_FinalPrepared" % f] = np.array(side.image("Final", fi), copy=True)
+        out["f%d_BloomInput" % f] = np.array(side.image("BloomInput", fi), copy=True)
     if grad is not None:
         grad.close()
     return out
@@ -90,5 +100,5 @@ if __name__ == "__main__":
     from oracle import ref
     oracle.build(); synth.build(); ref.build()
     r = ref.RefDenoiser(W, H)
-    np.savez_compressed(PATH, **run(r))
+    np.savez_compressed(PATH, **run(r, {k: ref.lpm_setup(*v) for k, v in LPM_PARAMS.items()}))
     print("wrote", PATH, os.path.getsize(PATH), "bytes")

@@ -48,12 +48,11 @@ def test_band_set_is_bit_identical_to_the_single_handle(bands, boundaries):
 
 
 def test_band_set_across_devices_is_bit_identical():
-    """The same gate with the bands on DIFFERENT GPUs (peer copies over NVLink); needs at least two devices."""
+    """The same gate with the bands on DIFFERENT GPUs (peer copies over NVLink) when the box has several; on a one-GPU box the
+    device list degenerates to [0, 0] (two bands of a 640x720 frame on one device) instead of skipping."""
     import torch
     n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("one GPU: the multi-band schedule itself is covered by the single-device cases above")
-    _run(640, 720, list(range(min(n, 4))), None, frames=5)
+    _run(640, 720, list(range(min(n, 4))) if n >= 2 else [0, 0], None, frames=5)
 
 
 def test_band_set_five_iterations_and_ragged_size():

@@ -20,7 +20,7 @@ def test_oracle_reproduces_reference_shader_fixtures():
     ref = np.load(mg.PATH)
     o = oracle.Oracle(mg.W, mg.H, mg.N)
     try:
-        got = mg.run(o)
+        got = mg.run(o, {k: ref[k] for k in mg.LPM_PARAMS})
     finally:
         o.close()
     assert sorted(ref.files) == sorted(got)
@@ -79,6 +79,13 @@ def test_cuda_path_matches_reference_shader_fixtures():
             d.synchronize()
             assert np.float32(d.tonemapping().avgLuminance) == ref["f%d_avgLuminance" % f][0]
             for n in mg.POST:
-                assert np.array_equal(ref["f%d_%s" % (f, n)], d.download(n, fi)), (f, n)
+                if n != "BloomInput":
+                    assert np.array_equal(ref["f%d_%s" % (f, n)], d.download(n, fi)), (f, n)
+            # the final prepare (LPM tonemap: pow() on the device is not libm's): within one code of the 6/6/5-bit mantissas
+            d.prepare_final(fi, u, ref["lpm_default" if f % 2 == 0 else "lpm_tinted"])
+            d.synchronize()
+            for n, key in (("Final", "FinalPrepared"), ("BloomInput", "BloomInput")):
+                r = compare_image(n, ref["f%d_%s" % (f, key)], d.download(n, fi))
+                assert r["ok"] and r["exact_frac"] >= 0.998, (f, n, r)
     finally:
         d.close()

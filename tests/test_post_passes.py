@@ -182,6 +182,70 @@ def test_oracle_scatter_accumulation_known_answers():
         o.close()
 
 
+def _lpm_blocks():
+    """The LPM control blocks of the reference's host-side setup, as stored in the reference-generated fixture."""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asvgf_ref_96x54.npz"))
+    return ref["lpm_default"], ref["lpm_tinted"]
+
+
+def test_oracle_prepare_final_known_answers():
+    """CmPrepareFinal.comp on hand-computed pixels.  Classic-shading columns: Uncharted 2 of 2 * hdr over its white-point value
+    (:75-93); LPM columns: a grey pixel keeps its hue and lands on the tone curve luma^c / (luma^c * a + b) of the control block
+    (ffx_lpm.h:759-761 with ratio = 1); bloom input = (hdr + emission * 2^(EV+m-3)) * exposure * smoothstep (:123-140);
+    exposure = 1 / (1.2 * 2^EV100), EV100 = log2(avg * 100 / 12.5) (Exposure.h:36-58)."""
+    W, H = 16, 4
+    lpm, _ = _lpm_blocks()
+    o = oracle_mod.Oracle(W, H)
+    try:
+        u = synth.uniform(W, H, 0)
+        u.luminanceWhitePoint, u.bloomThreshold, u.bloomEmissionMultiplier, u.emissionMaxScreenColor = 10.0, 4.0, 16.0, 1.5
+        u.lightmapScreenCoverage = 0.5             # columns 0..7 classic, 8..15 ray traced
+        o.tonemapping.avgLuminance = 0.125         # EV100 = log2(1) = 0 -> exposure = 1 / 1.2
+        fin, sc = o.image("Final", 0), o.image("Scattering", 0)
+        grey = [0.0, 0.5, 1.0, 2.0, 8.0, 0.25, 4.0, 16.0]
+        for x in range(W):
+            fin[:, x] = _pack111110(grey[x % 8], grey[x % 8], grey[x % 8])
+        sc[...] = np.array([0, 0, 0, 1], np.float16)   # no in-scattering, full transmittance
+        o.image("ScreenEmission", 0)[...] = 0
+        o.image("AcidFog", 0)[...] = 0
+        o.prepare_final(0, u, lpm)
+        out = layout.decode_b10g11r11(o.image("Final", 0))
+        bloom = layout.decode_b10g11r11(o.image("BloomInput", 0))
+        f32 = np.float32
+
+        def unch(x):
+            A, B, C, D, E, F = map(f32, (0.15, 0.50, 0.10, 0.20, 0.02, 0.30))
+            return ((x * (A * x + C * B) + D * E) / (x * (A * x + B) + D * F)) - E / F
+        exposure = f32(1.0) / (f32(1.2) * f32(1.0))
+        k = lpm.view(np.float32)
+        contrast, tsb_x, tsb_y = k[3], k[4], k[5]
+        for x in range(W):
+            v = f32(grey[x % 8])
+            if x < 8:
+                want = unch(f32(2.0) * v) / unch(f32(10.0))
+            else:
+                luma = np.power(v * exposure * f32(k[6] + k[7] + k[8]), contrast) if v > 0 else f32(0)   # lumaT sums to ~1 on a grey pixel
+                want = min(max(luma / (luma * tsb_x + tsb_y), f32(0)), f32(1))
+            if v == 0 and x >= 8:
+                continue    # black: 0 * (1/0) is NaN in the shader; whatever the pack makes of it is covered by the reference-pinned tests
+            assert abs(out[0, x, 1] - want) <= max(float(want), 1e-3) * 2.0 ** -5, (x, out[0, x], want)
+            assert abs(out[0, x, 0] - out[0, x, 1]) <= max(float(want), 1e-3) * 2.0 ** -5   # grey stays grey
+            b = v * exposure                     # no emission
+            t = min(max(b / f32(4.0), f32(0)), f32(1))
+            wb = b * (t * t * (f32(3) - f32(2) * t))
+            assert abs(bloom[0, x, 1] - wb) <= max(float(wb), 1e-3) * 2.0 ** -5, (x, bloom[0, x], wb)
+        # avgLuminance = 0: EV100 = -inf, the luminous exposure is defined as 0 (Exposure.h:50-54) -> black frame, no NaN
+        o.tonemapping.avgLuminance = 0.0
+        for x in range(W):
+            fin[:, x] = _pack111110(1.0, 2.0, 3.0)
+        u.lightmapScreenCoverage = 0.0
+        o.prepare_final(0, u, lpm)
+        assert not o.image("BloomInput", 0).any()
+    finally:
+        o.close()
+
+
 def test_uniform_and_tonemapping_layout():
     assert layout.GlobalUniform.volumeEnableType.offset == 832 and layout.GlobalUniform.volumeScattering.offset == 836
     assert layout.GlobalUniform.volumeAmbient.offset == 992
@@ -280,5 +344,58 @@ def test_histogram_every_half_pattern_and_flat_image():
             p.oracle.luminance_histogram(0, u)
             p.cuda.luminance_histogram(0, u)
             assert list(p.cuda.tonemapping().histogram) == list(p.oracle.tonemapping.histogram)
+    finally:
+        p.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["default", "tinted_classic_half", "debug_motion", "debug_gradients", "debug_unfiltered_specular", "debug_normals"])
+def test_prepare_final_parity(case):
+    """asvgfPrepareFinal (CmPrepareFinal.comp) against the oracle from identical state, after a full frame + scattering + exposure +
+    resolve.  pow() on the device is CUDA's powf, the oracle's is libm's: the 6/6/5-bit outputs agree within one code, >= 99.8 %
+    of the texels bit for bit; the debug views involve no transcendental and are bit-exact."""
+    from _harness import Pair, compare_image
+    from raytracedgl1_b200 import denoiser as dn
+    W, H = 642, 362
+    lpm_default, lpm_tinted = _lpm_blocks()
+    p = Pair(W, H)
+    try:
+        rng = np.random.default_rng(5)
+        for frame in range(3):
+            def mutate(g):
+                g["Throughput"][..., 3] = (rng.random((H, W)) < 0.33).astype(np.float16)
+                finite = np.uint32(~((1 << 10) | (1 << 21) | (1 << 31)) & 0xFFFFFFFF) & np.uint32(0x3BDEF7BF | 0x3FF)   # modest magnitudes
+                for name in ("ScreenEmisRT", "AcidFogRT"):
+                    g[name] = rng.integers(0, 2 ** 32, size=(H, W), dtype=np.uint64).astype(np.uint32) & finite
+            fi, u = p.run_frame(frame, mutate=mutate)
+            u.volumeEnableType, u.volumeScattering = 1, 1500.0
+            u.luminanceWhitePoint, u.bloomThreshold, u.bloomEmissionMultiplier, u.emissionMaxScreenColor = 10.0, 4.0, 16.0, 1.5
+            lpm = lpm_default
+            if case == "tinted_classic_half":
+                u.lightmapScreenCoverage, lpm = 0.5, lpm_tinted
+            flag = {"debug_motion": 0, "debug_gradients": 1, "debug_unfiltered_specular": 3, "debug_normals": 10}.get(case)
+            p.sync_state_to_cuda()
+            for side in (p.oracle, p.cuda):
+                side.scatter_accumulate(fi, u, 16.0)
+                side.resolve_checkerboard(fi, u)
+                side.luminance_histogram(fi, u)
+            p.oracle.luminance_average(u)
+            p.cuda.luminance_average(fi, u)
+            p.cuda.set_tonemapping(p.oracle.tonemapping)      # identical exposure state on both sides
+            if flag is not None:
+                u.debugShowFlags = 1 << flag
+            p.oracle.prepare_final(fi, u, lpm)
+            p.cuda.prepare_final(fi, u, lpm)
+            p.cuda.synchronize()
+            for name in ("Final", "BloomInput"):
+                ref, got = p.oracle.image(name, fi), p.cuda.download(name, fi)
+                r = compare_image(name, ref, got)
+                assert r["ok"] and r["exact_frac"] >= 0.998, (case, frame, name, r)
+                if flag is not None and name == "Final":
+                    assert np.array_equal(ref, got), (case, frame)
+        u.debugShowFlags = 1 << 8
+        with pytest.raises(dn.AsvgfError) as e:
+            p.cuda.prepare_final(fi, u, lpm_default)
+        assert e.value.code == dn.UNSUPPORTED
     finally:
         p.close()

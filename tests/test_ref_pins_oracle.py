@@ -64,6 +64,8 @@ def _run_sequence(W, H, frames, edit=None, mutate=None):
                 o.image(n, fi)[...] = a
             u = synth.uniform(W, H, frame)
             u.volumeEnableType, u.volumeScattering = 1, 1500.0
+            # the final-prepare uniforms at the reference's defaults (Source/DrawFrameInfo.h:103,118-119,177)
+            u.luminanceWhitePoint, u.bloomThreshold, u.bloomEmissionMultiplier, u.emissionMaxScreenColor = 10.0, 4.0, 16.0, 1.5
             if edit:
                 edit(u)
             o.gradient_samples(fi, u)
@@ -82,6 +84,11 @@ def _run_sequence(W, H, frames, edit=None, mutate=None):
             o.scatter_accumulate(fi, u, 16.0)
             r.scatter_accumulate(fi, u, 16.0)
             _assert_tables_equal(o, r, "%dx%d frame %d post passes" % (W, H, frame))
+            # CmPrepareFinal.comp with the LPM control block of the reference's own host-side setup (defaults, and a tinted one)
+            lpm = ref.lpm_setup() if frame % 2 == 0 else ref.lpm_setup((0.1, -0.2, 0.05), (1.0, 0.5, 0.25))
+            o.prepare_final(fi, u, lpm)
+            r.prepare_final(fi, u, lpm)
+            _assert_tables_equal(o, r, "%dx%d frame %d final prepare" % (W, H, frame))
     finally:
         o.close()
         r.close()
@@ -116,7 +123,8 @@ def test_light_switch_frames():
 
 
 @pytest.mark.parametrize("case", ["antifirefly_off", "debug_white_albedo", "classic_shading_half", "debug_only_specular",
-                                  "debug_only_direct", "debug_only_indirect", "volume_none"])
+                                  "debug_only_direct", "debug_only_indirect", "volume_none", "debug_motion", "debug_gradients",
+                                  "debug_unfiltered_diffuse", "debug_unfiltered_specular", "debug_unfiltered_indirect", "debug_normals"])
 def test_uniform_edges(case):
     def edit(u):
         if case == "antifirefly_off":
@@ -133,6 +141,11 @@ def test_uniform_edges(case):
             u.lightmapScreenCoverage = 0.5
         if case == "volume_none":
             u.volumeEnableType = 0
+        # the debug views of CmPrepareFinal.comp:175-226
+        flag = {"debug_motion": 0, "debug_gradients": 1, "debug_unfiltered_diffuse": 2, "debug_unfiltered_specular": 3,
+                "debug_unfiltered_indirect": 4, "debug_normals": 10}.get(case)
+        if flag is not None:
+            u.debugShowFlags = 1 << flag
     _run_sequence(128, 72, 3, edit=edit)
 
 
