@@ -185,11 +185,6 @@ struct AsvgfDenoiser_T
     bool      haveLut     = false;
     // internal per-frame scratch: the decoded geometry of the current frame (asvgf_atrous_tiled.cuh, k_guide)
     Img       guide{}, centre{};
-    // V split (asvgf_args.cuh, VarianceArgs): queue of the pixels that need the spatial estimate
-    uint32_t* vList = nullptr;
-    uint32_t* vCount = nullptr;
-    uint32_t  vCapacity = 0;
-    bool      varianceSplit = true;  // ASVGF_NO_VSPLIT=1 at asvgfCreate: the variance pass stays one full-frame dispatch (A/B; identical results)
     uint32_t* haloMiss = nullptr;  // band handles: device flag set by a reprojected tap outside the stored rows (asvgf_args.cuh)
     bool      centreValid = false; // `centre` holds the weight constants of the frame being denoised (written by a-trous iteration 0)
     // cross-stream ordering of the gradient chain (asvgfGradientSamples may be given another stream than asvgfDenoise):
@@ -379,19 +374,8 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.color = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi ); a.depth = d.get( ASVGF_IMAGE_DEPTH_WORLD, fi );
     a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
     a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
-    a.vList = d.vList; a.vCount = d.vCount; a.vCapacity = d.vCapacity;
-    if( d.varianceSplit && d.vList )
-    {
-        cudaError_t e = cudaMemsetAsync( d.vCount, 0, sizeof( uint32_t ), s );
-        if( e != cudaSuccess ) return cudaFail( e, "cudaMemsetAsync(variance queue)" );
-        k_variance_fast< true ><<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
-        AsvgfResult r = launchCheck( d, "k_variance" );
-        if( r != ASVGF_SUCCESS ) return r;
-        k_variance_fallback<<< ( unsigned )std::max( d.smCount, 1 ) * 4u, 256, 0, s >>>( a, u );
-        return launchCheck( d, "k_variance_fallback" );
-    }
     ASVGF_LITERAL_OR( d, ( k_variance<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_variance_fast< false ><<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
+                      ( k_variance_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
     return launchCheck( d, "k_variance" );
 }
 
@@ -736,7 +720,6 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     if( const char* e = std::getenv( "ASVGF_ATROUS_PAIR" ) ) d->atrousPair = std::atoi( e ) != 0;
     if( const char* e = std::getenv( "ASVGF_ATROUS_CENTRE" ) ) d->atrousCentre = std::atoi( e ) != 0;
-    if( const char* e = std::getenv( "ASVGF_NO_VSPLIT" ) ) d->varianceSplit = std::atoi( e ) == 0;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
     if( pInfo->bandRowEnd == 0 )
@@ -859,13 +842,6 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
             return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(centre plane)" );
         }
         setImgStorage( c, memC, pitch, 16 );
-        d->vCapacity = d->W * ( uint32_t )g.rows;
-        if( cudaMalloc( ( void** )&d->vList, ( size_t )d->vCapacity * sizeof( uint32_t ) ) != cudaSuccess || cudaMalloc( ( void** )&d->vCount, sizeof( uint32_t ) ) != cudaSuccess ||
-            cudaMemset( d->vCount, 0, sizeof( uint32_t ) ) != cudaSuccess )
-        {
-            asvgfDestroy( d );
-            return fail( ASVGF_OUT_OF_MEMORY, "cudaMalloc(variance queue)" );
-        }
         if( pInfo->bandRowEnd != 0 )
         {
             if( cudaMalloc( ( void** )&d->haloMiss, sizeof( uint32_t ) ) != cudaSuccess || cudaMemset( d->haloMiss, 0, sizeof( uint32_t ) ) != cudaSuccess )
@@ -888,8 +864,6 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
     if( d->haveLut ) releaseLut( d->device );
     if( d->guide.p ) cudaFree( d->guide.p );
     if( d->centre.p ) cudaFree( d->centre.p );
-    if( d->vList ) cudaFree( d->vList );
-    if( d->vCount ) cudaFree( d->vCount );
     if( d->haloMiss ) cudaFree( d->haloMiss );
     if( d->evTemporalDone ) cudaEventDestroy( d->evTemporalDone );
     if( d->evGradientsDone ) cudaEventDestroy( d->evGradientsDone );

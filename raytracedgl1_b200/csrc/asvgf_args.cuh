@@ -53,11 +53,6 @@ struct VarianceArgs
 {
     Img       color, normal, depth, histLen, moments, out;
     NormalLut lut;
-    // V split: k_variance_fast<true> evaluates the per-pixel branches and queues the pixels that need the 3x3 spatial estimate
-    // (history length <= 4: disocclusions, the first frames after a reset); k_variance_fallback runs it on the compacted queue
-    uint32_t* vList;         // queued pixels: x | y << 16
-    uint32_t* vCount;
-    uint32_t  vCapacity;
 };
 
 // A: a-trous, CmSVGFAtrous_Iter0.comp:92-335 (iteration 0) and CmSVGFAtrous.comp:65-349 (the last one composes PreFinal)

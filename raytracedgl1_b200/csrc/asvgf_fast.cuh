@@ -470,10 +470,8 @@ ASVGF_DEVICE float varianceSpatial( const VarianceArgs& a, const Rows& rows, int
     return variance;
 }
 
-// QUEUE = true (asvgfDenoise): a pixel with too little history is not estimated here -- one such lane would hold its whole warp for the
-// ~500 instructions of the 3x3 estimate -- but queued (warp-aggregated append) for k_variance_fallback, which runs the estimate on
-// full warps.  QUEUE = false: the single dispatch of the reference (asvgfDenoisePass).  Same results bit for bit.
-template< bool QUEUE >
+// One thread per pixel.  (Measured and dropped in round 2: four pixels per thread with 16-byte loads, 0.102 ms instead of 0.082 ms at
+// 4K; queueing the short-history pixels for a second, compacted kernel, 0.096 ms.)
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance_fast( const __grid_constant__ VarianceArgs a, const __grid_constant__ Uniform u )
 {
     const int px = blockIdx.x * kBlockW + threadIdx.x;
@@ -495,52 +493,12 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance_fast( const __g
     {
         const float  historyLength   = __low2float( *reinterpret_cast< const __half2* >( &hl.x ) );
         const float2 temporalMoments = __half22float2( *reinterpret_cast< const __half2* >( &mo ) );
-        if( historyLength > 4.0f ) // :153-161
-        {
-            variance = fmaxf( 0.0f, subr( temporalMoments.y, mulr( temporalMoments.x, temporalMoments.x ) ) ) * frcp( fmaxf( 1.0f, historyLength - 4.0f ) ); // the cancellation keeps the oracle's rounding
-        }
-        else
-        {
-            // (a warp where at least half of the lanes need the estimate -- the first frames after a reset -- runs it in place: queueing
-            //  would only add the round trip through the list)
-            const uint32_t act = QUEUE ? __activemask() : 0u;
-            if( QUEUE && __popc( act ) < 16 )
-            {
-                const uint32_t lane = threadIdx.x & 31u, leader = ( uint32_t )( __ffs( ( int )act ) - 1 );
-                uint32_t       base = 0u;
-                if( lane == leader ) base = atomicAdd( a.vCount, ( uint32_t )__popc( act ) );
-                base = __shfl_sync( act, base, ( int )leader );
-                const uint32_t idx = base + ( uint32_t )__popc( act & ( ( 1u << lane ) - 1u ) );
-                if( idx < a.vCapacity ) a.vList[ idx ] = ( uint32_t )px | ( ( uint32_t )py << 16 );
-                return; // k_variance_fallback writes this texel
-            }
-            else variance = varianceSpatial( a, rows, px, py, pixDepth, historyLength, temporalMoments, color );
-        }
+        if( historyLength > 4.0f ) // :153-161; the cancellation keeps the oracle's rounding
+            variance = fmaxf( 0.0f, subr( temporalMoments.y, mulr( temporalMoments.x, temporalMoments.x ) ) ) * frcp( fmaxf( 1.0f, historyLength - 4.0f ) );
+        else variance = varianceSpatial( a, rows, px, py, pixDepth, historyLength, temporalMoments, color );
     }
     const __half2 o0 = __floats2half2_rn( color.x, color.y ), o1 = __floats2half2_rn( color.z, variance );
     *atW< uint2 >( a.out, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
-}
-
-// V split, second half: the pixels k_variance_fast<true> queued.  Grid-stride over the queue: under one percent of the frame in
-// steady state, every valid pixel in the first four frames after a reset.
-__global__ void __launch_bounds__( 256 ) k_variance_fallback( const __grid_constant__ VarianceArgs a, const __grid_constant__ Uniform u )
-{
-    const Rows     rows = rowsOf( a.depth );
-    const uint32_t n    = min( __ldg( a.vCount ), a.vCapacity );
-    for( uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u )
-    {
-        const uint32_t e  = __ldg( a.vList + i );
-        const int      px = ( int )( e & 0xffffu ), py = ( int )( e >> 16 );
-        const float  pixDepth        = h2f( __ldg( at< uint16_t >( a.depth, px, py ) ) );
-        float3       color           = decodeE5( __ldg( at< uint32_t >( a.color, px, py ) ) );
-        const uint2  hl              = __ldg( at< uint2 >( a.histLen, px, py ) );
-        const uint32_t mo            = __ldg( at< uint32_t >( a.moments, px, py ) );
-        const float  historyLength   = __low2float( *reinterpret_cast< const __half2* >( &hl.x ) );
-        const float2 temporalMoments = __half22float2( *reinterpret_cast< const __half2* >( &mo ) );
-        const float  variance        = varianceSpatial( a, rows, px, py, pixDepth, historyLength, temporalMoments, color );
-        const __half2 o0 = __floats2half2_rn( color.x, color.y ), o1 = __floats2half2_rn( color.z, variance );
-        *atW< uint2 >( a.out, px, py ) = make_uint2( *reinterpret_cast< const uint32_t* >( &o0 ), *reinterpret_cast< const uint32_t* >( &o1 ) );
-    }
 }
 
 } // namespace asvgf

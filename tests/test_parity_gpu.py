@@ -255,46 +255,3 @@ def test_external_images_via_torch():
                 assert np.array_equal(a, b), name
     finally:
         p.close(); ext.close()
-
-
-def test_variance_split_equals_the_single_dispatch():
-    """The variance pass runs as two kernels (k_variance_fast<true> evaluates the per-pixel branches of CmSVGFEstimateVariance.comp and
-    queues the short-history pixels, k_variance_fallback runs the 3x3 spatial estimate on the compacted queue).  A handle created
-    under ASVGF_NO_VSPLIT=1 keeps the single full-frame dispatch.  Both must agree bit for bit, after the variance pass itself and
-    at the end of the frame: frames 0-3 queue every valid pixel (history length <= 4), the later ones only the disocclusions."""
-    import os
-    import synth
-    from raytracedgl1_b200 import denoiser as dn
-    W, H = 642, 362
-    a = dn.Denoiser(W, H, 4, flags=dn.CREATE_EXPORT_DEBUG_MASK)
-    os.environ["ASVGF_NO_VSPLIT"] = "1"
-    try:
-        b = dn.Denoiser(W, H, 4, flags=dn.CREATE_EXPORT_DEBUG_MASK)
-    finally:
-        del os.environ["ASVGF_NO_VSPLIT"]
-    try:
-        for frame in range(7):
-            fi = frame & 1
-            g = synth.generate(W, H, frame)
-            u = synth.uniform(W, H, frame)
-            for d in (a, b):
-                for name, arr in g.items():
-                    d.upload(name, fi, arr)
-                d.gradient_samples(fi, u)
-                for ps in range(1, layout.PASS_VARIANCE + 1):
-                    d.denoise_pass(ps, fi, u)
-                d.synchronize()
-            x, y = a.download("DiffPingColorAndVariance", fi), b.download("DiffPingColorAndVariance", fi)
-            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), "frame %d: DiffPingColorAndVariance after the variance pass" % frame
-            assert a.launch_count - b.launch_count == frame + 1, "the split handle launches one more kernel per frame"
-            for d in (a, b):
-                for ps in range(layout.PASS_ATROUS_0, layout.PASS_ATROUS_0 + 4):
-                    d.denoise_pass(ps, fi, u)
-                d.synchronize()
-            for name in ["PreFinal", "HistogramInput", "DiffColorHistory", "AtrousFilteredVariance", "DiffAccumColor", "SpecPongColor", "IndirPong",
-                         "DiffPongColorAndVariance", "DiffPingColorAndVariance", "AccumHistoryLength", "DiffAccumMoments"]:
-                x, y = a.download(name, fi), b.download(name, fi)
-                assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), "frame %d: %s differs between the split and the single dispatch" % (frame, name)
-    finally:
-        a.close()
-        b.close()
