@@ -44,7 +44,8 @@ def measured_traffic(kernel, W, H, N):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
     capture (profiles/); None when no capture exists for this workload."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic_4k.json")) as f:
+        name = "r02_dram_traffic_4k.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_dram_traffic_4k.json")) else "r01_dram_traffic_4k.json"
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             t = json.load(f)
         if (W, H, N) == (3840, 2160, 4):
             return t["kernels"][kernel]["bytes_per_launch"]
@@ -396,8 +397,12 @@ def run_ours(args, rank, world, local_rank):
     launches0 = d.launch_count
     sampler.start() if sampler.ok else None
     e_begin.record(stream)
+    frame_evs = []                            # an event behind every frame: per-frame times (p50 / p95), not part of `value`
     for i in range(args.steps):
         step_production(args.warmup + i)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        frame_evs.append(ev)
     stream.wait_stream(gstream)               # (the last frame's gradient chain is already behind its temporal pass)
     e_end.record(stream)
     torch.cuda.synchronize()
@@ -405,6 +410,9 @@ def run_ours(args, rank, world, local_rank):
     launches = d.launch_count - launches0
     barrier()
     total_ms = e_begin.elapsed_time(e_end)
+    per_frame = sorted(a.elapsed_time(b) for a, b in zip([e_begin] + frame_evs[:-1], frame_evs))
+    frame_stats = {"p50_ms": per_frame[len(per_frame) // 2], "p95_ms": per_frame[min(len(per_frame) - 1, int(0.95 * len(per_frame)))],
+                   "min_ms": per_frame[0], "max_ms": per_frame[-1]}
 
     # ---- per-pass breakdown (same launches, an event after each): explains the number above, not part of it ----
     pp_steps = max(3, min(args.steps, 50))
@@ -517,6 +525,7 @@ def run_ours(args, rank, world, local_rank):
             "config": run_config(args.workload, n_frames),
             "sequence": "%d consecutive synthetic frames (camera motion, moving objects, disocclusions), cycled" % n_frames,
             "algorithmic_bytes_per_px": chain_bpp,
+            "frame_ms": {k: round(v, 4) for k, v in frame_stats.items()},
             "clocks": clocks,
             "e2e": {"value": world * W * H * e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
