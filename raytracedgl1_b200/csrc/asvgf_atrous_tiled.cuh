@@ -205,11 +205,12 @@ ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows
             const int  r = e / G::TW, c = e - r * G::TW;
             const int  gx = xBase - G::HALO + c, gy = yBase + ( r - 1 ) * STEP;
             const bool ok = e < G::NPX && rows.in( gx, gy );
-            const uint32_t o = ( uint32_t )( gy * ( int )a.guide.pitchT + gx ); // the four images share the pitch in texels when uniformPitch
-            ga[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const float4* >( a.guide.p0 ) + o : at< float4 >( a.guide, gx, gy ) ) : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-            dd[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const uint2* >( a.srcDiff.p0 ) + o : at< uint2 >( a.srcDiff, gx, gy ) ) : make_uint2( 0u, 0u );
-            ss[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const uint32_t* >( a.srcSpec.p0 ) + o : at< uint32_t >( a.srcSpec, gx, gy ) ) : 0u;
-            ii[ it ] = ok ? __ldg( a.uniformPitch ? reinterpret_cast< const uint32_t* >( a.srcIndir.p0 ) + o : at< uint32_t >( a.srcIndir, gx, gy ) ) : 0u;
+            // one multiply-add per image (a run-time "the four images share their pitch" switch was tried: the compiler evaluated
+            // both address forms and selected per load, ~30 instructions per staged texel)
+            ga[ it ] = ok ? __ldg( at< float4 >( a.guide, gx, gy ) ) : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+            dd[ it ] = ok ? __ldg( at< uint2 >( a.srcDiff, gx, gy ) ) : make_uint2( 0u, 0u );
+            ss[ it ] = ok ? __ldg( at< uint32_t >( a.srcSpec, gx, gy ) ) : 0u;
+            ii[ it ] = ok ? __ldg( at< uint32_t >( a.srcIndir, gx, gy ) ) : 0u;
         }
 #pragma unroll
         for( int it = 0; it < NIT; it++ )
