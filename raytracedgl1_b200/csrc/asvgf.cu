@@ -338,15 +338,16 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     const dim3 grid = gridFor( ( int )d.W, u.yEnd - u.yBegin );
     a.haloMiss = d.haloMiss;
     auto production = [ & ]() {
+        const dim3 tGrid( grid.x, ( unsigned )( ( u.yEnd - u.yBegin + kTBlockH - 1 ) / kTBlockH ), 1 ), tBlock( kBlockW, kTBlockH, 1 );
         if( d.haloMiss )
         {
-            if( uniformPitch ) k_temporal_fast< true, true ><<< grid, kBlock, 0, s >>>( a, u );
-            else k_temporal_fast< false, true ><<< grid, kBlock, 0, s >>>( a, u );
+            if( uniformPitch ) k_temporal_fast< true, true ><<< tGrid, tBlock, 0, s >>>( a, u );
+            else k_temporal_fast< false, true ><<< tGrid, tBlock, 0, s >>>( a, u );
         }
         else
         {
-            if( uniformPitch ) k_temporal_fast< true, false ><<< grid, kBlock, 0, s >>>( a, u );
-            else k_temporal_fast< false, false ><<< grid, kBlock, 0, s >>>( a, u );
+            if( uniformPitch ) k_temporal_fast< true, false ><<< tGrid, tBlock, 0, s >>>( a, u );
+            else k_temporal_fast< false, false ><<< tGrid, tBlock, 0, s >>>( a, u );
         }
     };
     ASVGF_LITERAL_OR( d, ( k_temporal<<< grid, kBlock, 0, s >>>( a, u ) ), production() );
