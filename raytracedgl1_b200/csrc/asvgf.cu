@@ -450,7 +450,6 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     const int    tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
     const size_t smem   = atrousSmemBytes( step );
     const dim3   grid( ( unsigned )tilesX, ( unsigned )( bands * step ), 1 );
-    a.uniformPitch = a.guide.pitchT == a.srcDiff.pitchT && a.guide.pitchT == a.srcSpec.pitchT && a.guide.pitchT == a.srcIndir.pitchT;
     const bool pair = d.atrousPair;
     // the opt-in to more than 48 KB of dynamic shared memory is per function and per device: once, not per launch
     auto launch = [ & ]( auto kernel, bool& optedIn ) -> cudaError_t {

@@ -66,7 +66,6 @@ struct AtrousArgs
     int32_t   centreValid; // iterations >= 1: read `centre` instead of re-deriving the constants from three more images
     NormalLut lut;
     int32_t   iteration;
-    int32_t   uniformPitch; // guide and the three source images hold the same number of texels per row
 };
 
 } // namespace asvgf

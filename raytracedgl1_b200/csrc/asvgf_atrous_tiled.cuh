@@ -1,13 +1,18 @@
-// asvgf_atrous_tiled.cuh -- the a-trous kernel (CmSVGFAtrous.comp iterations >= 1, and CmSVGFAtrous_Iter0.comp when the fused
-// F+V+A0 kernel is not used), sm_100a, plus the per-frame guide plane it reads.
+// asvgf_atrous_tiled.cuh -- the a-trous kernel (CmSVGFAtrous_Iter0.comp for iteration 0, CmSVGFAtrous.comp for iterations >= 1 and
+// the composition), sm_100a, plus the per-frame guide plane it reads.
 //
 // Arithmetic: CmSVGFAtrous_Iter0.comp:158-335 / CmSVGFAtrous.comp:65-349.  Structure (round 2; ncu of the round-1 kernel:
 // 578 instructions per pixel, issue 73 %, shared-memory pipe 60 %, ALU pipe 41 % -- instruction- and LDS-bound, DRAM 30 %):
 //
 //  * GUIDE PLANE.  Normal, depth and roughness do not change between the iterations of a frame, yet every iteration used to
-//    re-decode them per staged texel (two dependent sin/cos-table gathers per normal).  k_guide decodes them ONCE per frame
-//    into a float4 plane (n.xyz, depth); roughness rides in the low byte of the depth word (an fp16 depth leaves the low 13
-//    mantissa bits of its fp32 form zero) and is split off while staging.  A tile's geometry costs one 16-byte load per texel.
+//    re-decode them per staged texel (two dependent sin/cos-table gathers per normal).  They are decoded ONCE per frame -- by the
+//    temporal pass, which has them in registers anyway (k_guide only when that pass did not cover the rows) -- into a float4
+//    plane (n.xyz, depth); roughness rides in the low byte of the depth word (an fp16 depth leaves the low 13 mantissa bits of
+//    its fp32 form zero) and is split off while staging.  A tile's geometry costs one 16-byte load per texel.
+//  * CENTRE PLANE.  The four weight constants of a pixel that do not depend on the iteration (luminance scale, the two depth
+//    scales, the specular power) are derived by iteration 0 from three more images and published; iterations >= 1 read them.
+//  * SKY TILES.  A tile without a single valid surface passes its centre texels through (the shader's early return): the CTA
+//    votes on the centre depths first and skips staging and taps.
 //  * DILATED TILE.  For stride s a pixel only touches rows y, y+-s: a CTA owns 64 columns of 8 rows spaced s apart (the s
 //    residues go to s different CTAs); halo = one dilated row above/below, max(s,4) columns left/right.  Read amplification
 //    1.4-1.56 at every stride, every global access a full-line row segment.
@@ -18,7 +23,7 @@
 //    render-area test are folded into the exponent (lk = log2 k, or -inf outside):
 //      wBase = ex2(128 L + lk - wz^2 log2e),  wDiff = ex2(128 L + lk - (wz^2 + wl) log2e),  wSpec = r * ex2(. + P L)
 //    1 lg2 + 3 ex2 and ~30 FMA-pipe instructions per tap.  Tiles whose taps all stay inside the render area (all but the
-//    frame / checkerboard-separator borders) take a loop with immediate lk; the choice is per CTA, not per pixel.
+//    frame / checkerboard-separator borders) take a copy of the tap loop compiled with immediate lk; the choice is per CTA.
 //  * 64 registers, 41-51 KB of shared memory: four CTAs = 32 warps per SM.
 #pragma once
 
