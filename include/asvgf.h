@@ -135,6 +135,17 @@ ASVGF_API AsvgfResult asvgfDownloadImage( AsvgfDenoiser denoiser, AsvgfStream st
                                           uint32_t frameIndex, void* pHost, size_t hostPitchBytes );
 /* Zero every owned image (= fresh images after a resolution change, Framebuffers.cpp:216-230). */
 ASVGF_API AsvgfResult asvgfResetHistory( AsvgfDenoiser denoiser, AsvgfStream stream );
+/* Checkpoint / resume of the temporal state.  The reference keeps it in GPU images only and loses it on a resolution change
+   (Framebuffers.cpp:216-230); here it can be taken out and put back: both members of every cur/prev pair (accumulated colours,
+   moments, history lengths, the previous frame's depth / normals / roughness / surface positions / gradient inputs, scattering),
+   the a-trous colour history, the gradient history, the other images the passes write (some are only partly overwritten per frame)
+   and the exposure state (AsvgfTonemapping) -- everything but the producer's per-frame inputs -- as tightly packed rows behind a
+   small header.  Copies are enqueued on `stream` (pinned host memory makes them asynchronous); a frame computed after asvgfLoadState is
+   bit-identical to the frame the saving handle would have computed.  Loading into a handle of another size, band or image set is
+   ASVGF_WRONG_ARGUMENT. */
+ASVGF_API AsvgfResult asvgfGetStateSize( AsvgfDenoiser denoiser, size_t* pBytes );
+ASVGF_API AsvgfResult asvgfSaveState( AsvgfDenoiser denoiser, AsvgfStream stream, void* pHost, size_t bytes );
+ASVGF_API AsvgfResult asvgfLoadState( AsvgfDenoiser denoiser, AsvgfStream stream, const void* pHost, size_t bytes );
 
 /* = PathTracer::CalculateGradientsSamples, image-space part (RtGradients.rgen:44-105,139-181); the ray-traced
    re-shade is read from ASVGF_IMAGE_FWD_LUM.  Enqueues only.  `stream` may differ from the stream asvgfDenoise is given:

@@ -942,6 +942,84 @@ AsvgfResult asvgfResetHistory( AsvgfDenoiser d, AsvgfStream stream )
     return ASVGF_SUCCESS;
 }
 
+// ---- checkpoint / resume of the temporal state (the reference keeps it in GPU images only) ----
+namespace
+{
+// Everything but the producer's per-frame inputs: both members of every cur/prev pair (history, and the previous frame's G-buffer),
+// the a-trous colour history, the gradient history -- what frame t+1 reads of frame t -- and also the images the passes only
+// partly overwrite (GradientPrevPix keeps the slot of strata without a sample, AtrousFilteredVariance the value of pixels that
+// turned into sky), so that a resumed handle's whole table equals the one that kept running; plus the exposure state.
+bool isStateImage( uint32_t i )
+{
+    switch( i )
+    {
+        case ASVGF_IMAGE_ALBEDO: case ASVGF_IMAGE_IS_SKY: case ASVGF_IMAGE_DEPTH_GRAD: case ASVGF_IMAGE_MOTION: case ASVGF_IMAGE_UNFILTERED_DIRECT:
+        case ASVGF_IMAGE_UNFILTERED_SPECULAR: case ASVGF_IMAGE_UNFILTERED_INDIR: case ASVGF_IMAGE_VIEW_DIRECTION: case ASVGF_IMAGE_THROUGHPUT:
+        case ASVGF_IMAGE_FWD_LUM: case ASVGF_IMAGE_SCATTER_CURRENT: case ASVGF_IMAGE_ACID_FOG_RT: case ASVGF_IMAGE_SCREEN_EMIS_RT: return false;
+        default: return true;
+    }
+}
+struct StateHeader { uint32_t magic, version, width, height, row0, rows, grow0, grows, imageCount, tonemappingBytes; };
+constexpr uint32_t kStateMagic = 0x53565341u; // "ASVS"
+size_t stateBytes( const AsvgfDenoiser_T& d, uint32_t* pCount )
+{
+    size_t   n = sizeof( StateHeader ) + sizeof( AsvgfTonemapping );
+    uint32_t count = 0;
+    ImageDesc desc;
+    for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
+        if( isStateImage( i ) && describe( i, &desc ) && d.img[ i ].p ) { n += 2 * sizeof( uint32_t ) + ( size_t )d.img[ i ].w * desc.bpp * d.img[ i ].rows; count++; }
+    if( pCount ) *pCount = count;
+    return n;
+}
+}
+
+AsvgfResult asvgfGetStateSize( AsvgfDenoiser d, size_t* pBytes )
+{
+    if( !d || !pBytes ) return fail( ASVGF_WRONG_ARGUMENT, "null argument" );
+    *pBytes = stateBytes( *d, nullptr );
+    return ASVGF_SUCCESS;
+}
+
+static AsvgfResult copyState( AsvgfDenoiser d, AsvgfStream stream, uint8_t* host, size_t bytes, bool save )
+{
+    if( !d || !host ) return fail( ASVGF_WRONG_ARGUMENT, "null argument" );
+    uint32_t     count = 0;
+    const size_t need  = stateBytes( *d, &count );
+    if( bytes < need ) return fail( ASVGF_WRONG_ARGUMENT, "state buffer too small (" + std::to_string( need ) + " bytes needed)" );
+    DeviceGuard        guard( d->device );
+    const cudaStream_t s = ( cudaStream_t )stream;
+    StateHeader        h = { kStateMagic, 1u, d->W, d->H, ( uint32_t )d->row0, ( uint32_t )d->rows, ( uint32_t )d->grow0, ( uint32_t )d->grows, count, ( uint32_t )sizeof( AsvgfTonemapping ) };
+    if( save ) std::memcpy( host, &h, sizeof( h ) );
+    else
+    {
+        StateHeader g;
+        std::memcpy( &g, host, sizeof( g ) );
+        if( std::memcmp( &g, &h, sizeof( h ) ) != 0 ) return fail( ASVGF_WRONG_ARGUMENT, "the state was saved by a handle of another size / band / image set" );
+    }
+    size_t off = sizeof( StateHeader );
+    if( save ) CUDA_TRY( cudaMemcpyAsync( host + off, d->tm, sizeof( AsvgfTonemapping ), cudaMemcpyDeviceToHost, s ) );
+    else CUDA_TRY( cudaMemcpyAsync( d->tm, host + off, sizeof( AsvgfTonemapping ), cudaMemcpyHostToDevice, s ) );
+    off += sizeof( AsvgfTonemapping );
+    ImageDesc desc;
+    for( uint32_t i = 0; i < ASVGF_IMAGE_COUNT; i++ )
+    {
+        if( !isStateImage( i ) || !describe( i, &desc ) || !d->img[ i ].p ) continue;
+        const Img&     im       = d->img[ i ];
+        const size_t   rowBytes = ( size_t )im.w * desc.bpp;
+        const uint32_t tag[ 2 ] = { i, ( uint32_t )( rowBytes * im.rows ) };
+        if( save ) std::memcpy( host + off, tag, sizeof( tag ) );
+        else if( std::memcmp( host + off, tag, sizeof( tag ) ) != 0 ) return fail( ASVGF_WRONG_ARGUMENT, "corrupt state buffer" );
+        off += sizeof( tag );
+        if( save ) CUDA_TRY( cudaMemcpy2DAsync( host + off, rowBytes, im.p, im.pitch, rowBytes, ( size_t )im.rows, cudaMemcpyDeviceToHost, s ) );
+        else CUDA_TRY( cudaMemcpy2DAsync( im.p, im.pitch, host + off, rowBytes, rowBytes, ( size_t )im.rows, cudaMemcpyHostToDevice, s ) );
+        off += rowBytes * im.rows;
+    }
+    if( !save ) d->guideValid = d->centreValid = false;
+    return ASVGF_SUCCESS;
+}
+AsvgfResult asvgfSaveState( AsvgfDenoiser d, AsvgfStream stream, void* pHost, size_t bytes ) { return copyState( d, stream, ( uint8_t* )pHost, bytes, true ); }
+AsvgfResult asvgfLoadState( AsvgfDenoiser d, AsvgfStream stream, const void* pHost, size_t bytes ) { return copyState( d, stream, ( uint8_t* )const_cast< void* >( pHost ), bytes, false ); }
+
 AsvgfResult asvgfGradientSamples( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
 {
     AsvgfResult r = checkCall( d, frameIndex, pUniform );

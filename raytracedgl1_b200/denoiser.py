@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "asvgfSynchronize", "asvgfGetLaunchCount", "asvgfPassName", "asvgfPassBytesPerPixel", "asvgfResultString",
     "asvgfLastErrorMessage", "asvgfPassKernelName", "asvgfBandApronRows", "asvgfResolveCheckerboard", "asvgfCalculateExposure", "asvgfLuminanceHistogram",
     "asvgfLuminanceAverage", "asvgfGetTonemappingBuffer", "asvgfUploadTonemapping", "asvgfDownloadTonemapping",
-    "asvgfScatterAccumulate", "asvgfPrepareFinal",
+    "asvgfScatterAccumulate", "asvgfPrepareFinal", "asvgfGetStateSize", "asvgfSaveState", "asvgfLoadState",
     "asvgfBandSetCreate", "asvgfBandSetDestroy", "asvgfBandSetGetBandCount", "asvgfBandSetGetBand", "asvgfBandSetFrame",
     "asvgfBandSetSynchronize", "asvgfBandSetBeginTiming", "asvgfBandSetEndTiming",
     "asvgfImportExternalMemoryFd", "asvgfExternalMemoryGetBuffer", "asvgfDestroyExternalMemory", "asvgfImportExternalSemaphoreFd",
@@ -85,6 +85,9 @@ def lib():
             getattr(L, name).argtypes = [vp, vp, u32, puni]
         L.asvgfScatterAccumulate.argtypes = [vp, vp, u32, puni, ctypes.c_float]
         L.asvgfPrepareFinal.argtypes = [vp, vp, u32, puni, ctypes.c_void_p]
+        L.asvgfGetStateSize.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+        L.asvgfSaveState.argtypes = [vp, vp, ctypes.c_void_p, ctypes.c_size_t]
+        L.asvgfLoadState.argtypes = [vp, vp, ctypes.c_void_p, ctypes.c_size_t]
         L.asvgfGetTonemappingBuffer.argtypes = [vp, ctypes.POINTER(vp)]
         L.asvgfUploadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
         L.asvgfDownloadTonemapping.argtypes = [vp, vp, ctypes.POINTER(layout.Tonemapping)]
@@ -206,6 +209,20 @@ class Denoiser:
         if not isinstance(out, int):
             self.synchronize(stream)
         return out
+
+    def save_state(self, stream=0):
+        """The temporal state (history images + exposure) as a numpy byte array (asvgfSaveState)."""
+        n = ctypes.c_size_t()
+        _check(lib().asvgfGetStateSize(self._h, ctypes.byref(n)), "asvgfGetStateSize")
+        buf = np.empty(n.value, dtype=np.uint8)
+        _check(lib().asvgfSaveState(self._h, stream, buf.ctypes.data, buf.nbytes), "asvgfSaveState")
+        self.synchronize(stream)
+        return buf
+
+    def load_state(self, buf, stream=0):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        _check(lib().asvgfLoadState(self._h, stream, buf.ctypes.data, buf.nbytes), "asvgfLoadState")
+        self.synchronize(stream)
 
     def reset_history(self, stream=0):
         _check(lib().asvgfResetHistory(self._h, stream), "asvgfResetHistory")

@@ -255,3 +255,43 @@ def test_external_images_via_torch():
                 assert np.array_equal(a, b), name
     finally:
         p.close(); ext.close()
+
+
+def test_state_checkpoint_resumes_bit_identically():
+    """asvgfSaveState / asvgfLoadState (checkpoint / resume): a handle that loads the state saved after frame 3
+    computes frames 4 and 5 bit for bit like the handle that kept running -- history images, previous-frame G-buffer and the
+    exposure state all travel; a buffer from a handle of another size is refused."""
+    import synth
+    from raytracedgl1_b200 import denoiser as dn
+    W, H = 322, 182
+    a = dn.Denoiser(W, H, 4, flags=dn.CREATE_EXPORT_DEBUG_MASK)
+    b = dn.Denoiser(W, H, 4, flags=dn.CREATE_EXPORT_DEBUG_MASK)
+    other = dn.Denoiser(160, 90, 4)
+    try:
+        def frame(d, f):
+            fi = f & 1
+            u = synth.uniform(W, H, f)
+            for name, arr in synth.generate(W, H, f).items():
+                d.upload(name, fi, arr)
+            d.gradient_samples(fi, u)
+            d.denoise(fi, u)
+            d.calculate_exposure(fi, u)
+            d.synchronize()
+            return fi
+        for f in range(4):
+            frame(a, f)
+        state = a.save_state()
+        assert state.nbytes > W * H * 60
+        with pytest.raises(dn.AsvgfError):
+            other.load_state(state)
+        with pytest.raises(dn.AsvgfError):
+            b.load_state(state[:1000])
+        b.load_state(state)
+        for f in (4, 5):
+            fi = frame(a, f)
+            frame(b, f)
+            for name in layout.IMAGES:      # the whole table, scratch images and partly overwritten ones included
+                assert np.array_equal(a.download(name, fi).view(np.uint8), b.download(name, fi).view(np.uint8)), (f, name)
+            assert a.tonemapping().avgLuminance == b.tonemapping().avgLuminance
+    finally:
+        a.close(); b.close(); other.close()
