@@ -1,8 +1,8 @@
 // asvgf_fast.cuh -- production kernels of the gradient, temporal, anti-firefly and variance passes (sm_100a).
 //
-// Same results as the literal kernels of asvgf_kernels.cuh (which restate the shaders expression by expression), but
-// written for the B200 SM, where the literal forms are instruction-issue bound, not HBM bound (ncu, profiles/r01_v2_*:
-// k_temporal 3040 instructions per pixel with DRAM at 12 %, k_antifirefly 1860 per pixel with DRAM at 3 %):
+// Written for the B200 SM, where a one-thread-per-pixel translation of the shaders (experiments/asvgf_literal_kernels.cuh, not
+// part of the library) is instruction-issue bound, not HBM bound (ncu, profiles/r01_v2_*: k_temporal 3040 instructions per pixel
+// with DRAM at 12 %, k_antifirefly 1860 per pixel with DRAM at 3 %):
 //
 //   * everything that decides an INTEGER/BOOLEAN output (reprojected pixel positions, bilinear tap weights, the depth /
 //     normal / render-area disocclusion tests, the chosen stratum slot) keeps the explicitly rounded operation order
