@@ -206,6 +206,9 @@ struct AsvgfDenoiser_T
     AsvgfTonemapping* tm       = nullptr;
     float*            log2Half = nullptr; // correctly rounded log2 of every fp16 bit pattern
     uint8_t*          binTable = nullptr; // histogram bin of every fp16 bit pattern for the current uniform
+    float*            transmittance = nullptr; // exp(-depth * density) of every fp16 depth for `transmittanceDensity` (asvgfScatterAccumulate)
+    float             transmittanceDensity = -1.0f;
+    float*            finalScalars = nullptr;  // asvgfPrepareFinal: exposure, bloom luminance, white scale of the call
 
     const Img& get( uint32_t index, uint32_t frameIndex ) const
     {
@@ -512,7 +515,18 @@ AsvgfResult runPrepareFinal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, co
     a.acidFog = d.get( ASVGF_IMAGE_ACID_FOG, fi ); a.bloomInput = d.get( ASVGF_IMAGE_BLOOM_INPUT, fi );
     a.motion = d.get( ASVGF_IMAGE_MOTION, fi ); a.disPing = d.get( ASVGF_IMAGE_DIS_PING_GRADIENT, fi ); a.normal = d.get( ASVGF_IMAGE_NORMAL, fi );
     a.unfiltered[ 0 ] = d.get( ASVGF_IMAGE_UNFILTERED_DIRECT, fi ); a.unfiltered[ 1 ] = d.get( ASVGF_IMAGE_UNFILTERED_SPECULAR, fi ); a.unfiltered[ 2 ] = d.get( ASVGF_IMAGE_UNFILTERED_INDIR, fi );
-    a.lut = d.lut; a.tm = d.tm;
+    a.lut = d.lut;
+    if( !d.finalScalars )
+    {
+        cudaError_t e = cudaMalloc( ( void** )&d.finalScalars, 4 * sizeof( float ) );
+        if( e != cudaSuccess ) return cudaFail( e, "cudaMalloc(final-prepare scalars)" );
+    }
+    a.scalars = d.finalScalars;
+    k_prepare_final_scalars<<< 1, 1, 0, s >>>( d.tm, g.bloomEmissionMultiplier, g.luminanceWhitePoint, d.finalScalars );
+    {
+        AsvgfResult r = launchCheck( d, "k_prepare_final_scalars" );
+        if( r != ASVGF_SUCCESS ) return r;
+    }
     // the members of the 24 x uvec4 control block LpmFilter hands to LpmMap in this configuration (LPM/ffx_lpm.h:913-938)
     auto f = [ & ]( int vec, int comp ) { float v; std::memcpy( &v, &lpm[ vec * 4 + comp ], 4 ); return v; };
     for( int i = 0; i < 3; i++ ) { a.saturation[ i ] = f( 0, i ); a.crosstalk[ i ] = f( 2, 1 + i ); a.rcpLumaT[ i ] = f( 3, i ); }
@@ -538,6 +552,24 @@ AsvgfResult runScatterAccumulate( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t f
     a.scatPrev = d.get( ASVGF_IMAGE_SCATTERING_PREV, fi ); a.histPrev = d.get( ASVGF_IMAGE_SCATTERING_HISTORY_PREV, fi );
     a.scat = d.get( ASVGF_IMAGE_SCATTERING, fi ); a.hist = d.get( ASVGF_IMAGE_SCATTERING_HISTORY, fi ); a.current = d.get( ASVGF_IMAGE_SCATTER_CURRENT, fi );
     a.lut = d.lut; a.maxHistoryLength = maxHistoryLength; a.volumeScattering = g.volumeScattering; a.volumeEnableType = g.volumeEnableType;
+    a.transmittance = d.transmittance;
+    if( g.volumeEnableType == ASVGF_VOLUME_ENABLE_SIMPLE )
+    {
+        const float density = g.volumeScattering * 0.00005f; // = mulr( volumeScattering, 0.00005f ) of the kernel (CmScatterAccum.comp:81)
+        if( !d.transmittance )
+        {
+            cudaError_t e = cudaMalloc( ( void** )&d.transmittance, 65536 * sizeof( float ) );
+            if( e != cudaSuccess ) return cudaFail( e, "cudaMalloc(transmittance table)" );
+            a.transmittance = d.transmittance;
+        }
+        if( std::memcmp( &density, &d.transmittanceDensity, sizeof( float ) ) != 0 ) // rebuilt only when the density changes
+        {
+            k_scatter_transmittance_table<<< 256, 256, 0, s >>>( d.transmittance, density );
+            AsvgfResult r = launchCheck( d, "k_scatter_transmittance_table" );
+            if( r != ASVGF_SUCCESS ) return r;
+            d.transmittanceDensity = density;
+        }
+    }
     for( int i = 0; i < 3; i++ ) a.volumeAmbient[ i ] = g.volumeAmbient[ i ];
     k_scatter_accum<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
     return launchCheck( d, "k_scatter_accum" );
@@ -869,6 +901,8 @@ AsvgfResult asvgfDestroy( AsvgfDenoiser d )
     if( d->evGradientsDone ) cudaEventDestroy( d->evGradientsDone );
     if( d->log2Half ) cudaFree( d->log2Half );
     if( d->binTable ) cudaFree( d->binTable );
+    if( d->transmittance ) cudaFree( d->transmittance );
+    if( d->finalScalars ) cudaFree( d->finalScalars );
     if( d->tm ) cudaFree( d->tm );
     delete d;
     return ASVGF_SUCCESS;

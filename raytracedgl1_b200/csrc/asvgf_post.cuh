@@ -224,7 +224,17 @@ struct ScatterArgs
     NormalLut lut;
     float     maxHistoryLength, volumeScattering, volumeAmbient[ 3 ];
     uint32_t  volumeEnableType;
+    // SIMPLE volume mode: exp(-depth * density) of every fp16 depth pattern for the current density (k_scatter_transmittance_table):
+    // the depth is an fp16 texel, so the correctly rounded exp -- evaluated in double, the pin of this path -- is a function of 16 bits;
+    // computing it per pixel was 60 % of the kernel's instructions
+    float*    transmittance;
 };
+
+__global__ void __launch_bounds__( 256 ) k_scatter_transmittance_table( float* table, float density )
+{
+    const uint32_t bits = blockIdx.x * 256u + threadIdx.x; // 65536 entries
+    table[ bits ] = ( float )exp( ( double )mulr( -h2f( ( uint16_t )bits ), density ) ); // pin: correctly rounded fp32
+}
 
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __grid_constant__ ScatterArgs a, const __grid_constant__ Uniform u )
 {
@@ -310,10 +320,9 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __g
     }
     else if( a.volumeEnableType == ASVGF_VOLUME_ENABLE_SIMPLE )
     {
-        const float density = mulr( a.volumeScattering, 0.00005f );
         if( !( depth > ASVGF_MAX_RAY_LENGTH ) ) // the regular pixel maps back to this checkerboard pixel: virtualdepth = depth
         {
-            const float f = ( float )exp( ( double )mulr( -depth, density ) ); // pin: correctly rounded fp32
+            const float f = __ldg( a.transmittance + dv ); // = (float)exp((double)(-depth * density)), correctly rounded
             const float g = subr( 1.0f, f );
             cur = make_float4( mulr( a.volumeAmbient[ 0 ], g ), mulr( a.volumeAmbient[ 1 ], g ), mulr( a.volumeAmbient[ 2 ], g ), f );
         }
@@ -329,16 +338,14 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_scatter_accum( const __g
 // One thread per regular pixel: Final * transmittance + in-scattering, exposure from the eye-adapted average luminance
 // (Exposure.h:36-58), AMD LPM tonemap of the ray-traced columns (LpmMap, LPM/ffx_lpm.h:747-819, in the 709 -> 709 configuration
 // the shader instantiates: every optional stage off) or Uncharted 2 on the classic-shading columns, + AcidFog, the debug views,
-// and the bloom input.  Arithmetic in the shader's order (explicitly rounded); pow() is powf.  The three scalars every pixel
-// shares -- luminous exposure, bloom luminance, the white-point scale -- need log2 / exp2 at the pinned precision (correctly
-// rounded fp32): one thread per CTA evaluates them in double.
+// and the bloom input.  Arithmetic in the shader's order (explicitly rounded); pow() is ex2(y lg2 x).
 // ------------------------------------------------------------------------------------------------------------
 struct PrepareFinalArgs
 {
     Img       final, screenEmission, scattering, acidFog, bloomInput;
     Img       motion, disPing, normal, unfiltered[ 3 ]; // the debug views (CmPrepareFinal.comp:175-226)
     NormalLut lut;
-    const AsvgfTonemapping* tm;
+    const float* scalars; // luminous exposure, bloom luminance, Uncharted 2 white scale (k_prepare_final_scalars)
     float     saturation[ 3 ], contrast, toneScaleBias[ 2 ], lumaT[ 3 ], crosstalk[ 3 ], rcpLumaT[ 3 ]; // LPM control block, ffx_lpm.h:913-938
     float     luminanceWhitePoint, emissionMaxScreenColor, bloomThreshold, bloomEmissionMultiplier;
     float     classicEdge; // lightmapScreenCoverage * renderWidth (ShaderCommonGLSLFunc.h:492-495)
@@ -359,9 +366,11 @@ ASVGF_DEVICE float3 lpmMap709( const PrepareFinalArgs& a, float3 c )
     auto  sat = [ & ]( float x ) { return fminf( fmaxf( x, sat01lo ), 1.0f ); };
     float colorR = c.x, colorG = c.y, colorB = c.z;
     const float rcpMax = divr( 1.0f, fmaxf( colorR, fmaxf( colorG, colorB ) ) );
-    float ratioR = powf( mulr( colorR, rcpMax ), a.saturation[ 0 ] ), ratioG = powf( mulr( colorG, rcpMax ), a.saturation[ 1 ] ), ratioB = powf( mulr( colorB, rcpMax ), a.saturation[ 2 ] );
+    // pow(x, y) = ex2(y * lg2 x) on the MUFU pipe (relative error ~2^-21: invisible behind the 6/6/5-bit mantissas of the output);
+    // the precise powf was four fifths of this kernel's instructions
+    float ratioR = fpow( mulr( colorR, rcpMax ), a.saturation[ 0 ] ), ratioG = fpow( mulr( colorG, rcpMax ), a.saturation[ 1 ] ), ratioB = fpow( mulr( colorB, rcpMax ), a.saturation[ 2 ] );
     float luma = addr( mulr( colorG, a.lumaT[ 1 ] ), addr( mulr( colorR, a.lumaT[ 0 ] ), mulr( colorB, a.lumaT[ 2 ] ) ) );
-    luma       = powf( luma, a.contrast );
+    luma       = fpow( luma, a.contrast );
     luma       = mulr( luma, divr( 1.0f, addr( mulr( luma, a.toneScaleBias[ 0 ] ), a.toneScaleBias[ 1 ] ) ) );
     const float lumaRatio  = addr( addr( mulr( ratioR, a.lumaT[ 0 ] ), mulr( ratioG, a.lumaT[ 1 ] ) ), mulr( ratioB, a.lumaT[ 2 ] ) );
     const float ratioScale = sat( mulr( luma, divr( 1.0f, lumaRatio ) ) );
@@ -377,23 +386,24 @@ ASVGF_DEVICE float3 lpmMap709( const PrepareFinalArgs& a, float3 c )
     return make_float3( sat( addr( mulr( lumaAdd, a.rcpLumaT[ 0 ] ), colorR ) ), sat( addr( mulr( lumaAdd, a.rcpLumaT[ 1 ] ), colorG ) ), sat( addr( mulr( lumaAdd, a.rcpLumaT[ 2 ] ), colorB ) ) );
 }
 
+// the three scalars every pixel of the final prepare shares, at the pinned precision (log2 / exp2 correctly rounded: evaluated in
+// double): ONE thread, once per call.  (Evaluating them in thread 0 of every CTA behind a barrier cost a third of the kernel.)
+__global__ void k_prepare_final_scalars( const AsvgfTonemapping* tm, float bloomEmissionMultiplier, float luminanceWhitePoint, float* out )
+{
+    // Exposure.h:36-58: EV100 = log2(avgLuminance * S / K), S = 100, K = 12.5
+    const float ev100 = ( float )log2( ( double )divr( mulr( fmaxf( 0.0f, tm->avgLuminance ), 100.0f ), 12.5f ) );
+    const float maxLuminance = mulr( 1.2f, ( float )exp2( ( double )ev100 ) );
+    out[ 0 ] = maxLuminance > 0.0f ? divr( 1.0f, maxLuminance ) : 0.0f;                            // ev100ToLuminousExposure
+    out[ 1 ] = ( float )exp2( ( double )subr( addr( ev100, bloomEmissionMultiplier ), 3.0f ) );  // ev100ToLuminance(evBloom)
+    out[ 2 ] = uncharted2Op( luminanceWhitePoint );
+}
+
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_prepare_final( const __grid_constant__ PrepareFinalArgs a, const __grid_constant__ Uniform u )
 {
-    __shared__ float sScalars[ 3 ];
-    if( threadIdx.x == 0 && threadIdx.y == 0 )
-    {
-        // Exposure.h:36-58: EV100 = log2(avgLuminance * S / K), S = 100, K = 12.5
-        const float ev100 = ( float )log2( ( double )divr( mulr( fmaxf( 0.0f, a.tm->avgLuminance ), 100.0f ), 12.5f ) );
-        const float maxLuminance = mulr( 1.2f, ( float )exp2( ( double )ev100 ) );
-        sScalars[ 0 ] = maxLuminance > 0.0f ? divr( 1.0f, maxLuminance ) : 0.0f;                              // ev100ToLuminousExposure
-        sScalars[ 1 ] = ( float )exp2( ( double )subr( addr( ev100, a.bloomEmissionMultiplier ), 3.0f ) );    // ev100ToLuminance(evBloom)
-        sScalars[ 2 ] = uncharted2Op( a.luminanceWhitePoint );
-    }
-    __syncthreads();
     const int x = blockIdx.x * kBlockW + threadIdx.x;
     const int y = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
     if( x >= u.W || y >= u.yEnd ) return;
-    const float exposure = sScalars[ 0 ], bloomLum = sScalars[ 1 ], whiteScale = sScalars[ 2 ];
+    const float exposure = __ldg( a.scalars ), bloomLum = __ldg( a.scalars + 1 ), whiteScale = __ldg( a.scalars + 2 );
 
     float3       hdr  = unpackUfloat111110( __ldg( at< uint32_t >( a.final, x, y ) ) );
     const float3 emis = unpackUfloat111110( __ldg( at< uint32_t >( a.screenEmission, x, y ) ) );
