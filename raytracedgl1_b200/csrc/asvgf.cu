@@ -200,6 +200,11 @@ struct AsvgfDenoiser_T
     // three CTAs per SM).  Measured on one box, back to back: 1.450 ms per 4K frame against 1.424 ms for the default (one pixel
     // after the other, 64 registers, four CTAs per SM) -- the traffic it saves is paid back in occupancy.
     bool      atrousPair = false;
+    // Programmatic dependent launch (ASVGF_PDL=0 turns it off).  Inside asvgfGradientSamples / asvgfDenoise a kernel whose
+    // predecessor on the stream is this call's previous kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+    // its CTAs are scheduled while the predecessor's last wave drains and block in griddepcontrol.wait (asvgf_device.cuh).  The
+    // first kernel of a call, and a kernel behind an event record / wait, are launched normally.
+    bool      pdl = true, pdlChain = false, pdlArmed = false;
     int       smCount     = 0;
     int32_t   passGyBegin = 0, passGyEnd = 0; // gradient rows the current gradient pass computes (runPass sets them)
     // exposure state (= the reference's tonemapping buffer) and the tables of the histogram pass
@@ -268,6 +273,20 @@ AsvgfResult launchCheck( AsvgfDenoiser_T& d, const char* name )
     return ASVGF_SUCCESS;
 }
 
+// every production kernel goes through here: <<<>>> semantics, plus the programmatic-serialization attribute when armed
+template< typename... KArgs, typename... Args >
+void launchK( AsvgfDenoiser_T& d, void ( *kernel )( KArgs... ), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Args&... args )
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[ 1 ];
+    attr[ 0 ].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[ 0 ].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ( d.pdlChain && d.pdlArmed ) ? 1u : 0u;
+    ( void )cudaLaunchKernelEx( &cfg, kernel, args... ); // the error is picked up by launchCheck
+    d.pdlArmed = d.pdlChain;
+}
+
 #ifdef ASVGF_WITH_LITERAL
 bool literal( const AsvgfDenoiser_T& d ) { return ( d.info.flags & ASVGF_CREATE_LITERAL_KERNELS ) != 0; }
     #define ASVGF_LITERAL_OR( d, literalLaunch, productionLaunch ) do { if( literal( d ) ) { literalLaunch; } else { productionLaunch; } } while( 0 )
@@ -287,7 +306,7 @@ AsvgfResult runGradientSamples( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi,
     a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
     a.haloMiss = d.haloMiss;
     ASVGF_LITERAL_OR( d, ( k_gradient_samples<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_gradient_samples_fast<<< gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ) );
+                      ( launchK( d, k_gradient_samples_fast, gridFor( a.disPing.w, a.gyEnd - a.gyBegin ), kBlock, 0, s, a, u ) ) );
     return launchCheck( d, "k_gradient_samples" );
 }
 
@@ -301,7 +320,7 @@ AsvgfResult runGradientAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, 
     a.history = d.get( ASVGF_IMAGE_DIS_GRADIENT_HISTORY, fi );
     a.iteration = ( int32_t )iteration; a.gyBegin = d.passGyBegin; a.gyEnd = d.passGyEnd;
     ASVGF_LITERAL_OR( d, ( k_gradient_atrous<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_gradient_atrous_fast<<< gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s >>>( a, u ) ) );
+                      ( launchK( d, k_gradient_atrous_fast, gridFor( a.dst.w, a.gyEnd - a.gyBegin ), kBlock, 0, s, a, u ) ) );
     return launchCheck( d, "k_gradient_atrous" );
 }
 
@@ -344,13 +363,13 @@ AsvgfResult runTemporal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
         const dim3 tGrid( grid.x, ( unsigned )( ( u.yEnd - u.yBegin + kTBlockH - 1 ) / kTBlockH ), 1 ), tBlock( kBlockW, kTBlockH, 1 );
         if( d.haloMiss )
         {
-            if( uniformPitch ) k_temporal_fast< true, true ><<< tGrid, tBlock, 0, s >>>( a, u );
-            else k_temporal_fast< false, true ><<< tGrid, tBlock, 0, s >>>( a, u );
+            if( uniformPitch ) launchK( d, k_temporal_fast< true, true >, tGrid, tBlock, 0, s, a, u );
+            else launchK( d, k_temporal_fast< false, true >, tGrid, tBlock, 0, s, a, u );
         }
         else
         {
-            if( uniformPitch ) k_temporal_fast< true, false ><<< tGrid, tBlock, 0, s >>>( a, u );
-            else k_temporal_fast< false, false ><<< tGrid, tBlock, 0, s >>>( a, u );
+            if( uniformPitch ) launchK( d, k_temporal_fast< true, false >, tGrid, tBlock, 0, s, a, u );
+            else launchK( d, k_temporal_fast< false, false >, tGrid, tBlock, 0, s, a, u );
         }
     };
     ASVGF_LITERAL_OR( d, ( k_temporal<<< grid, kBlock, 0, s >>>( a, u ) ), production() );
@@ -366,7 +385,7 @@ AsvgfResult runAntiFirefly( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, con
     a.dst[ 0 ] = d.get( ASVGF_IMAGE_DIFF_ACCUM_COLOR, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SPEC_PING_COLOR, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_INDIR_PING, fi );
     const dim3 grid( ( unsigned )( ( d.W + kAfTile - 1 ) / kAfTile ), ( unsigned )( ( u.yEnd - u.yBegin + kAfTile - 1 ) / kAfTile ), 3 );
     ASVGF_LITERAL_OR( d, ( k_antifirefly<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_antifirefly_fast<<< grid, kAfThreads, 0, s >>>( a, u ) ) );
+                      ( launchK( d, k_antifirefly_fast, grid, dim3( kAfThreads ), 0, s, a, u ) ) );
     return launchCheck( d, "k_antifirefly" );
 }
 
@@ -379,7 +398,7 @@ AsvgfResult runVariance( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     a.histLen = d.get( ASVGF_IMAGE_ACCUM_HISTORY_LENGTH, fi ); a.moments = d.get( ASVGF_IMAGE_DIFF_ACCUM_MOMENTS, fi );
     a.out = d.get( ASVGF_IMAGE_DIFF_PING_COLOR_AND_VARIANCE, fi ); a.lut = d.lut;
     ASVGF_LITERAL_OR( d, ( k_variance<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ),
-                      ( k_variance_fast<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u ) ) );
+                      ( launchK( d, k_variance_fast, gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s, a, u ) ) );
     return launchCheck( d, "k_variance" );
 }
 
@@ -392,7 +411,7 @@ AsvgfResult runGuide( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi )
     a.guide = d.guide; a.lut = d.lut;
     a.yBegin = d.row0; a.yEnd = d.row0 + d.rows;
     const dim3 grid( ( unsigned )( ( d.W + 255 ) / 256 ), ( unsigned )( ( d.rows + 3 ) / 4 ), 1 );
-    k_guide<<< grid, 256, 0, s >>>( a );
+    launchK( d, k_guide, grid, dim3( 256 ), 0, s, a );
     return launchCheck( d, "k_guide" );
 }
 
@@ -462,7 +481,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
             if( e != cudaSuccess ) return e;
             optedIn = true;
         }
-        kernel<<< grid, kAtThreads, smem, s >>>( a, u );
+        launchK( d, kernel, grid, dim3( kAtThreads ), smem, s, a, u );
         return cudaSuccess;
     };
     cudaError_t e = cudaErrorInvalidValue;
@@ -687,6 +706,14 @@ AsvgfResult runPassRows( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const 
     return fail( ASVGF_WRONG_ARGUMENT, "unknown pass " + std::to_string( pass ) );
 }
 
+// the launches of one API call form a chain of programmatic dependent launches (whole-frame handles only)
+struct PdlScope
+{
+    AsvgfDenoiser_T& d;
+    explicit PdlScope( AsvgfDenoiser_T& d_ ) : d( d_ ) { d.pdlChain = d.pdl && d.info.bandRowEnd == 0; d.pdlArmed = false; }
+    ~PdlScope() { d.pdlChain = d.pdlArmed = false; }
+};
+
 AsvgfResult checkCall( AsvgfDenoiser d, uint32_t frameIndex, const AsvgfGlobalUniform* pUniform )
 {
     if( !d ) return fail( ASVGF_WRONG_ARGUMENT, "null denoiser" );
@@ -752,6 +779,7 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
     if( const char* e = std::getenv( "ASVGF_ATROUS_PAIR" ) ) d->atrousPair = std::atoi( e ) != 0;
     if( const char* e = std::getenv( "ASVGF_ATROUS_CENTRE" ) ) d->atrousCentre = std::atoi( e ) != 0;
+    if( const char* e = std::getenv( "ASVGF_PDL" ) ) d->pdl = std::atoi( e ) != 0;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
     if( pInfo->bandRowEnd == 0 )
@@ -1065,6 +1093,7 @@ AsvgfResult asvgfGradientSamples( AsvgfDenoiser d, AsvgfStream stream, uint32_t 
     // (DISPingGradient): when the two are enqueued on different streams the order must be made explicit
     if( d->temporalRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evTemporalDone, 0 ) );
     d->guideValid = d->centreValid = false; // a new frame starts
+    const PdlScope pdl( *d );
     r = runPass( *d, s, frameIndex, u, ASVGF_PASS_GRADIENT_SAMPLES );
     if( r != ASVGF_SUCCESS ) return r;
     d->gradientAtrousDone = false;
@@ -1087,12 +1116,14 @@ AsvgfResult asvgfDenoise( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameInd
     const cudaStream_t s = ( cudaStream_t )stream;
     const Uniform      u = makeUniform( *d, *pUniform );
     d->guideValid = d->centreValid = false;
+    const PdlScope pdl( *d );
     if( d->info.bandRowEnd != 0 && !( d->info.flags & ASVGF_CREATE_BAND_APRON ) )
     {
         r = runGuide( *d, s, frameIndex ); // per-pass band schedule: the temporal pass covers the owned rows only
         if( r != ASVGF_SUCCESS ) return r;
     }
     if( d->gradientsRecorded ) CUDA_TRY( cudaStreamWaitEvent( s, d->evGradientsDone, 0 ) );
+    d->pdlArmed = false;
     if( !d->gradientAtrousDone )
     {
         r = runPass( *d, s, frameIndex, u, ASVGF_PASS_GRADIENT_ATROUS_ALL ); // Denoiser.cpp:87-120
@@ -1107,6 +1138,7 @@ AsvgfResult asvgfDenoise( AsvgfDenoiser d, AsvgfStream stream, uint32_t frameInd
         {
             CUDA_TRY( cudaEventRecord( d->evTemporalDone, s ) );
             d->temporalRecorded = true;
+            d->pdlArmed = false; // the anti-firefly pass sits behind the event record: launched normally
         }
     }
     return ASVGF_SUCCESS;

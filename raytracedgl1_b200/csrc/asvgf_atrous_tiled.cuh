@@ -92,9 +92,11 @@ ASVGF_DEVICE float guideRoughByte( float w ) { return ( float )( __float_as_uint
 __global__ void __launch_bounds__( 256 ) k_guide( const __grid_constant__ GuideArgs a )
 {
     // one thread = four consecutive pixels of a row (W is even; a partial group at the right edge is handled per pair)
+    pdlLaunchDependents();
     const int x0 = ( blockIdx.x * 64 + ( threadIdx.x & 63 ) ) * 4;
     const int y  = a.yBegin + blockIdx.y * 4 + ( threadIdx.x >> 6 );
     if( x0 >= a.guide.w || y >= a.yEnd ) return;
+    pdlWait();
     const bool full = x0 + 3 < a.guide.w;
     uint32_t   n[ 4 ];
     uint16_t   d[ 4 ], mr[ 4 ];
@@ -377,6 +379,7 @@ ASVGF_DEVICE void atrousStore( const AtrousArgs& a, const Uniform& u, int px, in
 template< int STEP, bool ITER0, bool LAST, bool PAIR, bool CENTRE >
 __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : ASVGF_AT_MIN_CTAS ) k_atrous_tiled( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
+    pdlLaunchDependents();
     extern __shared__ __align__( 128 ) uint8_t smemRaw[];
     using G = AtrousGeom< STEP >;
     constexpr int RP = G::RP, NPX = G::NPX, HALO = G::HALO;
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
             const float dz = h2f( ldIf< uint16_t >( a.depth, px, py, ok, ( uint16_t )0x7c00 ) ); // the depth the guide plane carries
             anyValid = anyValid || ( ok && !( dz < 0.0f || dz > 10000.0f ) );
         }
+        pdlWait(); // the depth image is the producer's (complete before the frame's first pass started); everything below reads this frame's passes
         if( !__syncthreads_or( anyValid ) )
         {
 #pragma unroll
@@ -434,6 +438,8 @@ __global__ void __launch_bounds__( kAtThreads, PAIR ? ASVGF_AT_PAIR_MIN_CTAS : A
             return;
         }
     }
+#else
+    pdlWait();
 #endif
 
     // ---- centre-only inputs of this thread's pixels: in flight while the tile is staged ----

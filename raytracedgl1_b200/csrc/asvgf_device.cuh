@@ -67,6 +67,14 @@ struct NormalLut // (sin, cos) of phi_j = j*pi/65535 and theta_k = k*2*pi/65536,
 
 #define ASVGF_DEVICE __device__ __forceinline__
 
+// ---- programmatic dependent launch (sm_90+): inside asvgfDenoise the passes of a frame are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of pass k+1 are scheduled while the last wave of pass k drains
+// (launch latency, argument fetch and index arithmetic overlap the tail) and block in pdlWait() until pass k has completed and
+// flushed.  Nothing written by an earlier pass of the frame is touched before pdlWait(); without the launch attribute both
+// instructions do nothing. ----
+ASVGF_DEVICE void pdlLaunchDependents() { asm volatile( "griddepcontrol.launch_dependents;" ); }
+ASVGF_DEVICE void pdlWait() { asm volatile( "griddepcontrol.wait;" ::: "memory" ); }
+
 // ---- exactly rounded arithmetic (never fused) ----
 ASVGF_DEVICE float mulr( float a, float b ) { return __fmul_rn( a, b ); }
 ASVGF_DEVICE float addr( float a, float b ) { return __fadd_rn( a, b ); }
@@ -110,6 +118,8 @@ ASVGF_DEVICE float4 mulMat( const float* m, float4 v )
 // ---- storage formats ----
 ASVGF_DEVICE float3 decodeE5( uint32_t p ) // Utils.h:194-207; scale 2^(e-24) built from bits, exact
 {
+    // (mantissa | 2^23 bits, then one FMA that takes the 2^23 back out, was tried instead of the int->float conversions: the mask
+    // and the OR need two LOP3 -- one immediate per instruction -- so the count does not drop: 33 I2FP become 33 LOP3 + 11 IADD3 in T)
     const float s = __uint_as_float( ( ( p >> 27 ) + 103u ) << 23 );
     return make_float3( mulr( s, ( float )( p & 0x1ffu ) ), mulr( s, ( float )( ( p >> 9 ) & 0x1ffu ) ), mulr( s, ( float )( ( p >> 18 ) & 0x1ffu ) ) );
 }

@@ -125,11 +125,13 @@ ASVGF_DEVICE bool quotientBelowTenth( float a, float b )
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_samples_fast( const __grid_constant__ GradientSamplesArgs a, const __grid_constant__ Uniform u )
 {
+    pdlLaunchDependents();
     const int gx = blockIdx.x * kBlockW + threadIdx.x;
     const int gy = a.gyBegin + blockIdx.y * kBlockH + threadIdx.y;
     if( gx >= a.disPing.w || gy >= a.gyEnd ) return;
     constexpr int S = 3;
     if( gx * S >= u.W || gy * S >= u.H ) return;
+    pdlWait();
 
     uint32_t* outGrad = atW< uint32_t >( a.disPing, gx, gy );
     uint8_t*  outSlot = atW< uint8_t >( a.gradientPrevPix, gx, gy );
@@ -237,6 +239,7 @@ ASVGF_DEVICE uint32_t gradientAtrousTexel( const uint32_t ( &tap )[ 9 ], const f
 
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_atrous_fast( const __grid_constant__ GradientAtrousArgs a, const __grid_constant__ Uniform u )
 {
+    pdlLaunchDependents();
     const int gx = blockIdx.x * kBlockW + threadIdx.x;
     const int gy = a.gyBegin + blockIdx.y * kBlockH + threadIdx.y;
     if( gx >= a.dst.w || gy >= a.gyEnd ) return;
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_gradient_atrous_fast( co
     const int ax0 = ( gx * S >= sep ? sep : 0 ) / S, ax1 = ( gx * S >= sep ? 2 * sep : sep ) / S;
     const int step = 1 << a.iteration;
     const int sy0 = max( a.src.row0, 0 ), sy1 = min( a.src.row0 + a.src.rows, a.src.h );
+    pdlWait();
 
     uint32_t tap[ 9 ];
     float    w[ 9 ];
@@ -318,10 +322,12 @@ __global__ void __launch_bounds__( kAfThreads, ASVGF_AF_MIN_CTAS ) k_antifirefly
 {
     __shared__ __align__( 16 ) uint32_t sRG[ kAfT ][ kAfT ];
     __shared__ __align__( 16 ) uint16_t sB[ kAfT ][ kAfBPitch ];
+    pdlLaunchDependents();
     const Img& src = a.src[ blockIdx.z ];
     const Img& dst = a.dst[ blockIdx.z ];
     const Rows rows = rowsOf( src );
     const int  bx = blockIdx.x * kAfTile - kAfR, by = u.yBegin + blockIdx.y * kAfTile - kAfR;
+    pdlWait();
 
     constexpr int AF_UNROLL = 5; // loads in flight per thread while staging
     for( int base = threadIdx.x; base < kAfT * kAfT; base += kAfThreads * AF_UNROLL )
@@ -474,10 +480,12 @@ ASVGF_DEVICE float varianceSpatial( const VarianceArgs& a, const Rows& rows, int
 // 4K; queueing the short-history pixels for a second, compacted kernel, 0.096 ms.)
 __global__ void __launch_bounds__( kBlockW* kBlockH ) k_variance_fast( const __grid_constant__ VarianceArgs a, const __grid_constant__ Uniform u )
 {
+    pdlLaunchDependents();
     const int px = blockIdx.x * kBlockW + threadIdx.x;
     const int py = u.yBegin + blockIdx.y * kBlockH + threadIdx.y;
     if( px >= u.W || py >= u.yEnd ) return;
     const Rows rows = rowsOf( a.depth );
+    pdlWait();
 
     const uint16_t dv = __ldg( at< uint16_t >( a.depth, px, py ) );
     const uint32_t ce = __ldg( at< uint32_t >( a.color, px, py ) );

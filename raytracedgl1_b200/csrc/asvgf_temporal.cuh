@@ -137,9 +137,11 @@ ASVGF_DEVICE void reproject( const Uniform& u, int px, int py, float mx, float m
 template< bool UNIFORM, bool BAND >
 __global__ void __launch_bounds__( kBlockW* kTBlockH, ASVGF_T_MIN_CTAS ) k_temporal_fast( const __grid_constant__ TemporalArgs a, const __grid_constant__ Uniform u )
 {
+    pdlLaunchDependents();
     const int px = blockIdx.x * kBlockW + threadIdx.x;
     const int py = u.yBegin + blockIdx.y * kTBlockH + threadIdx.y;
     if( px >= u.W || py >= u.yEnd ) return;
+    pdlWait(); // (the gradient image and, when the previous kernel of the stream is this handle's, the history it may still be writing)
     const Rows     rows   = rowsOf( a.depth );
     const uint32_t pitchT = a.depth.pitchT;
     const uint32_t o      = ( uint32_t )( py * ( int )pitchT + px );
