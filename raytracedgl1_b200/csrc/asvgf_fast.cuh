@@ -329,6 +329,7 @@ __global__ void __launch_bounds__( kAfThreads, ASVGF_AF_MIN_CTAS ) k_antifirefly
     const int  bx = blockIdx.x * kAfTile - kAfR, by = u.yBegin + blockIdx.y * kAfTile - kAfR;
     pdlWait();
 
+#ifdef ASVGF_AF_SCALAR_STAGING
     constexpr int AF_UNROLL = 5; // loads in flight per thread while staging
     for( int base = threadIdx.x; base < kAfT * kAfT; base += kAfThreads * AF_UNROLL )
     {
@@ -350,6 +351,48 @@ __global__ void __launch_bounds__( kAfThreads, ASVGF_AF_MIN_CTAS ) k_antifirefly
             sB[ r ][ c ]  = __half_as_ushort( __float2half_rn( v.z ) );
         }
     }
+#else
+    // Staging by texel PAIRS (ncu of the one-texel form: 57 instructions per staged texel, more than half of the kernel -- a
+    // division by the tile pitch, four bounds tests and a branch around every load).  The tile origin is even and W is even, so a
+    // pair is inside or outside together and its address is 8-byte aligned: lane -> pair column, warp -> row, nine sweeps of
+    // eight rows with all loads in flight, the column test hoisted, one row-pointer increment per sweep; the two pair columns
+    // beyond the 32 lanes (tile columns 64..67) go to threads 0..135.  Out-of-image texels stage as zeros (the pinned fetch).
+    {
+        static_assert( kAfT == 68 && kAfThreads == 256 && ( kAfBPitch % 2 ) == 0, "staging geometry" );
+        constexpr int SWEEPS = ( kAfT + 7 ) / 8; // 9
+        const int  tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        const int  gxp = bx + 2 * tx;
+        const bool okx = ( unsigned )gxp < ( unsigned )rows.w;
+        const int  er = threadIdx.x >> 1, ec = 64 + 2 * ( threadIdx.x & 1 ); // the extra pair of threads 0..135
+        const int  gxe = bx + ec;
+        uint2      raw[ SWEEPS ], rawE = make_uint2( 0u, 0u );
+#pragma unroll
+        for( int k = 0; k < SWEEPS; k++ )
+        {
+            const int  r = 8 * k + ty, gy = by + r;
+            const bool ok = okx && r < kAfT && gy >= rows.y0 && gy < rows.y1;
+            raw[ k ] = make_uint2( 0u, 0u );
+            if( ok ) raw[ k ] = __ldg( reinterpret_cast< const uint2* >( at< uint32_t >( src, gxp, gy ) ) );
+        }
+        {
+            const int gy = by + er;
+            if( er < kAfT && ( unsigned )gxe < ( unsigned )rows.w && gy >= rows.y0 && gy < rows.y1 ) rawE = __ldg( reinterpret_cast< const uint2* >( at< uint32_t >( src, gxe, gy ) ) );
+        }
+        auto put = [ & ]( int r, int c, const uint2 q ) {
+            const float3  v0 = decodeE5( q.x ), v1 = decodeE5( q.y );
+            const __half2 rg0 = __floats2half2_rn( v0.x, v0.y ), rg1 = __floats2half2_rn( v1.x, v1.y ), bb = __floats2half2_rn( v0.z, v1.z );
+            *reinterpret_cast< uint2* >( &sRG[ r ][ c ] )   = make_uint2( *reinterpret_cast< const uint32_t* >( &rg0 ), *reinterpret_cast< const uint32_t* >( &rg1 ) );
+            *reinterpret_cast< uint32_t* >( &sB[ r ][ c ] ) = *reinterpret_cast< const uint32_t* >( &bb );
+        };
+#pragma unroll
+        for( int k = 0; k < SWEEPS; k++ )
+        {
+            const int r = 8 * k + ty;
+            if( r < kAfT ) put( r, 2 * tx, raw[ k ] );
+        }
+        if( er < kAfT ) put( er, ec, rawE );
+    }
+#endif
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
