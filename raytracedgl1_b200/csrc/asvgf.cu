@@ -453,6 +453,7 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     a.lut = d.lut; a.iteration = ( int32_t )iteration;
     a.guide = d.guide;
     a.centre = d.centre; a.centreValid = d.centreValid ? 1 : 0;
+    a.uniformPitch = ( a.guide.pitchT == a.srcDiff.pitchT && a.guide.pitchT == a.srcSpec.pitchT && a.guide.pitchT == a.srcIndir.pitchT ) ? 1 : 0;
     if( iteration == 0 ) d.centreValid = true; // this launch writes it
 
     const int step = 1 << iteration;

@@ -64,6 +64,7 @@ struct AtrousArgs
     Img       guide;       // (n.xyz, depth | roughness byte) of the current frame, written by the temporal pass or k_guide
     Img       centre;      // (kLum, invK1, invK2, P) per pixel: the iteration-independent weight constants, written by iteration 0
     int32_t   centreValid; // iterations >= 1: read `centre` instead of re-deriving the constants from three more images
+    int32_t   uniformPitch; // guide, srcDiff, srcSpec and srcIndir hold the same number of texels per row: one texel offset per staged texel
     NormalLut lut;
     int32_t   iteration;
 };

@@ -151,10 +151,22 @@ constexpr size_t atrousSmemBytes( int step )
     return step >= 4 ? atrousTiledSmemBytes( step ) : ( size_t )( kAtTileW + 2 * step ) * ( kAtTileH + 2 ) * 64;
 }
 
-template< int STEP >
-ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, float4* sB, float4* sC, float4* sD )
+// Staging of one tile.  UNI: the guide plane and the three colour images hold the same number of texels per row (the library's
+// own allocation): one texel offset serves the four loads of a texel.  INTERIOR: every staged texel lies inside the image and the
+// stored rows (all tiles but the frame / band border): no bounds tests, no zero fill.  Both are uniform per CTA; the general form
+// (own pitch per image, every texel tested) is the third copy.  (ncu / SASS of the single general form: 90 instructions per staged
+// texel at STEP < 4 and 66 at STEP >= 4, of which 37 decode, 8 move data and the rest was addressing, bounds and zero fill.)
+template< int STEP, bool UNI, bool INTERIOR >
+ASVGF_DEVICE void atrousStageImpl( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, float4* sB, float4* sC, float4* sD )
 {
     using G = AtrousGeom< STEP >;
+    const uint32_t pitchT = a.guide.pitchT;
+    // texel offset of staged (row 0, column 0); wraps for tiles that start outside the image -- only dereferenced under `ok`
+    const uint32_t off0 = ( uint32_t )( ( yBase - STEP ) * ( int )pitchT + xBase - G::HALO );
+    const float4*   bG = reinterpret_cast< const float4* >( a.guide.p0 );
+    const uint2*    bD = reinterpret_cast< const uint2* >( a.srcDiff.p0 );
+    const uint32_t* bS = reinterpret_cast< const uint32_t* >( a.srcSpec.p0 );
+    const uint32_t* bI = reinterpret_cast< const uint32_t* >( a.srcIndir.p0 );
     if constexpr( G::VEC )
     {
         constexpr int NGRP = G::GROUPS * G::TROWS;
@@ -165,23 +177,34 @@ ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows
             if( NGRP % kAtThreads != 0 && g >= NGRP ) break;
             const int  r = g / G::GROUPS, cg = g - r * G::GROUPS;
             const int  gx = xBase - G::HALO + 4 * cg, gy = yBase + ( r - 1 ) * STEP;
-            const bool rowOk = gy >= rows.y0 && gy < rows.y1;
-            const bool ok01 = rowOk && gx >= 0 && gx < u.W, ok23 = rowOk && gx >= 0 && gx + 2 < u.W; // gx is a multiple of 4, W is even
+            const bool rowOk = INTERIOR || ( gy >= rows.y0 && gy < rows.y1 );
+            const bool ok01 = INTERIOR || ( rowOk && gx >= 0 && gx < u.W ), ok23 = INTERIOR || ( rowOk && gx >= 0 && gx + 2 < u.W ); // gx is a multiple of 4, W is even
             float4 ga[ 4 ];
             uint4  d01, d23, sp, in;
             {
-                const float4* pg = at< float4 >( a.guide, gx, gy );
-                const float4  z4 = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-                ga[ 0 ] = ok01 ? __ldg( pg ) : z4;
-                ga[ 1 ] = ok01 ? __ldg( pg + 1 ) : z4;
-                ga[ 2 ] = ok23 ? __ldg( pg + 2 ) : z4;
-                ga[ 3 ] = ok23 ? __ldg( pg + 3 ) : z4;
-                const uint4 z = make_uint4( 0u, 0u, 0u, 0u );
-                const uint4* pd = reinterpret_cast< const uint4* >( at< uint2 >( a.srcDiff, gx, gy ) );
-                d01 = ok01 ? __ldg( pd ) : z;
-                d23 = ok23 ? __ldg( pd + 1 ) : z;
-                sp  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcSpec, gx, gy ) ) ) : z;
-                in  = ok01 ? __ldg( reinterpret_cast< const uint4* >( at< uint32_t >( a.srcIndir, gx, gy ) ) ) : z;
+                const uint32_t off = off0 + ( uint32_t )r * ( ( uint32_t )STEP * pitchT ) + 4u * ( uint32_t )cg;
+                const float4*  pg = UNI ? bG + off : at< float4 >( a.guide, gx, gy );
+                const uint4*   pd = UNI ? reinterpret_cast< const uint4* >( bD + off ) : reinterpret_cast< const uint4* >( at< uint2 >( a.srcDiff, gx, gy ) );
+                const uint4*   ps = UNI ? reinterpret_cast< const uint4* >( bS + off ) : reinterpret_cast< const uint4* >( at< uint32_t >( a.srcSpec, gx, gy ) );
+                const uint4*   pi = UNI ? reinterpret_cast< const uint4* >( bI + off ) : reinterpret_cast< const uint4* >( at< uint32_t >( a.srcIndir, gx, gy ) );
+                if constexpr( INTERIOR )
+                {
+                    ga[ 0 ] = __ldg( pg ); ga[ 1 ] = __ldg( pg + 1 ); ga[ 2 ] = __ldg( pg + 2 ); ga[ 3 ] = __ldg( pg + 3 );
+                    d01 = __ldg( pd ); d23 = __ldg( pd + 1 ); sp = __ldg( ps ); in = __ldg( pi );
+                }
+                else
+                {
+                    const float4 z4 = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+                    const uint4  z  = make_uint4( 0u, 0u, 0u, 0u );
+                    ga[ 0 ] = ok01 ? __ldg( pg ) : z4;
+                    ga[ 1 ] = ok01 ? __ldg( pg + 1 ) : z4;
+                    ga[ 2 ] = ok23 ? __ldg( pg + 2 ) : z4;
+                    ga[ 3 ] = ok23 ? __ldg( pg + 3 ) : z4;
+                    d01 = ok01 ? __ldg( pd ) : z;
+                    d23 = ok23 ? __ldg( pd + 1 ) : z;
+                    sp  = ok01 ? __ldg( ps ) : z;
+                    in  = ok01 ? __ldg( pi ) : z;
+                }
             }
             const int      e0 = r * G::RP + cg; // texel k of the group -> quarter row k
             const uint32_t dd[ 8 ] = { d01.x, d01.y, d01.z, d01.w, d23.x, d23.y, d23.z, d23.w };
@@ -211,19 +234,18 @@ ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows
             const int  e = threadIdx.x + it * kAtThreads;
             const int  r = e / G::TW, c = e - r * G::TW;
             const int  gx = xBase - G::HALO + c, gy = yBase + ( r - 1 ) * STEP;
-            const bool ok = e < G::NPX && rows.in( gx, gy );
-            // one multiply-add per image (a run-time "the four images share their pitch" switch was tried: the compiler evaluated
-            // both address forms and selected per load, ~30 instructions per staged texel)
-            ga[ it ] = ok ? __ldg( at< float4 >( a.guide, gx, gy ) ) : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-            dd[ it ] = ok ? __ldg( at< uint2 >( a.srcDiff, gx, gy ) ) : make_uint2( 0u, 0u );
-            ss[ it ] = ok ? __ldg( at< uint32_t >( a.srcSpec, gx, gy ) ) : 0u;
-            ii[ it ] = ok ? __ldg( at< uint32_t >( a.srcIndir, gx, gy ) ) : 0u;
+            const bool ok = ( ( it + 1 ) * kAtThreads <= G::NPX || e < G::NPX ) && ( INTERIOR || rows.in( gx, gy ) ); // (threadIdx.x < kAtThreads)
+            const uint32_t off = off0 + ( uint32_t )r * ( ( uint32_t )STEP * pitchT ) + ( uint32_t )c;
+            ga[ it ] = ok ? __ldg( UNI ? bG + off : at< float4 >( a.guide, gx, gy ) ) : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+            dd[ it ] = ok ? __ldg( UNI ? bD + off : at< uint2 >( a.srcDiff, gx, gy ) ) : make_uint2( 0u, 0u );
+            ss[ it ] = ok ? __ldg( UNI ? bS + off : at< uint32_t >( a.srcSpec, gx, gy ) ) : 0u;
+            ii[ it ] = ok ? __ldg( UNI ? bI + off : at< uint32_t >( a.srcIndir, gx, gy ) ) : 0u;
         }
 #pragma unroll
         for( int it = 0; it < NIT; it++ )
         {
             const int e = threadIdx.x + it * kAtThreads;
-            if( e >= G::NPX ) break;
+            if( ( it + 1 ) * kAtThreads > G::NPX && e >= G::NPX ) break;
             const float2 rg = __half22float2( *reinterpret_cast< const __half2* >( &dd[ it ].x ) );
             const float2 bv = __half22float2( *reinterpret_cast< const __half2* >( &dd[ it ].y ) );
             const float3 s3 = decodeE5( ss[ it ] ), i3 = decodeE5( ii[ it ] );
@@ -233,6 +255,24 @@ ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows
             sD[ e ] = make_float4( i3.x, i3.y, i3.z, guideRoughByte( ga[ it ].w ) );
         }
     }
+}
+
+template< int STEP >
+ASVGF_DEVICE void atrousStage( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, float4* sB, float4* sC, float4* sD )
+{
+    using G = AtrousGeom< STEP >;
+#ifdef ASVGF_AT_GENERAL_STAGING
+    atrousStageImpl< STEP, false, false >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
+#else
+    // staged rows yBase - STEP .. yBase + kAtTileH * STEP, staged columns xBase - HALO .. xBase + kAtTileW + HALO - 1
+    const bool interior = xBase - G::HALO >= 0 && xBase + kAtTileW + G::HALO <= u.W && yBase - STEP >= rows.y0 && yBase + kAtTileH * STEP < rows.y1;
+    if( a.uniformPitch )
+    {
+        if( interior ) atrousStageImpl< STEP, true, true >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
+        else atrousStageImpl< STEP, true, false >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
+    }
+    else atrousStageImpl< STEP, false, false >( a, u, rows, xBase, yBase, sA, sB, sC, sD );
+#endif
 }
 
 // state of one output pixel while its taps are evaluated
