@@ -17,7 +17,7 @@
 // 60 KB and more from stride 8 (three).
 #pragma once
 
-#include "asvgf_atrous_half.cuh"
+#include "../raytracedgl1_b200/csrc/asvgf_atrous_half.cuh"
 
 namespace asvgf
 {

@@ -9,7 +9,6 @@
 #include "asvgf_temporal.cuh"
 #include "asvgf_atrous_tiled.cuh"
 #include "asvgf_atrous_half.cuh"
-#include "asvgf_atrous_pipe.cuh"
 #include "asvgf_post.cuh"
 #ifdef ASVGF_WITH_LITERAL // expression-by-expression kernels for A/B numerics; not part of the release build
     #include "../../experiments/asvgf_literal_kernels.cuh"
@@ -196,18 +195,8 @@ struct AsvgfDenoiser_T
     bool        gradientAtrousDone = false; // ASVGF_CREATE_EAGER_GRADIENT_ATROUS: the chain already ran behind the gradient samples
     bool        guideValid = false;         // the guide plane matches the geometry images of the frame being denoised
     uint64_t  launchCount = 0;
-    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 32 ] = {}; // cudaFuncSetAttribute done for (iteration, composing + 2 * pair + 4 * centre + 8 * packed tile)
+    bool      atrousOptIn[ ASVGF_MAX_ATROUS_ITERATIONS ][ 4 ] = {}; // cudaFuncSetAttribute done for (iteration, composing + 2 * centre)
     bool      atrousCentre = true; // iterations >= 1 read the weight constants iteration 0 published (ASVGF_ATROUS_CENTRE=0: re-derive them)
-    // ASVGF_ATROUS_PAIR=1: a thread filters two vertically adjacent pixels together (2/3 of the shared-memory traffic, 80 registers,
-    // three CTAs per SM).  Measured on one box, back to back: 1.450 ms per 4K frame against 1.424 ms for the default (one pixel
-    // after the other, 64 registers, four CTAs per SM) -- the traffic it saves is paid back in occupancy.
-    bool      atrousPair = false;
-    // ASVGF_ATROUS_HALF=0/1: the a-trous tile in shared memory as fp32 planes (k_atrous_tiled, 64 B per texel) or packed with the
-    // colours as the fp16 values they are (k_atrous_half, 40 B per texel; identical results)
-    bool      atrousHalf = true;
-    // ASVGF_ATROUS_PIPE=0/1: persistent CTAs that receive the next tile's raw texels by asynchronous copies while they filter the
-    // current one (k_atrous_pipe, asvgf_atrous_pipe.cuh)
-    bool      atrousPipe = false;
     // Programmatic dependent launch (ASVGF_PDL=0 turns it off).  Inside asvgfGradientSamples / asvgfDenoise a kernel whose
     // predecessor on the stream is this call's previous kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization:
     // its CTAs are scheduled while the predecessor's last wave drains and block in griddepcontrol.wait (asvgf_device.cuh).  The
@@ -479,13 +468,9 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     const int    rows   = u.yEnd - u.yBegin;
     const int    bands  = ( rows + kAtTileH * step - 1 ) / ( kAtTileH * step );
     const int    tilesX = ( int )( ( d.W + kAtTileW - 1 ) / kAtTileW );
-    const bool   pipe   = d.atrousPipe && !d.atrousPair;
-    const bool   half   = d.atrousHalf && !d.atrousPair && !pipe;
-    const size_t smem   = pipe ? atrousPipeSmemBytes( step ) : half ? atrousHalfSmemBytes( step ) : atrousSmemBytes( step );
-    const int    numTiles = tilesX * bands * step;
-    const dim3   grid = pipe ? dim3( ( unsigned )std::min( numTiles, d.smCount * atrousPipeCtasPerSm( step ) ), 1, 1 ) : dim3( ( unsigned )tilesX, ( unsigned )( bands * step ), 1 );
-    const bool pair = d.atrousPair;
-    // the opt-in to more than 48 KB of dynamic shared memory is per function and per device: once, not per launch
+    const size_t smem   = atrousHalfSmemBytes( step );
+    const dim3   grid( ( unsigned )tilesX, ( unsigned )( bands * step ), 1 );
+    // the opt-in to more than 48 KB of dynamic shared memory (strides >= 16) is per function and per device: once, not per launch
     auto launch = [ & ]( auto kernel, bool& optedIn ) -> cudaError_t {
         if( !optedIn )
         {
@@ -496,26 +481,15 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
         launchK( d, kernel, grid, dim3( kAtThreads ), smem, s, a, u );
         return cudaSuccess;
     };
-    auto launchPipe = [ & ]( auto kernel, bool& optedIn ) -> cudaError_t {
-        if( !optedIn )
-        {
-            cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
-            if( e != cudaSuccess ) return e;
-            optedIn = true;
-        }
-        launchK( d, kernel, grid, dim3( kAtThreads ), smem, s, a, u, tilesX, numTiles );
-        return cudaSuccess;
-    };
     cudaError_t e = cudaErrorInvalidValue;
     const bool  centre = a.centreValid != 0 && iteration > 0 && d.atrousCentre;
-    bool&       opted = d.atrousOptIn[ iteration ][ ( last ? 1 : 0 ) + ( pair ? 2 : 0 ) + ( centre ? 4 : 0 ) + ( half ? 8 : 0 ) + ( pipe ? 16 : 0 ) ];
-#define ASVGF_ATROUS_LAUNCH2( S, I0, L, C ) ( pipe ? launchPipe( k_atrous_pipe< S, I0, L, C >, opted ) : half ? launch( k_atrous_half< S, I0, L, C >, opted ) : pair ? launch( k_atrous_tiled< S, I0, L, true, C >, opted ) : launch( k_atrous_tiled< S, I0, L, false, C >, opted ) )
-#define ASVGF_ATROUS_LAUNCH( S, I0, L ) ( centre ? ASVGF_ATROUS_LAUNCH2( S, I0, L, true ) : ASVGF_ATROUS_LAUNCH2( S, I0, L, false ) )
+    bool&       opted = d.atrousOptIn[ iteration ][ ( last ? 1 : 0 ) + ( centre ? 2 : 0 ) ];
+#define ASVGF_ATROUS_LAUNCH( S, I0, L ) ( centre ? launch( k_atrous_half< S, I0, L, true >, opted ) : launch( k_atrous_half< S, I0, L, false >, opted ) )
 #define ASVGF_ATROUS_CASE( S ) \
     case S: e = last ? ASVGF_ATROUS_LAUNCH( S, false, true ) : ASVGF_ATROUS_LAUNCH( S, false, false ); break;
     switch( step )
     {
-        case 1: e = ASVGF_ATROUS_LAUNCH2( 1, true, false, false ); break; // iteration 0 is never the last (atrousIterations >= 2)
+        case 1: e = launch( k_atrous_half< 1, true, false, false >, opted ); break; // iteration 0 is never the last (atrousIterations >= 2)
         ASVGF_ATROUS_CASE( 2 )
         ASVGF_ATROUS_CASE( 4 )
         ASVGF_ATROUS_CASE( 8 )
@@ -527,9 +501,8 @@ AsvgfResult runAtrous( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Un
     }
 #undef ASVGF_ATROUS_CASE
 #undef ASVGF_ATROUS_LAUNCH
-#undef ASVGF_ATROUS_LAUNCH2
-    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_tiled)" );
-    return launchCheck( d, "k_atrous_tiled" );
+    if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_atrous_half)" );
+    return launchCheck( d, "k_atrous_half" );
 }
 
 AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const Uniform& u )
@@ -799,11 +772,8 @@ AsvgfResult asvgfCreate( const AsvgfCreateInfo* pInfo, AsvgfDenoiser* pDenoiser 
     if( !d ) return fail( ASVGF_OUT_OF_MEMORY, "host allocation failed" );
     d->info = *pInfo; d->device = device;
     d->W = pInfo->renderWidth; d->H = pInfo->renderHeight; d->iterations = pInfo->atrousIterations;
-    if( const char* e = std::getenv( "ASVGF_ATROUS_PAIR" ) ) d->atrousPair = std::atoi( e ) != 0;
     if( const char* e = std::getenv( "ASVGF_ATROUS_CENTRE" ) ) d->atrousCentre = std::atoi( e ) != 0;
     if( const char* e = std::getenv( "ASVGF_PDL" ) ) d->pdl = std::atoi( e ) != 0;
-    if( const char* e = std::getenv( "ASVGF_ATROUS_HALF" ) ) d->atrousHalf = std::atoi( e ) != 0;
-    if( const char* e = std::getenv( "ASVGF_ATROUS_PIPE" ) ) d->atrousPipe = std::atoi( e ) != 0;
     const int32_t H = ( int32_t )d->H, gH = ( int32_t )( ( d->H + 1 ) / 3 > 1 ? ( d->H + 1 ) / 3 : 1 );
 
     if( pInfo->bandRowEnd == 0 )
@@ -1315,14 +1285,14 @@ const char* asvgfPassName( uint32_t pass )
     if( pass == ASVGF_PASS_TEMPORAL ) return "k_temporal";
     if( pass == ASVGF_PASS_ANTIFIREFLY ) return "k_antifirefly";
     if( pass == ASVGF_PASS_VARIANCE ) return "k_variance";
-    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_tiled";
+    if( pass >= ASVGF_PASS_ATROUS_0 && pass < ASVGF_PASS_COUNT ) return "k_atrous_half";
     return "?";
 }
 
 // kernel the default configuration launches for a pass of an N-iteration chain
 const char* asvgfPassKernelName( uint32_t pass, uint32_t atrousIterations )
 {
-    ( void )atrousIterations; // every a-trous iteration runs k_atrous_tiled by default
+    ( void )atrousIterations; // every a-trous iteration runs k_atrous_half
     return asvgfPassName( pass );
 }
 
