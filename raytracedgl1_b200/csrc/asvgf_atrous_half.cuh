@@ -1,20 +1,25 @@
 // asvgf_atrous_half.cuh -- the a-trous kernel on a PACKED tile (CmSVGFAtrous_Iter0.comp / CmSVGFAtrous.comp), sm_100a.
 //
-// Same filter, same arithmetic and the same results bit for bit as k_atrous_tiled (asvgf_atrous_tiled.cuh); what changes is what
-// a tap reads from shared memory.  ncu of k_atrous_tiled: 36 + 4 LDS.128 per pixel = 160 shared-memory wavefronts per warp-pixel;
-// four schedulers at ~525 issue slots per warp-pixel ask the 128 B/clk pipe for 640 clk of loads per 525 clk of issue -- the tap
-// loop is bound by shared-memory bandwidth (pipe 65-72 % busy, issue 53-62 %), and trimming instructions elsewhere does not move it
-// (staging cut from 90 to 64 instructions per texel: 0.3 % of the frame).  So the tile shrinks instead:
+// Same filter, same arithmetic and the same results bit for bit as the kernel that kept the tile as four fp32 planes
+// (experiments/asvgf_atrous_fp32.cuh); what changes is what a tap reads from shared memory.  ncu of that kernel: 36 + 4 LDS.128 per
+// pixel = 160 shared-memory wavefronts per warp-pixel; four schedulers at ~525 issue slots per warp-pixel ask the 128 B/clk pipe
+// for 640 clk of loads per 525 clk of issue -- the tap loop was bound by shared-memory bandwidth (pipe 65-72 % busy, issue
+// 53-62 %), and trimming instructions elsewhere did not move it (staging cut from 90 to 64 instructions per texel: 0.3 % of the
+// frame).  So the tile shrinks instead:
 //
 //   * every colour the filter reads is EXACT in fp16 -- the diffuse image is rgba16f, E5B9G9R9 components are 9-bit mantissas
 //     times 2^(e-24) with e <= 31 (all representable, subnormals included), depth is r16f, roughness a byte -- so a texel is kept as
 //       plane A (16 B): n.x, n.y, n.z (fp32), half2( depth, roughness byte )
-//       plane B (16 B): half2( diff.r, diff.g ), half2( diff.b, variance ), luminance (fp32), half2( spec.r, spec.g )
-//       plane C ( 8 B): half2( spec.b, indir.r ), half2( indir.g, indir.b )
-//     40 bytes instead of 64: a tap costs 4 + 4 + 2 = 10 wavefronts instead of 16, and the ten colour halves are widened in
-//     registers (HADD2.F32; the depth and roughness differences take the half operand directly: FHADD).  Widening is exact, the
-//     sums and products see the same fp32 values as before: identical output.
-//   * the 8-byte plane has its own quarter-row pitch in the vector layout (a wavefront of LDS.64 spans 16 lanes).
+//       plane B (16 B): diff.r, diff.g, diff.b, variance (fp32)
+//       plane C (16 B): luminance (fp32), half2( spec.r, spec.g ), half2( spec.b, indir.r ), half2( indir.g, indir.b )
+//     48 bytes instead of 64: a tap costs 12 wavefronts instead of 16, and the six packed colours are widened in registers
+//     (HADD2.F32; the depth and roughness differences take the half operand directly: FHADD, sm_100's mixed-precision add).
+//     Widening is exact, the sums and products see the same fp32 values as before: identical output.
+//   * -DASVGF_AT_ALL_HALF packs the diffuse colour too (plane B: half2( r, g ), half2( b, variance ), luminance, half2( spec.r,
+//     spec.g ); plane C 8 bytes with its own quarter-row pitch: 40 B per texel, 10 wavefronts and 10 widenings per tap).  Measured
+//     back to back at 4K: fp32 planes 1.3865 ms per frame, all-half 1.3160, this layout 1.3107 -- once the shared-memory pipe
+//     is no longer the limit (38-54 % busy) the widenings cost what the wavefronts save.
+//   * the sky vote of iterations >= 1 comes from the staged guide depths (one memory round trip per tile, not two).
 #pragma once
 
 #include "asvgf_atrous_tiled.cuh"
@@ -24,10 +29,22 @@ namespace asvgf
 
 // quarter-row pitch of the 8-byte plane: the 16 slots a half warp touches, q * GP8 + j (q, j = 0..3), must differ modulo 16
 constexpr int    atrousGroupPitch8( int step ) { int g = ( kAtTileW + 2 * atrousHalo( step ) ) / 4; while( g % 16 != 4 && g % 16 != 12 ) g++; return g; }
+#ifndef ASVGF_AT_ALL_HALF
+    #define ASVGF_AT_HYBRID // the default layout (above)
+#endif
+#ifdef ASVGF_AT_HYBRID
+using AtC = uint4;
+#else
+using AtC = uint2;
+#endif
 template< int STEP > struct AtrousGeomH : AtrousGeom< STEP >
 {
     using G = AtrousGeom< STEP >;
+#ifdef ASVGF_AT_HYBRID
+    static constexpr int GP8  = G::GP;
+#else
     static constexpr int GP8  = G::VEC ? atrousGroupPitch8( STEP ) : 0;
+#endif
     static constexpr int RP8  = G::VEC ? 4 * GP8 : G::TW;
     static constexpr int NPX8 = RP8 * G::TROWS;
     static __device__ __forceinline__ int slot8( int row, int col ) { return G::VEC ? row * RP8 + ( col & 3 ) * GP8 + ( col >> 2 ) : row * RP8 + col; }
@@ -36,7 +53,11 @@ constexpr size_t atrousHalfSmemBytes( int step )
 {
     const int tw  = kAtTileW + 2 * ( step >= 4 ? atrousHalo( step ) : step );
     const int npx = ( step >= 4 ? 4 * atrousGroupPitch( step ) : tw ) * ( kAtTileH + 2 ), npx8 = ( step >= 4 ? 4 * atrousGroupPitch8( step ) : tw ) * ( kAtTileH + 2 );
+#ifdef ASVGF_AT_HYBRID
+    return ( size_t )npx * 48;
+#else
     return ( size_t )npx * 32 + ( size_t )npx8 * 8;
+#endif
 }
 
 ASVGF_DEVICE uint32_t packHalf2( float lo, float hi )
@@ -60,14 +81,19 @@ ASVGF_DEVICE float halfHiMinus( uint32_t v, float f )
 }
 
 // one staged texel -> the three planes
-ASVGF_DEVICE void atrousPackTexel( const float4 ga, const uint32_t d0, const uint32_t d1, const uint32_t encSpec, const uint32_t encIndir, float4& pA, uint4& pB, uint2& pC )
+ASVGF_DEVICE void atrousPackTexel( const float4 ga, const uint32_t d0, const uint32_t d1, const uint32_t encSpec, const uint32_t encIndir, float4& pA, uint4& pB, AtC& pC )
 {
     const float2 rg = unpackHalf2( d0 ), bv = unpackHalf2( d1 );
     const float3 s3 = decodeE5( encSpec ), i3 = decodeE5( encIndir );
     // depth came from an fp16 image and the roughness byte is an integer <= 255: both convert back exactly
     pA = make_float4( ga.x, ga.y, ga.z, __uint_as_float( packHalf2( guideDepth( ga.w ), guideRoughByte( ga.w ) ) ) );
+#ifdef ASVGF_AT_HYBRID
+    pB = make_uint4( __float_as_uint( rg.x ), __float_as_uint( rg.y ), __float_as_uint( bv.x ), __float_as_uint( bv.y ) );
+    pC = make_uint4( __float_as_uint( luminance( make_float3( rg.x, rg.y, bv.x ) ) ), packHalf2( s3.x, s3.y ), packHalf2( s3.z, i3.x ), packHalf2( i3.y, i3.z ) );
+#else
     pB = make_uint4( d0, d1, __float_as_uint( luminance( make_float3( rg.x, rg.y, bv.x ) ) ), packHalf2( s3.x, s3.y ) );
     pC = make_uint2( packHalf2( s3.z, i3.x ), packHalf2( i3.y, i3.z ) );
+#endif
 }
 
 // Loads the tile into registers, takes the CTA's vote "does the tile hold a valid surface among its own pixels" from the guide
@@ -78,7 +104,7 @@ ASVGF_DEVICE void atrousPackTexel( const float4 ga, const uint32_t d0, const uin
 template< int STEP > constexpr bool atrousFusedVote() { return !AtrousGeom< STEP >::VEC || AtrousGeom< STEP >::GROUPS * AtrousGeom< STEP >::TROWS <= kAtThreads; }
 
 template< int STEP, bool UNI, bool INTERIOR, bool VOTE >
-ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, uint2* sC )
+ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, AtC* sC )
 {
     using G = AtrousGeomH< STEP >;
     constexpr bool FUSED = VOTE && atrousFusedVote< STEP >();
@@ -139,7 +165,7 @@ ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, co
 #pragma unroll
             for( int k = 0; k < 4; k++ )
             {
-                float4 pA; uint4 pB; uint2 pC;
+                float4 pA; uint4 pB; AtC pC;
                 atrousPackTexel( ga[ k ], dd[ 2 * k ], dd[ 2 * k + 1 ], ss[ k ], ii[ k ], pA, pB, pC );
                 sA[ e0 + k * G::GP ]  = pA;
                 sB[ e0 + k * G::GP ]  = pB;
@@ -175,7 +201,7 @@ ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, co
         {
             const int e = threadIdx.x + it * kAtThreads;
             if( ( it + 1 ) * kAtThreads > G::NPX && e >= G::NPX ) break;
-            float4 pA; uint4 pB; uint2 pC;
+            float4 pA; uint4 pB; AtC pC;
             atrousPackTexel( ga[ it ], dd[ it ].x, dd[ it ].y, ss[ it ], ii[ it ], pA, pB, pC );
             sA[ e ] = pA; sB[ e ] = pB; sC[ e ] = pC;
         }
@@ -184,7 +210,7 @@ ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, co
 }
 
 template< int STEP, bool VOTE >
-ASVGF_DEVICE bool atrousStageHalf( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, uint2* sC )
+ASVGF_DEVICE bool atrousStageHalf( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, AtC* sC )
 {
     using G = AtrousGeom< STEP >;
     const bool interior = xBase - G::HALO >= 0 && xBase + kAtTileW + G::HALO <= u.W && yBase - STEP >= rows.y0 && yBase + kAtTileH * STEP < rows.y1;
@@ -201,20 +227,27 @@ struct AtrousWide
 {
     float4 A, B, C, D; // the four planes of k_atrous_tiled: (n, depth), (diff, variance), (spec, luminance), (indir, roughness byte)
 };
-ASVGF_DEVICE AtrousWide atrousWiden( const float4 pA, const uint4 pB, const uint2 pC )
+ASVGF_DEVICE AtrousWide atrousWiden( const float4 pA, const uint4 pB, const AtC pC )
 {
     const float2 dr = unpackHalf2( __float_as_uint( pA.w ) );
+#ifdef ASVGF_AT_HYBRID
+    const float2 rg = make_float2( __uint_as_float( pB.x ), __uint_as_float( pB.y ) ), bv = make_float2( __uint_as_float( pB.z ), __uint_as_float( pB.w ) );
+    const float2 s01 = unpackHalf2( pC.y ), s2i0 = unpackHalf2( pC.z ), i12 = unpackHalf2( pC.w );
+    const float  lum = __uint_as_float( pC.x );
+#else
     const float2 rg = unpackHalf2( pB.x ), bv = unpackHalf2( pB.y ), s01 = unpackHalf2( pB.w ), s2i0 = unpackHalf2( pC.x ), i12 = unpackHalf2( pC.y );
+    const float  lum = __uint_as_float( pB.z );
+#endif
     AtrousWide w;
     w.A = make_float4( pA.x, pA.y, pA.z, dr.x );
     w.B = make_float4( rg.x, rg.y, bv.x, bv.y );
-    w.C = make_float4( s01.x, s01.y, s2i0.x, __uint_as_float( pB.z ) );
+    w.C = make_float4( s01.x, s01.y, s2i0.x, lum );
     w.D = make_float4( s2i0.y, i12.x, i12.y, dr.y );
     return w;
 }
 
 // one tap from the packed planes: AtrousPix::tap with the widening folded in (same operations on the same fp32 values)
-ASVGF_DEVICE void atrousTapHalf( AtrousPix& s, const float4 qA, const uint4 qB, const uint2 qC, const bool diag, const float lk )
+ASVGF_DEVICE void atrousTapHalf( AtrousPix& s, const float4 qA, const uint4 qB, const AtC qC, const bool diag, const float lk )
 {
     const float TINY = __uint_as_float( 0x00800000u );
     const float nN    = fmaxf( TINY, fmaf( s.n.z, qA.z, fmaf( s.n.y, qA.y, s.n.x * qA.x ) ) );
@@ -223,13 +256,23 @@ ASVGF_DEVICE void atrousTapHalf( AtrousPix& s, const float4 qA, const uint4 qB, 
     const float wZ    = fabsf( halfLoMinus( dr, s.depth ) ) * ( diag ? s.invK2 : s.invK1 ); // |q.depth - depth| = |depth - q.depth|
     const float eN    = fmaf( 128.0f, L, lk );
     const float eBase = fmaf( -wZ, wZ, eN );
-    const float eDiff = fmaf( fabsf( s.l - __uint_as_float( qB.z ) ), -s.kLum, eBase );
+#ifdef ASVGF_AT_HYBRID
+    const float qLum = __uint_as_float( qC.x );
+#else
+    const float qLum = __uint_as_float( qB.z );
+#endif
+    const float eDiff = fmaf( fabsf( s.l - qLum ), -s.kLum, eBase );
     const float wBase = fex2( eBase );
     const float wDiff = fex2( eDiff );
     float       rfac;
     asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( halfHiMinus( dr, s.roughByte ) ) ), "f"( -s.wR10 ), "f"( s.wRough ) );
     const float wSpec = rfac * fex2( fmaf( s.P, L, eBase ) );
+#ifdef ASVGF_AT_HYBRID
+    const float2 rg = make_float2( __uint_as_float( qB.x ), __uint_as_float( qB.y ) ), bv = make_float2( __uint_as_float( qB.z ), __uint_as_float( qB.w ) );
+    const float2 s01 = unpackHalf2( qC.y ), s2i0 = unpackHalf2( qC.z ), i12 = unpackHalf2( qC.w );
+#else
     const float2 rg = unpackHalf2( qB.x ), bv = unpackHalf2( qB.y ), s01 = unpackHalf2( qB.w ), s2i0 = unpackHalf2( qC.x ), i12 = unpackHalf2( qC.y );
+#endif
     s.diff.x = fmaf( rg.x, wDiff, s.diff.x ); s.diff.y = fmaf( rg.y, wDiff, s.diff.y ); s.diff.z = fmaf( bv.x, wDiff, s.diff.z );
     s.spec.x = fmaf( s01.x, wSpec, s.spec.x ); s.spec.y = fmaf( s01.y, wSpec, s.spec.y ); s.spec.z = fmaf( s2i0.x, wSpec, s.spec.z );
     s.indir.x = fmaf( s2i0.y, wBase, s.indir.x ); s.indir.y = fmaf( i12.x, wBase, s.indir.y ); s.indir.z = fmaf( i12.y, wBase, s.indir.z );
@@ -248,7 +291,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
     static_assert( PIX == 2, "two pixels per thread" );
     float4* sA = reinterpret_cast< float4* >( smemRaw );
     uint4*  sB = reinterpret_cast< uint4* >( sA + NPX );
-    uint2*  sC = reinterpret_cast< uint2* >( sB + NPX );
+    AtC*    sC = reinterpret_cast< AtC* >( sB + NPX );
 
     const int band  = blockIdx.y / STEP, res = blockIdx.y - band * STEP;
     const int yBase = u.yBegin + band * ( kAtTileH * STEP ) + res;
@@ -370,7 +413,11 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
                 for( int yy = -1; yy <= 1; yy++ )
 #pragma unroll
                     for( int xx = -1; xx <= 1; xx++ )
+#ifdef ASVGF_AT_HYBRID
+                        r = fmaf( __uint_as_float( sB[ ce + yy * RP + xx * dC ].w ), ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+#else
                         r = fmaf( unpackHalf2( sB[ ce + yy * RP + xx * dC ].y ).y, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+#endif
                 sigmaL = __fsqrt_rn( fmaxf( r, 0.0f ) );
             }
             s.init( cw.A, cw.B, cw.C, cw.D, h2f( cGrad[ k ] ), sigmaL, h2f( cSpecLen[ k ] ), a.iteration );
