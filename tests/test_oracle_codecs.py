@@ -55,6 +55,18 @@ def test_e5_round_trip_random():
         assert np.allclose(layout.decode_e5(np.array([p], dtype=np.uint32))[0], d)
 
 
+def test_every_e5_component_is_exact_in_fp16():
+    """The a-trous kernel keeps specular / indirect colours of the staged tile as fp16 (asvgf_atrous_half.cuh) and the anti-firefly
+    kernel runs its min / max on fp16 planes: both rely on every decoded E5B9G9R9 component m * 2^(e-24) (m < 512, e < 32;
+    Utils.h:194-207) surviving f32 -> f16 -> f32 unchanged, subnormal halves included."""
+    m = np.arange(512, dtype=np.float64)
+    for e in range(32):
+        v = (m * 2.0 ** (e - 24)).astype(np.float32)
+        assert np.array_equal(v.astype(np.float16).astype(np.float32), v), e
+    # ... and so do the tile's depth / roughness words: an r16f depth and a byte 0..255
+    assert np.array_equal(np.arange(256, dtype=np.float32).astype(np.float16).astype(np.float32), np.arange(256, dtype=np.float32))
+
+
 def test_half_conversions_match_ieee():
     allh = np.arange(65536, dtype=np.uint16)
     ref = allh.view(np.float16).astype(np.float32)
