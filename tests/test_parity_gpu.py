@@ -124,10 +124,12 @@ def test_light_switch_produces_gradients():
         p.close()
 
 
-@pytest.mark.parametrize("case", ["antifirefly_off", "gradients_off", "five_iterations", "two_iterations",
+@pytest.mark.parametrize("case", ["antifirefly_off", "gradients_off", "five_iterations", "two_iterations", "eight_iterations",
                                   "debug_white_albedo", "classic_shading_half", "debug_only_specular"])
 def test_parameter_edges(case):
-    N = {"five_iterations": 5, "two_iterations": 2}.get(case, 4)
+    # eight iterations: strides 32, 64 and 128 -- tiles of more than one staged group per thread (the separate sky vote) and
+    # more than 48 KB of shared memory (the per-function opt-in)
+    N = {"five_iterations": 5, "two_iterations": 2, "eight_iterations": 8}.get(case, 4)
     p = Pair(256, 144, iterations=N)
 
     def edit(u):
