@@ -1,4 +1,8 @@
-// asvgf_atrous_pipe.cuh -- the a-trous kernel as a PERSISTENT, ASYNCHRONOUSLY STAGED pipeline (sm_100a).
+// asvgf_atrous_pipe.cuh -- EXPERIMENT, not part of libasvgf.so: the a-trous kernel as a PERSISTENT, ASYNCHRONOUSLY STAGED pipeline
+// (sm_100a).  Parity-green and measured 10-25 % slower than the CTA-per-tile kernel: 4K frame 1.4530 ms against
+// 1.3245 ms; ncu (profile of the four launches): +11 % instructions, warps-active 40 % instead of 50 % (static tile schedule),
+// three CTAs per SM at stride 8.  As measured it was built on the all-half tile (-DASVGF_AT_ALL_HALF: plane C = uint2) and
+// launched from asvgf.cu with grid = min(tiles, SMs x atrousPipeCtasPerSm(step)) and the two extra arguments (tilesX, numTiles).
 //
 // Same filter and the same packed tile as k_atrous_half (asvgf_atrous_half.cuh), identical results.  What changes is when the tile
 // arrives.  ncu of k_atrous_half: the largest stall left is the long scoreboard (3.0-3.5 warps per issue slot, a third of all
