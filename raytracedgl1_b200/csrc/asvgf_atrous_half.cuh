@@ -54,7 +54,7 @@ constexpr size_t atrousHalfSmemBytes( int step )
     const int tw  = kAtTileW + 2 * ( step >= 4 ? atrousHalo( step ) : step );
     const int npx = ( step >= 4 ? 4 * atrousGroupPitch( step ) : tw ) * ( kAtTileH + 2 ), npx8 = ( step >= 4 ? 4 * atrousGroupPitch8( step ) : tw ) * ( kAtTileH + 2 );
 #ifdef ASVGF_AT_HYBRID
-    return ( size_t )npx * 48;
+    return ( size_t )npx * 48 + ( step == 1 ? ( size_t )npx * 4 : 0 ); // iteration 0 keeps the variances once more as a compact plane
 #else
     return ( size_t )npx * 32 + ( size_t )npx8 * 8;
 #endif
@@ -104,7 +104,7 @@ ASVGF_DEVICE void atrousPackTexel( const float4 ga, const uint32_t d0, const uin
 template< int STEP > constexpr bool atrousFusedVote() { return !AtrousGeom< STEP >::VEC || AtrousGeom< STEP >::GROUPS * AtrousGeom< STEP >::TROWS <= kAtThreads; }
 
 template< int STEP, bool UNI, bool INTERIOR, bool VOTE >
-ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, AtC* sC )
+ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, AtC* sC, float* sV )
 {
     using G = AtrousGeomH< STEP >;
     constexpr bool FUSED = VOTE && atrousFusedVote< STEP >();
@@ -204,22 +204,25 @@ ASVGF_DEVICE bool atrousStageHalfImpl( const AtrousArgs& a, const Uniform& u, co
             float4 pA; uint4 pB; AtC pC;
             atrousPackTexel( ga[ it ], dd[ it ].x, dd[ it ].y, ss[ it ], ii[ it ], pA, pB, pC );
             sA[ e ] = pA; sB[ e ] = pB; sC[ e ] = pC;
+#ifdef ASVGF_AT_HYBRID
+            if constexpr( STEP == 1 ) sV[ e ] = __uint_as_float( pB.w ); // the 3x3 variance filter of iteration 0 reads these: 4-byte stride, conflict-free
+#endif
         }
     }
     return true;
 }
 
 template< int STEP, bool VOTE >
-ASVGF_DEVICE bool atrousStageHalf( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, AtC* sC )
+ASVGF_DEVICE bool atrousStageHalf( const AtrousArgs& a, const Uniform& u, const Rows& rows, int xBase, int yBase, float4* sA, uint4* sB, AtC* sC, float* sV )
 {
     using G = AtrousGeom< STEP >;
     const bool interior = xBase - G::HALO >= 0 && xBase + kAtTileW + G::HALO <= u.W && yBase - STEP >= rows.y0 && yBase + kAtTileH * STEP < rows.y1;
     if( a.uniformPitch )
     {
-        if( interior ) return atrousStageHalfImpl< STEP, true, true, VOTE >( a, u, rows, xBase, yBase, sA, sB, sC );
-        return atrousStageHalfImpl< STEP, true, false, VOTE >( a, u, rows, xBase, yBase, sA, sB, sC );
+        if( interior ) return atrousStageHalfImpl< STEP, true, true, VOTE >( a, u, rows, xBase, yBase, sA, sB, sC, sV );
+        return atrousStageHalfImpl< STEP, true, false, VOTE >( a, u, rows, xBase, yBase, sA, sB, sC, sV );
     }
-    return atrousStageHalfImpl< STEP, false, false, VOTE >( a, u, rows, xBase, yBase, sA, sB, sC );
+    return atrousStageHalfImpl< STEP, false, false, VOTE >( a, u, rows, xBase, yBase, sA, sB, sC, sV );
 }
 
 // the packed texel, widened: what AtrousPix::init / initFromCentre / finish take for the centre
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
     float4* sA = reinterpret_cast< float4* >( smemRaw );
     uint4*  sB = reinterpret_cast< uint4* >( sA + NPX );
     AtC*    sC = reinterpret_cast< AtC* >( sB + NPX );
+    float*  sV = reinterpret_cast< float* >( sC + G::NPX8 ); // iteration 0 only (atrousHalfSmemBytes)
 
     const int band  = blockIdx.y / STEP, res = blockIdx.y - band * STEP;
     const int yBase = u.yBegin + band * ( kAtTileH * STEP ) + res;
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
             }
         }
     }
-    if( !atrousStageHalf< STEP, FUSED_VOTE >( a, u, rows, xBase, yBase, sA, sB, sC ) ) { skyTile(); return; } // (the vote: uniform per CTA)
+    if( !atrousStageHalf< STEP, FUSED_VOTE >( a, u, rows, xBase, yBase, sA, sB, sC, sV ) ) { skyTile(); return; } // (the vote: uniform per CTA)
     __syncthreads();
 
     const int   sep  = u.W / 2;
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
 #pragma unroll
                     for( int xx = -1; xx <= 1; xx++ )
 #ifdef ASVGF_AT_HYBRID
-                        r = fmaf( __uint_as_float( sB[ ce + yy * RP + xx * dC ].w ), ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
+                        r = fmaf( sV[ ce + yy * RP + xx * dC ], ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r ); // (plane B's .w at a 16-byte stride: 4-way conflicts)
 #else
                         r = fmaf( unpackHalf2( sB[ ce + yy * RP + xx * dC ].y ).y, ( xx == 0 ? 0.5f : 0.25f ) * ( yy == 0 ? 0.5f : 0.25f ), r );
 #endif
