@@ -16,6 +16,15 @@
 
 #include <nvtx3/nvToolsExt.h> // header-only in CUDA 12: ranges are no-ops unless a profiler is attached
 
+// tests/hostsim compiles this file with g++ -DASVGF_HOSTSIM against a stub of the CUDA runtime, so that the CPU test suite can
+// drive the library's host logic and the kernels' source without a GPU (test infrastructure: tests/hostsim/README.md; the
+// product is built by nvcc, where the macro is never defined and a launch is a launch)
+#ifndef ASVGF_HOSTSIM
+    #define ASVGF_LAUNCH( kernel, grid, block, smem, stream, ... ) kernel<<< grid, block, smem, stream >>>( __VA_ARGS__ )
+#else
+    #define ASVGF_LAUNCH( kernel, grid, block, smem, stream, ... ) ( ( void )( stream ), hostsim::launch( kernel, grid, block, smem, __VA_ARGS__ ) )
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -274,6 +283,7 @@ AsvgfResult launchCheck( AsvgfDenoiser_T& d, const char* name )
 template< typename... KArgs, typename... Args >
 void launchK( AsvgfDenoiser_T& d, void ( *kernel )( KArgs... ), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Args&... args )
 {
+#ifndef ASVGF_HOSTSIM
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[ 1 ];
@@ -281,6 +291,10 @@ void launchK( AsvgfDenoiser_T& d, void ( *kernel )( KArgs... ), dim3 grid, dim3 
     attr[ 0 ].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = ( d.pdlChain && d.pdlArmed ) ? 1u : 0u;
     ( void )cudaLaunchKernelEx( &cfg, kernel, args... ); // the error is picked up by launchCheck
+#else
+    ( void )s;
+    hostsim::launch( kernel, grid, block, smem, args... );
+#endif
     d.pdlArmed = d.pdlChain;
 }
 
@@ -515,7 +529,7 @@ AsvgfResult runResolveCheckerboard( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t
     a.src[ 1 ] = d.get( ASVGF_IMAGE_SCREEN_EMIS_RT, fi ); a.dst[ 1 ] = d.get( ASVGF_IMAGE_SCREEN_EMISSION, fi );
     a.src[ 2 ] = d.get( ASVGF_IMAGE_ACID_FOG_RT, fi ); a.dst[ 2 ] = d.get( ASVGF_IMAGE_ACID_FOG, fi );
     a.pairs = ( a.src[ 1 ].p && a.dst[ 1 ].p && a.src[ 2 ].p && a.dst[ 2 ].p ) ? 3 : 1;
-    k_checkerboard_resolve<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LAUNCH( k_checkerboard_resolve, gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s, a, u );
     return launchCheck( d, "k_checkerboard_resolve" );
 }
 
@@ -536,7 +550,7 @@ AsvgfResult runPrepareFinal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, co
         if( e != cudaSuccess ) return cudaFail( e, "cudaMalloc(final-prepare scalars)" );
     }
     a.scalars = d.finalScalars;
-    k_prepare_final_scalars<<< 1, 1, 0, s >>>( d.tm, g.bloomEmissionMultiplier, g.luminanceWhitePoint, d.finalScalars );
+    ASVGF_LAUNCH( k_prepare_final_scalars, dim3( 1 ), dim3( 1 ), 0, s, d.tm, g.bloomEmissionMultiplier, g.luminanceWhitePoint, d.finalScalars );
     {
         AsvgfResult r = launchCheck( d, "k_prepare_final_scalars" );
         if( r != ASVGF_SUCCESS ) return r;
@@ -550,7 +564,7 @@ AsvgfResult runPrepareFinal( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, co
     a.bloomThreshold = g.bloomThreshold; a.bloomEmissionMultiplier = g.bloomEmissionMultiplier;
     a.classicEdge = g.lightmapScreenCoverage * g.renderWidth;
     a.debugShowFlags = g.debugShowFlags;
-    k_prepare_final<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LAUNCH( k_prepare_final, gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s, a, u );
     return launchCheck( d, "k_prepare_final" );
 }
 
@@ -578,14 +592,14 @@ AsvgfResult runScatterAccumulate( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t f
         }
         if( std::memcmp( &density, &d.transmittanceDensity, sizeof( float ) ) != 0 ) // rebuilt only when the density changes
         {
-            k_scatter_transmittance_table<<< 256, 256, 0, s >>>( d.transmittance, density );
+            ASVGF_LAUNCH( k_scatter_transmittance_table, dim3( 256 ), dim3( 256 ), 0, s, d.transmittance, density );
             AsvgfResult r = launchCheck( d, "k_scatter_transmittance_table" );
             if( r != ASVGF_SUCCESS ) return r;
             d.transmittanceDensity = density;
         }
     }
     for( int i = 0; i < 3; i++ ) a.volumeAmbient[ i ] = g.volumeAmbient[ i ];
-    k_scatter_accum<<< gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s >>>( a, u );
+    ASVGF_LAUNCH( k_scatter_accum, gridFor( ( int )d.W, u.yEnd - u.yBegin ), kBlock, 0, s, a, u );
     return launchCheck( d, "k_scatter_accum" );
 }
 
@@ -605,7 +619,7 @@ AsvgfResult runLuminanceHistogram( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t 
     NEED( ASVGF_IMAGE_HISTOGRAM_INPUT );
     const NvtxRange range( "Exposure" );
     const LumArgs a = lumArgs( d, fi, g );
-    k_lum_bin_table<<< 256, 256, 0, s >>>( a );
+    ASVGF_LAUNCH( k_lum_bin_table, dim3( 256 ), dim3( 256 ), 0, s, a );
     AsvgfResult r = launchCheck( d, "k_lum_bin_table" );
     if( r != ASVGF_SUCCESS ) return r;
     const size_t smem   = 65536 + ( kLumThreads / 32 ) * 256 * sizeof( uint32_t );
@@ -615,14 +629,14 @@ AsvgfResult runLuminanceHistogram( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t 
     if( ctas < 1 ) ctas = 1;
     cudaError_t e = cudaFuncSetAttribute( k_lum_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, ( int )smem );
     if( e != cudaSuccess ) return cudaFail( e, "cudaFuncSetAttribute(k_lum_histogram)" );
-    k_lum_histogram<<< ( unsigned )ctas, kLumThreads, smem, s >>>( a, u );
+    ASVGF_LAUNCH( k_lum_histogram, dim3( ( unsigned )ctas ), dim3( kLumThreads ), smem, s, a, u );
     return launchCheck( d, "k_lum_histogram" );
 }
 
 AsvgfResult runLuminanceAverage( AsvgfDenoiser_T& d, cudaStream_t s, uint32_t fi, const AsvgfGlobalUniform& g )
 {
     const LumArgs a = lumArgs( d, fi, g );
-    k_lum_average<<< 1, 256, 0, s >>>( a );
+    ASVGF_LAUNCH( k_lum_average, dim3( 1 ), dim3( 256 ), 0, s, a );
     return launchCheck( d, "k_lum_average" );
 }
 

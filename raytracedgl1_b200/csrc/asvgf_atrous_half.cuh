@@ -66,7 +66,14 @@ ASVGF_DEVICE uint32_t packHalf2( float lo, float hi )
     return *reinterpret_cast< const uint32_t* >( &h );
 }
 ASVGF_DEVICE float2 unpackHalf2( uint32_t v ) { return __half22float2( *reinterpret_cast< const __half2* >( &v ) ); }
+// hint only: the composition / centre texels of a pixel are requested before the tile is staged
+#ifndef ASVGF_HOSTSIM
+ASVGF_DEVICE void prefetchL1( const void* p ) { asm volatile( "prefetch.global.L1 [%0];" ::"l"( p ) ); }
+#else
+ASVGF_DEVICE void prefetchL1( const void* ) {}
+#endif
 // f32 = half - f32 in one instruction (FHADD): exact widening inside the add
+#ifndef ASVGF_HOSTSIM
 ASVGF_DEVICE float halfLoMinus( uint32_t v, float f )
 {
     float r;
@@ -79,6 +86,10 @@ ASVGF_DEVICE float halfHiMinus( uint32_t v, float f )
     asm( "{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; sub.rn.f32.f16 %0, hi, %2; }" : "=f"( r ) : "r"( v ), "f"( f ) );
     return r;
 }
+#else // tests/hostsim (host compile of this file by the CPU test suite): the same exactly rounded operation, spelled in C
+ASVGF_DEVICE float halfLoMinus( uint32_t v, float f ) { return __fsub_rn( unpackHalf2( v ).x, f ); }
+ASVGF_DEVICE float halfHiMinus( uint32_t v, float f ) { return __fsub_rn( unpackHalf2( v ).y, f ); }
+#endif
 
 // one staged texel -> the three planes
 ASVGF_DEVICE void atrousPackTexel( const float4 ga, const uint32_t d0, const uint32_t d1, const uint32_t encSpec, const uint32_t encIndir, float4& pA, uint4& pB, AtC& pC )
@@ -268,7 +279,11 @@ ASVGF_DEVICE void atrousTapHalf( AtrousPix& s, const float4 qA, const uint4 qB, 
     const float wBase = fex2( eBase );
     const float wDiff = fex2( eDiff );
     float       rfac;
+#ifndef ASVGF_HOSTSIM
     asm( "fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"( rfac ) : "f"( fabsf( halfHiMinus( dr, s.roughByte ) ) ), "f"( -s.wR10 ), "f"( s.wRough ) );
+#else
+    rfac = fminf( fmaxf( fmaf( fabsf( halfHiMinus( dr, s.roughByte ) ), -s.wR10, s.wRough ), 0.0f ), 1.0f ); // (.sat: NaN -> 0, as fmaxf gives)
+#endif
     const float wSpec = rfac * fex2( fmaf( s.P, L, eBase ) );
 #ifdef ASVGF_AT_HYBRID
     const float2 rg = make_float2( __uint_as_float( qB.x ), __uint_as_float( qB.y ) ), bv = make_float2( __uint_as_float( qB.z ), __uint_as_float( qB.w ) );
@@ -287,7 +302,11 @@ template< int STEP, bool ITER0, bool LAST, bool CENTRE >
 __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half( const __grid_constant__ AtrousArgs a, const __grid_constant__ Uniform u )
 {
     pdlLaunchDependents();
+#ifndef ASVGF_HOSTSIM
     extern __shared__ __align__( 128 ) uint8_t smemRaw[];
+#else
+    uint8_t* const smemRaw = hostsim::dynamicSmem(); // tests/hostsim: the launcher's per-grid allocation
+#endif
     using G = AtrousGeomH< STEP >;
     constexpr int RP = G::RP, RP8 = G::RP8, NPX = G::NPX, HALO = G::HALO;
     constexpr int PIX = ( kAtTileW * kAtTileH ) / kAtThreads; // 2
@@ -351,7 +370,7 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
         for( int k = 0; k < PIX; k++ )
         {
             const int py = yBase + jOf( k ) * STEP;
-            if( px < u.W && py < u.yEnd ) asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< float4 >( a.centre, px, py ) ) );
+            if( px < u.W && py < u.yEnd ) prefetchL1( at< float4 >( a.centre, px, py ) );
         }
     }
     else
@@ -375,10 +394,10 @@ __global__ void __launch_bounds__( kAtThreads, ASVGF_AT_MIN_CTAS ) k_atrous_half
             if( px < u.W && py < u.yEnd )
             {
                 const int sepx = u.W / 2, isOdd = px >= sepx ? 1 : 0, regX = ( px - isOdd * sepx ) * 2 + ( ( isOdd + py ) & 1 );
-                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint32_t >( a.albedo, regX, py ) ) );
-                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint2 >( a.throughput, px, py ) ) );
-                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint16_t >( a.metRough, px, py ) ) );
-                asm volatile( "prefetch.global.L1 [%0];" ::"l"( at< uint8_t >( a.isSky, px, py ) ) );
+                prefetchL1( at< uint32_t >( a.albedo, regX, py ) );
+                prefetchL1( at< uint2 >( a.throughput, px, py ) );
+                prefetchL1( at< uint16_t >( a.metRough, px, py ) );
+                prefetchL1( at< uint8_t >( a.isSky, px, py ) );
             }
         }
     }

@@ -72,8 +72,13 @@ struct NormalLut // (sin, cos) of phi_j = j*pi/65535 and theta_k = k*2*pi/65536,
 // (launch latency, argument fetch and index arithmetic overlap the tail) and block in pdlWait() until pass k has completed and
 // flushed.  Nothing written by an earlier pass of the frame is touched before pdlWait(); without the launch attribute both
 // instructions do nothing. ----
+#ifndef ASVGF_HOSTSIM
 ASVGF_DEVICE void pdlLaunchDependents() { asm volatile( "griddepcontrol.launch_dependents;" ); }
 ASVGF_DEVICE void pdlWait() { asm volatile( "griddepcontrol.wait;" ::: "memory" ); }
+#else // tests/hostsim (kernel source compiled for the host by the CPU test suite): grids run one after the other
+ASVGF_DEVICE void pdlLaunchDependents() {}
+ASVGF_DEVICE void pdlWait() {}
+#endif
 
 // ---- exactly rounded arithmetic (never fused) ----
 ASVGF_DEVICE float mulr( float a, float b ) { return __fmul_rn( a, b ); }

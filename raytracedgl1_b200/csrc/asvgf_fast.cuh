@@ -26,11 +26,19 @@ namespace asvgf
 // ------------------------------------------------------------------------------------------------------------
 // fast scalar helpers (colour math only)
 // ------------------------------------------------------------------------------------------------------------
+#ifndef ASVGF_HOSTSIM
 ASVGF_DEVICE float fex2( float x ) { float r; asm( "ex2.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
 ASVGF_DEVICE float flg2( float x ) { float r; asm( "lg2.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
 ASVGF_DEVICE float frcp( float x ) { float r; asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
 ASVGF_DEVICE float frsqrt( float x ) { float r; asm( "rsqrt.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
 ASVGF_DEVICE float fsqrt( float x ) { float r; asm( "sqrt.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r; }
+#else // tests/hostsim compiles this file for the host (test infrastructure, never the product): the MUFU approximations are libm calls there
+ASVGF_DEVICE float fex2( float x ) { return exp2f( x ); }
+ASVGF_DEVICE float flg2( float x ) { return log2f( x ); }
+ASVGF_DEVICE float frcp( float x ) { return 1.0f / x; }
+ASVGF_DEVICE float frsqrt( float x ) { return 1.0f / sqrtf( x ); }
+ASVGF_DEVICE float fsqrt( float x ) { return sqrtf( x ); }
+#endif
 ASVGF_DEVICE float fdiv( float a, float b ) { return a * frcp( b ); }
 // GLSL pow(x,y) for x >= 0, y > 0: exp2(y*log2(x)); pow(0,y) = 0
 ASVGF_DEVICE float fpow( float x, float y ) { return fex2( y * flg2( x ) ); }

@@ -92,13 +92,18 @@ constexpr int kLumThreads = 256;
 
 __global__ void __launch_bounds__( kLumThreads ) k_lum_histogram( const __grid_constant__ LumArgs a, const __grid_constant__ Uniform u )
 {
+#ifndef ASVGF_HOSTSIM
     extern __shared__ __align__( 16 ) uint8_t lumSmem[];
+#else
+    uint8_t* const lumSmem = hostsim::dynamicSmem();
+#endif
     uint8_t*  sTable = lumSmem;                                            // 64 KB
     uint32_t* sHist  = reinterpret_cast< uint32_t* >( lumSmem + 65536 );   // one 256-bin histogram per warp
     constexpr int WARPS = kLumThreads / 32;
     // the 64 KB bin table comes in as ONE bulk asynchronous copy (TMA, cp.async.bulk: no registers, no per-thread loads --
     // ncu of the per-thread copy: the kernel spent most of its 35 us filling this table) signalled through an mbarrier,
     // while the threads zero the per-warp histograms
+#ifndef ASVGF_HOSTSIM
     __shared__ __align__( 8 ) uint64_t tableBarrier;
     const uint32_t barAddr = ( uint32_t )__cvta_generic_to_shared( &tableBarrier ), dstAddr = ( uint32_t )__cvta_generic_to_shared( sTable );
     if( threadIdx.x == 0 )
@@ -109,16 +114,22 @@ __global__ void __launch_bounds__( kLumThreads ) k_lum_histogram( const __grid_c
         asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"( dstAddr ), "l"( a.binTable ), "r"( 65536u ), "r"( barAddr )
                       : "memory" );
     }
+#else // tests/hostsim (host compile of this file by the CPU test suite): the bulk copy is a memcpy
+    if( threadIdx.x == 0 ) memcpy( sTable, a.binTable, 65536 );
+#endif
     for( int i = threadIdx.x; i < WARPS * 256; i += kLumThreads ) sHist[ i ] = 0u;
     __syncthreads(); // the barrier word is initialised and the histograms are zero
+#ifndef ASVGF_HOSTSIM
     {
         uint32_t done = 0;
         while( !done )
             asm volatile( "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"( done ) : "r"( barAddr ) : "memory" );
     }
+#endif
 
     uint32_t* myHist = sHist + ( threadIdx.x >> 5 ) * 256;
     auto count = [ & ]( uint32_t bin, bool valid ) {
+#ifndef ASVGF_HOSTSIM
         // lanes with the same bin elect one of them to add their number: no same-address serialisation on flat images
         const uint32_t active = __ballot_sync( 0xffffffffu, valid );
         if( valid )
@@ -126,6 +137,9 @@ __global__ void __launch_bounds__( kLumThreads ) k_lum_histogram( const __grid_c
             const uint32_t peers = __match_any_sync( active, bin );
             if( ( threadIdx.x & 31 ) == ( uint32_t )( __ffs( peers ) - 1 ) ) atomicAdd( myHist + bin, ( uint32_t )__popc( peers ) );
         }
+#else // (no warps on the host: every thread adds its own count)
+        if( valid ) atomicAdd( myHist + bin, 1u );
+#endif
     };
 
     // rows of 8-texel groups (one uint4 per lane), dealt to the CTAs round-robin

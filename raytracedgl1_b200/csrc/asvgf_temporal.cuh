@@ -156,7 +156,9 @@ __global__ void __launch_bounds__( kBlockW* kTBlockH, ASVGF_T_MIN_CTAS ) k_tempo
     const uint32_t nv32 = __ldg( atOff< UNIFORM, uint32_t >( a.normal, o, px, py ) );
     const uint16_t mr   = __ldg( atOff< UNIFORM, uint16_t >( a.metRough, o, px, py ) );
     const float4   sp4  = __ldg( atOff< UNIFORM, float4 >( a.surfPos, o, px, py ) );
-    const uint32_t gr   = __ldg( at< uint32_t >( a.disPing, px / 3, py / 3 ) );
+    // the gradient image has (W+1)/3 x (H+1)/3 texels (Framebuffers.cpp:691-699): where W % 3 == 1 or H % 3 == 1 the last pixel column /
+    // row maps to a stratum beyond it, and the fetch returns 0 like every other fetch outside an image (CmSVGFTemporalAccumulation.comp:185)
+    const uint32_t gr   = ldIf< uint32_t >( a.disPing, px / 3, py / 3, px / 3 < a.disPing.w && py / 3 < a.disPing.h, 0u );
 
     const float2 mot01   = __half22float2( *reinterpret_cast< const __half2* >( &mv.x ) );
     const float  motionZ = __low2float( *reinterpret_cast< const __half2* >( &mv.y ) );

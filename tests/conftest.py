@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if os.environ.get("ASVGF_TEST_HOSTSIM") == "1":
+        # tests/test_hostsim.py re-runs a selection of the `-m gpu` tests in a child pytest against tests/hostsim/libasvgf_hostsim.so:
+        # the library's own source compiled for the host (test infrastructure, tests/hostsim/README.md).  Only a test process
+        # that sets this variable ever sees that file; raytracedgl1_b200 itself knows nothing about it.
+        import hostsim
+        from raytracedgl1_b200 import denoiser
+        denoiser._LIB_PATH = hostsim.build()
 
 
 @pytest.fixture(scope="session", autouse=True)
