@@ -459,7 +459,8 @@ __global__ void __launch_bounds__( kBlockW* kBlockH ) k_prepare_final( const __g
         else if( f & ( 1u << 8 ) ) { /* light grid: rejected by the host (not on this path) */ }
         else if( f & ( 1u << 1 ) )
         {
-            const uint32_t g = __ldg( at< uint32_t >( a.disPing, cbx / 3, y / 3 ) );
+            // (the stratum of the last pixel row / column lies outside the (W+1)/3 x (H+1)/3 gradient image where W % 3 == 1 or H % 3 == 1: 0)
+            const uint32_t g = ( cbx / 3 < a.disPing.w && y / 3 < a.disPing.h ) ? __ldg( at< uint32_t >( a.disPing, cbx / 3, y / 3 ) ) : 0u;
             color = make_float3( unorm8ToFloatFast( g & 0xffu ), unorm8ToFloatFast( ( g >> 8 ) & 0xffu ), unorm8ToFloatFast( ( g >> 16 ) & 0xffu ) );
         }
         else if( f & ( 1u << 10 ) )

@@ -59,6 +59,14 @@ struct BlockBarrier
         cv.wait( lock, [ & ] { return gen != g; } );
         return result;
     }
+    template< typename F > bool arriveLast( F hook ) // the last thread to arrive runs `hook` before anyone continues
+    {
+        std::unique_lock< std::mutex > lock( m );
+        if( ++waiting == live ) { hook(); release(); return true; }
+        const unsigned g = gen;
+        cv.wait( lock, [ & ] { return gen != g; } );
+        return false;
+    }
     void leave()
     {
         std::unique_lock< std::mutex > lock( m );
@@ -107,19 +115,28 @@ void launch( void ( *kernel )( KArgs... ), dim3 grid, dim3 block, size_t smemByt
                     }
                     threaded = true; // (what the block's first threads wrote before the barrier is written again below)
                 }
-                BlockBarrier bar;
-                bar.live = ( int )nThreads;
+                // threaded mode, from this block to the end of the grid: one host thread per CUDA thread, created once; the
+                // blocks still run one after the other (an all-thread barrier between them: static "shared memory")
+                const unsigned first = ( bz * grid.y + by ) * grid.x + bx, nBlocks = grid.x * grid.y * grid.z;
+                BlockBarrier   bar, between;
+                bar.live = between.live = ( int )nThreads;
                 std::vector< std::thread > pool;
                 pool.reserve( nThreads );
                 for( unsigned t = 0; t < nThreads; t++ )
                     pool.emplace_back( [ &, t ] {
-                        setIdx( t, b );
                         tBarrier = &bar;
-                        kernel( args... );
-                        bar.leave();
+                        for( unsigned k = first; k < nBlocks; k++ )
+                        {
+                            setIdx( t, uint3{ k % grid.x, ( k / grid.x ) % grid.y, k / ( grid.x * grid.y ) } );
+                            kernel( args... );
+                            bar.leave();
+                            between.arriveLast( [ & ] { bar.live = ( int )nThreads; bar.waiting = 0; bar.acc = 0; } ); // next block
+                        }
                     } );
                 for( auto& th : pool ) th.join();
+                goto done;
             }
+done:
     gDynamicSmem = nullptr;
     free( smem );
 }

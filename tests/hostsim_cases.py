@@ -1,0 +1,60 @@
+"""Cases that only make sense against tests/hostsim/libasvgf_hostsim.so (the library's source compiled for the host): sizes small
+enough for one host thread per CUDA thread.  Not collected by the normal runs (the file name does not match test_*.py);
+tests/test_hostsim.py passes it to a child pytest that has ASVGF_TEST_HOSTSIM=1 set (tests/conftest.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from _harness import Pair, assert_all_ok
+from test_bandset_gpu import _run as run_band_set
+from test_parity_gpu import OUTPUTS_PER_PASS
+
+pytestmark = pytest.mark.skipif(os.environ.get("ASVGF_TEST_HOSTSIM") != "1", reason="host-compiled library only")
+
+
+def test_the_library_under_test_is_the_host_build():
+    from raytracedgl1_b200 import denoiser
+    assert denoiser._LIB_PATH.endswith("libasvgf_hostsim.so")
+
+
+@pytest.mark.parametrize("size", [(130, 49), (64, 66)])
+def test_per_pass_parity_from_identical_state(size):
+    """Every dispatch of the chain from the oracle's state (as tests/test_parity_gpu.py does at 320x180 ... 1280x720 on the GPU): the
+    outputs of that pass within the single-pass tolerance, the integer images bit-exact."""
+    W, H = size
+    p = Pair(W, H)
+    try:
+        for frame in range(3):
+            fi = frame & 1
+            u = p.feed_inputs(frame, fi)
+            for pas in range(12):
+                p.sync_state_to_cuda()
+                p.oracle.run_pass(pas, fi, u)
+                p.cuda.denoise_pass(pas, fi, u)
+                p.cuda.synchronize()
+                res = p.compare(fi, OUTPUTS_PER_PASS[pas], whole_frame=False)
+                assert_all_ok(res, "%dx%d frame %d pass %d" % (W, H, frame, pas))
+                if pas in (0, 1, 2, 3, 4):      # the gradient chain is integer work end to end
+                    for name in OUTPUTS_PER_PASS[pas]:
+                        assert res[name]["exact_frac"] == 1.0, (name, res[name])
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("bands,boundaries,size", [(2, None, (64, 138)), (3, [0, 66, 135, 201], (34, 201)), (1, None, (34, 40))])
+def test_band_set_is_bit_identical_to_the_single_handle(bands, boundaries, size):
+    """asvgfBandSet* (apron schedule, the four push points, per-band OpenMP enqueue) with the bands on different pretend devices."""
+    run_band_set(size[0], size[1], list(range(bands)), boundaries, frames=4)
+
+
+def test_motion_beyond_the_halo_is_reported():
+    from raytracedgl1_b200 import denoiser as dn
+    W, H = 34, 240
+
+    def fast_motion(frame, g):
+        g["Motion"][..., 1] = np.float16(100.0 / H)
+
+    with pytest.raises(dn.AsvgfError) as e:
+        run_band_set(W, H, [0, 1], None, frames=2, mutate=fast_motion)
+    assert e.value.code == dn.HALO_EXCEEDED
