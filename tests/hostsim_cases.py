@@ -48,6 +48,48 @@ def test_band_set_is_bit_identical_to_the_single_handle(bands, boundaries, size)
     run_band_set(size[0], size[1], list(range(bands)), boundaries, frames=4)
 
 
+def run_tight_external(W, H, iterations=4, extra=0):
+    """Every image caller-owned (asvgfBindExternalImage) with a TIGHT row pitch -- row bytes rounded up to 16, plus `extra` x 16..48
+    bytes that differ from image to image -- instead of the library's align256(width) texels: what a Vulkan host's linear images
+    look like.  The images then hold different numbers of texels per row, which selects the UNIFORM = false forms of the temporal
+    and a-trous kernels (one offset per image instead of one shared texel offset).  Bit-identical to the owned-image handle."""
+    import ctypes
+    import synth
+    from raytracedgl1_b200 import denoiser as dn, layout
+    own = dn.Denoiser(W, H, iterations, flags=dn.CREATE_EXPORT_DEBUG_MASK)
+    ext = dn.Denoiser(W, H, iterations, flags=dn.CREATE_EXTERNAL_IMAGES | dn.CREATE_EXPORT_DEBUG_MASK)
+    keep = {}
+    try:
+        for name in layout.IMAGES:
+            idx = layout.INDEX[name]
+            f, w, h, b = [ctypes.c_uint32() for _ in range(4)]
+            assert dn.lib().asvgfGetImageInfo(idx, W, H, ctypes.byref(f), ctypes.byref(w), ctypes.byref(h), ctypes.byref(b)) == 0
+            pitch = ((w.value * b.value + 15) // 16) * 16 + 16 * extra * (1 + idx % 3)
+            buf = np.zeros(pitch * h.value + 16, dtype=np.uint8)     # (under the host build "device memory" is the heap)
+            keep[name] = buf
+            ext.bind_external(name, buf.ctypes.data + (-buf.ctypes.data) % 16, pitch)
+        for frame in range(3):
+            fi = frame & 1
+            g, u = synth.generate(W, H, frame), synth.uniform(W, H, frame)
+            for d in (own, ext):
+                for name, arr in g.items():
+                    d.upload(name, fi, arr)
+                d.gradient_samples(fi, u)
+                d.denoise(fi, u)
+                d.synchronize()
+            for name in layout.IMAGES:
+                a, b = own.download(name, fi), ext.download(name, fi)
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (W, H, frame, name)
+    finally:
+        own.close()
+        ext.close()
+
+
+@pytest.mark.parametrize("size,extra", [((34, 10), 0), ((66, 35), 1), ((130, 49), 1)])
+def test_tight_and_unequal_external_pitches(size, extra):
+    run_tight_external(size[0], size[1], extra=extra)
+
+
 def test_motion_beyond_the_halo_is_reported():
     from raytracedgl1_b200 import denoiser as dn
     W, H = 34, 240

@@ -78,26 +78,30 @@ for (W, H, N) in [(34, 10, 4), (66, 35, 5), (130, 49, 4), (4, 3, 2)]:
     p.close()
 from test_bandset_gpu import _run
 _run(34, 201, [0, 1, 2], [0, 66, 135, 201], frames=3)
+from hostsim_cases import run_tight_external
+run_tight_external(34, 10)
+run_tight_external(62, 31, extra=1)
 print("memcheck sweep done")
 """
 
 
 def test_kernel_addressing_under_address_sanitizer(tmp_path):
-    """The same source built with -fsanitize=address: every image is its own heap block, so a kernel that reads or writes one
-    row past an image (the class of bug compute-sanitizer memcheck finds on the GPU) aborts here with the source line."""
+    """The same source built with -fsanitize=address,alignment: every image is its own heap block, so a kernel that reads or writes
+    one row past an image (the class of bug compute-sanitizer memcheck finds on the GPU) aborts here with the source line, and so
+    does a vector access (uint2 / uint4 / float4: the host headers give them the GPU's alignment) at a misaligned address."""
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
     libasan = subprocess.run([gxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not libasan or not os.path.isabs(libasan) or not os.path.exists(libasan):
         pytest.skip("no libasan for " + gxx)
     lib = str(tmp_path / "libasvgf_hostsim_asan.so")
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    subprocess.run([gxx, "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off",
+    subprocess.run([gxx, "-O1", "-g", "-fsanitize=address,alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off",
                     "-fno-fast-math", "-DASVGF_HOSTSIM", "-Wno-unknown-pragmas", "-I" + HS, "-I" + cuda + "/include", "-shared", "-o", lib,
                     "-include", "cuda_host_shim.h", "-x", "c++", os.path.join(ROOT, "raytracedgl1_b200", "csrc", "asvgf.cu"),
                     "-x", "c++", os.path.join(HS, "cuda_runtime_stub.cpp"), "-ldl", "-lpthread"], check=True, cwd=HS)
-    env = _child_env(LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1")
+    env = _child_env(LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
     r = subprocess.run([sys.executable, "-c", ASAN_DRIVER % dict(root=ROOT, lib=lib)], cwd=ROOT, env=env, capture_output=True, text=True,
                        timeout=1500)
     out = r.stdout + r.stderr
-    assert "AddressSanitizer" not in out, out[-4000:]
+    assert "AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
     assert r.returncode == 0 and "memcheck sweep done" in out, out[-3000:]
