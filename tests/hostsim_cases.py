@@ -100,3 +100,75 @@ def test_motion_beyond_the_halo_is_reported():
     with pytest.raises(dn.AsvgfError) as e:
         run_band_set(W, H, [0, 1], None, frames=2, mutate=fast_motion)
     assert e.value.code == dn.HALO_EXCEEDED
+
+
+def _edit(case):
+    def general_projection(u):       # entries outside m0, m5, m8..m11, m14: the full mat4 products of the virtual-point reprojection
+        u.projection[1], u.projection[4], u.projection[12], u.projection[13] = 0.02, -0.015, 0.03, -0.01
+        u.projectionPrev[1], u.projectionPrev[4], u.projectionPrev[12], u.projectionPrev[13] = 0.021, -0.014, 0.031, -0.012
+
+    def time_delta_zero(u):
+        u.timeDelta = 0.0
+
+    def time_delta_negative(u):
+        u.timeDelta = -1.0
+
+    def time_delta_large(u):
+        u.timeDelta = 10.0
+
+    def coverage_one(u):
+        u.lightmapScreenCoverage = 1.0
+
+    def gradient_multipliers(u):
+        u.gradientMultDiffuse, u.gradientMultIndirect, u.gradientMultSpecular = 5.0, 0.0, 100.0
+
+    def camera_jump(u):
+        for i in range(3):
+            u.cameraPositionPrev[i] = u.cameraPosition[i] + 1000.0
+
+    def all_debug_flags(u):
+        u.debugShowFlags = 0xffffffff & ~(1 << 8)
+    return locals()[case]
+
+
+@pytest.mark.parametrize("case", ["general_projection", "time_delta_zero", "time_delta_negative", "time_delta_large", "coverage_one",
+                                  "gradient_multipliers", "camera_jump", "all_debug_flags"])
+def test_uniform_edges(case):
+    """Uniform values no GPU test sets (the general-projection branch of the temporal pass among them): whole frames against the oracle."""
+    p = Pair(66, 35)
+    try:
+        for frame in range(3 if case == "general_projection" else 2):
+            fi, u = p.run_frame(frame, uniform_edit=_edit(case))
+            res = p.compare(fi)
+            assert_all_ok(res, "%s frame %d" % (case, frame))
+            if case == "general_projection" and frame:
+                assert int(((p.oracle.image("DebugMask", fi) >> 5) & 1).sum()) > 500     # the virtual-point branch is taken
+            p.sync_state_to_cuda()
+    finally:
+        p.close()
+
+
+def test_call_orders():
+    """asvgfDenoise without asvgfGradientSamples (the host may keep its own gradient-sample pass), and
+    asvgfResetHistory in the middle of a sequence."""
+    p = Pair(66, 35)
+    try:
+        for frame in range(3):
+            fi = frame & 1
+            u = p.feed_inputs(frame, fi)
+            p.oracle.denoise(fi, u)
+            p.cuda.denoise(fi, u)
+            p.cuda.synchronize()
+            assert_all_ok(p.compare(fi), "denoise only, frame %d" % frame)
+    finally:
+        p.close()
+    p = Pair(66, 35)
+    try:
+        for frame in range(4):
+            if frame == 2:
+                p.oracle.reset_history()
+                p.cuda.reset_history()
+            fi, u = p.run_frame(frame)
+            assert_all_ok(p.compare(fi), "reset at 2, frame %d" % frame)
+    finally:
+        p.close()

@@ -69,7 +69,7 @@ denoiser._LIB_PATH = %(lib)r
 from _harness import Pair
 for (W, H, N) in [(34, 10, 4), (66, 35, 5), (130, 49, 4), (4, 3, 2)]:
     p = Pair(W, H, iterations=N)
-    for frame in range(3):
+    for frame in range(2):
         fi, u = p.run_frame(frame)
     u.volumeEnableType, u.volumeScattering = 1, 1500.0
     for side in (p.oracle, p.cuda):
@@ -77,7 +77,7 @@ for (W, H, N) in [(34, 10, 4), (66, 35, 5), (130, 49, 4), (4, 3, 2)]:
     p.cuda.synchronize()
     p.close()
 from test_bandset_gpu import _run
-_run(34, 201, [0, 1, 2], [0, 66, 135, 201], frames=3)
+_run(34, 201, [0, 1, 2], [0, 66, 135, 201], frames=2)
 from hostsim_cases import run_tight_external
 run_tight_external(34, 10)
 run_tight_external(62, 31, extra=1)
