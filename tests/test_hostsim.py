@@ -98,7 +98,7 @@ def test_kernel_addressing_under_address_sanitizer(tmp_path):
     subprocess.run([gxx, "-O1", "-g", "-fsanitize=address,alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off",
                     "-fno-fast-math", "-DASVGF_HOSTSIM", "-Wno-unknown-pragmas", "-I" + HS, "-I" + cuda + "/include", "-shared", "-o", lib,
                     "-include", "cuda_host_shim.h", "-x", "c++", os.path.join(ROOT, "raytracedgl1_b200", "csrc", "asvgf.cu"),
-                    "-x", "c++", os.path.join(HS, "cuda_runtime_stub.cpp"), "-ldl", "-lpthread"], check=True, cwd=HS)
+                    "-x", "c++", os.path.join(HS, "cuda_runtime_stub.cpp"), "-Wl,-Bsymbolic", "-ldl", "-lpthread"], check=True, cwd=HS)
     env = _child_env(LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
     r = subprocess.run([sys.executable, "-c", ASAN_DRIVER % dict(root=ROOT, lib=lib)], cwd=ROOT, env=env, capture_output=True, text=True,
                        timeout=1500)
