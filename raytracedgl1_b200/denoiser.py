@@ -16,6 +16,7 @@ from . import layout
 
 _LIB_PATH = os.environ.get("ASVGF_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libasvgf.so")  # ASVGF_LIB: A/B builds
 _lib = None
+_TEST_ONLY_ALLOW_HOST_BUILD = False  # set by tests/conftest.py in the child pytest of tests/test_hostsim.py, by nothing else
 
 SUCCESS, WRONG_ARGUMENT, CUDA_ERROR, OUT_OF_MEMORY, UNSUPPORTED, NOT_BOUND, HALO_EXCEEDED = range(7)
 CREATE_EXPORT_DEBUG_MASK = 1 << 0
@@ -66,6 +67,10 @@ def lib():
             raise ImportError("libasvgf.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                               "the A-SVGF path has no CPU fallback")
         L = ctypes.CDLL(_LIB_PATH)
+        if hasattr(L, "asvgfHostBuildMarker") and not _TEST_ONLY_ALLOW_HOST_BUILD:
+            # the test suite's g++ build of the library source (tests/hostsim) is a checker, like the oracle: never a way to run the product
+            raise ImportError("%s is the test suite's host build of the library source, not libasvgf.so: the A-SVGF path has no "
+                              "CPU fallback" % _LIB_PATH)
         vp, u32, sz = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_size_t
         pu32 = ctypes.POINTER(u32)
         puni = ctypes.POINTER(layout.GlobalUniform)

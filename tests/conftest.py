@@ -17,6 +17,7 @@ def pytest_configure(config):
         import hostsim
         from raytracedgl1_b200 import denoiser
         denoiser._LIB_PATH = hostsim.build()
+        denoiser._TEST_ONLY_ALLOW_HOST_BUILD = True
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -20,6 +20,9 @@ int deviceCount()
 
 extern "C" {
 
+// what raytracedgl1_b200.denoiser looks for to REFUSE this library outside the test suite (ASVGF_LIB cannot route the product to the CPU)
+int asvgfHostBuildMarker( void ) { return 1; }
+
 cudaError_t cudaGetDeviceCount( int* n ) { *n = deviceCount(); return cudaSuccess; }
 cudaError_t cudaGetDevice( int* d ) { *d = g_device; return cudaSuccess; }
 cudaError_t cudaSetDevice( int d ) { if( d < 0 || d >= deviceCount() ) return cudaErrorInvalidDevice; g_device = d; return cudaSuccess; }

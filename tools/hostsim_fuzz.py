@@ -7,6 +7,7 @@ ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,"tests"))
 from raytracedgl1_b200 import denoiser
 denoiser._LIB_PATH = os.path.join(ROOT, "tests/hostsim/libasvgf_hostsim.so")
+denoiser._TEST_ONLY_ALLOW_HOST_BUILD = True
 from _harness import Pair
 rng=np.random.default_rng(int(sys.argv[1]))
 t_end=time.time()+float(sys.argv[2])

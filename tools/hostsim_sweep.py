@@ -9,6 +9,7 @@ ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,"tests"))
 from raytracedgl1_b200 import denoiser as dn, layout
 dn._LIB_PATH = os.environ.get("HS_LIB", "/tmp/hs/libasvgf_hostsim_asan.so")
+dn._TEST_ONLY_ALLOW_HOST_BUILD = True
 from _harness import Pair, assert_all_ok
 import synth
 
