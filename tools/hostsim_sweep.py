@@ -1,6 +1,6 @@
 """Wider sweeps of the host-compiled library (tests/hostsim, test infrastructure) under AddressSanitizer: run as
     LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 HS_LIB=<sanitizer build> \
-        python tools/hostsim_sweep.py tight|chain|band
+        python tools/hostsim_sweep.py tight|chain|band|tsan
 (the sanitizer build: the g++ line of tests/test_hostsim.py::test_kernel_addressing_under_address_sanitizer).
 Results of the last run: profiles/r02_hostsim_memcheck.md."""
 import os, sys, ctypes
@@ -71,3 +71,12 @@ if what=="chain":
 if what=="band":
     band_handle(34,300,99,201,66,True); band_handle(34,300,0,99,66,True); band_handle(34,300,201,300,66,True)
     band_handle(34,301,201,301,66,True); band_handle(34,100,33,66,9,False); band_handle(66,100,0,33,12,False); band_handle(66,100,66,100,30,False)
+if what=="tsan":      # racecheck: HS_LIB = a -fsanitize=thread build, LD_PRELOAD = libtsan.so (profiles/r02_hostsim_memcheck.md)
+    for (W,H,N) in [(130,20,4),(66,40,6)]:
+        d=dn.Denoiser(W,H,N,flags=dn.CREATE_EXPORT_DEBUG_MASK)
+        for frame in range(2):
+            fi=frame&1; g=synth.generate(W,H,frame); u=synth.uniform(W,H,frame)
+            for name,arr in g.items(): d.upload(name,fi,arr)
+            d.gradient_samples(fi,u); d.denoise(fi,u); d.synchronize()
+        d.calculate_exposure(fi,u); d.resolve_checkerboard(fi,u); d.synchronize()
+        d.close(); print("tsan run",W,H,N,"done",flush=True)
