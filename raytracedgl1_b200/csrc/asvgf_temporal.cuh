@@ -56,13 +56,13 @@ template< bool UNIFORM, bool BAND >
 ASVGF_DEVICE uint32_t consistency2x2( const TemporalArgs& a, const Rows& rows, uint32_t pitchT, int bx, int by, int ax0, int ax1, int H, float depth, float motionZ,
                                       float3 normal, uint32_t encN, uint32_t& off00 )
 {
-    off00 = ( uint32_t )( by * ( int )pitchT + bx );
+    off00 = ( uint32_t )by * pitchT + ( uint32_t )bx; // (unsigned: a saturated tap coordinate wraps instead of overflowing; such a tap is never loaded)
     uint32_t dz[ 4 ], en[ 4 ];
     bool     in[ 4 ];
 #pragma unroll
     for( int t = 0; t < 4; t++ )
     {
-        const int x = bx + ( t & 1 ), y = by + ( t >> 1 );
+        const int x = ( int )( ( uint32_t )bx + ( t & 1 ) ), y = ( int )( ( uint32_t )by + ( t >> 1 ) ); // (INT_MAX + 1 wraps to INT_MIN: still outside)
         in[ t ] = y >= 0 && y < H && x >= ax0 && x < ax1 && y >= rows.y0 && y < rows.y1;
         if( BAND && !in[ t ] && y >= 0 && y < H && x >= ax0 && x < ax1 ) atomicOr( a.haloMiss, 1u ); // a tap of the frame this band does not hold
         const uint32_t o = off00 + ( t & 1 ) + ( t >> 1 ) * pitchT;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__( kBlockW* kTBlockH, ASVGF_T_MIN_CTAS ) k_tempo
 #pragma unroll
     for( int t = 0; t < 4; t++ )
     {
-        const int      x = pixPrevX + ( t & 1 ), y = pixPrevY + ( t >> 1 );
+        const int      x = ( int )( ( uint32_t )pixPrevX + ( t & 1 ) ), y = ( int )( ( uint32_t )pixPrevY + ( t >> 1 ) );
         const uint32_t ot = o00 + ( t & 1 ) + ( t >> 1 ) * pitchT;
         const bool     ok = ( mask >> t ) & 1u;
         hDiff[ t ] = ldOff< UNIFORM, uint2 >( a.diffHistory, ot, x, y, ok, make_uint2( 0u, 0u ) );
