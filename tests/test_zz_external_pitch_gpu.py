@@ -2,8 +2,8 @@
  -- instead of the library's align256(width) texels per row: selects the UNIFORM = false forms of the
 temporal and a-trous kernels (one offset per image instead of one shared texel offset).  Gate: every image bit-identical to the
 owned-image handle.  Written in the last session of round 2 from tests/hostsim_cases.py::test_tight_and_unequal_external_pitches,
-which passes on the host build (addresses and vector alignment checked there under the sanitizers); this file is collected last
-because its first run on a GPU is the round-end run."""
+which passes on the host build (addresses and vector alignment checked there under the sanitizers); passed on a B200 with the
+round's last GPU seconds (profiles/r02_final_gpu_check_b.log)."""
 import ctypes
 
 import numpy as np
